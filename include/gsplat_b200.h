@@ -1,0 +1,183 @@
+/*
+ * gsplat_b200.h -- C ABI of libgsplat_b200.so: the B200-native (sm_100a) replacement for the
+ * Taichi/CUB kernels on taichi-splatting's render hot path.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one device-code unit
+ * the reference's Python operators launch; the reference-side binding is in INTEGRATION.md.
+ * Paths below are relative to the reference tree (uc-vision/taichi-splatting v0.32.0).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host` (pinned host memory);
+ *  - tensors are dense row-major with the reference's layouts; the library never allocates or
+ *    frees caller-visible memory: outputs and workspaces are caller-owned (CUB-style size query);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *    the device; the only host-visible results (V, K) are written asynchronously into pinned
+ *    host words the caller reads after synchronising that stream;
+ *  - every function returns 0 on success or a negative GS_ERR_* code; gs_last_error_string()
+ *    gives the thread-local message (reference convention: Python assert / RuntimeError,
+ *    mapper/tile_mapper.py:177-178, cuda_lib/radix_sort_pairs.cu:66);
+ *  - `_f32` / `_f64`: the reference instantiates every operator for both (taichi_lib/__init__.py:8-14);
+ *    the tile mapper is f32 only (mapper/tile_mapper.py:14).
+ */
+#ifndef GSPLAT_B200_H
+#define GSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_OK 0
+#define GS_ERR_INVALID_ARGUMENT (-1)
+#define GS_ERR_UNSUPPORTED (-2)
+#define GS_ERR_CUDA (-3)
+#define GS_ERR_WORKSPACE_TOO_SMALL (-4)
+
+/* Mirrors RasterConfig (data_types.py:16-46): compile-time constants of the Taichi kernels. */
+typedef struct gs_raster_config {
+  int32_t tile_size;               /* 8, 16 or 32 (fast path: 16) */
+  int32_t pixel_stride_x;          /* accepted for API parity; thread mapping is the library's own */
+  int32_t pixel_stride_y;
+  int32_t antialias;               /* generic.py:340-404 */
+  int32_t use_alpha_blending;      /* 0: quantile (median-depth) mode, forward.py:107-112 */
+  int32_t compute_visibility;      /* forward.py:114-126 */
+  int32_t compute_point_heuristic; /* backward.py:190-194 */
+  int32_t reserved;
+  double clamp_max_alpha;          /* 0.99 */
+  double alpha_threshold;          /* 1/255 */
+  double saturate_threshold;       /* 0.9999 (backward stop; forward quantile threshold) */
+  double forward_saturate_eps;     /* forward early-out when 1-total_weight <= eps; 0 = never
+                                      (the reference forward never stops early: SURVEY D2) */
+} gs_raster_config;
+
+int gs_version(void);
+const char *gs_last_error_string(void);
+
+/* ---- R1: projection + cull + order-preserving compaction --------------------------------------
+ * replaces project_kernel + torch.nonzero + 2 gathers (perspective/projection.py:32-81,125-163).
+ * Two calls around the one unavoidable host read of V (the reference syncs in torch.nonzero):
+ *   gs_project_cull_*   : per-Gaussian in-view flag -> exclusive scan -> *num_visible_host
+ *   gs_project_write_*  : recompute and write compacted points (V,7), depth (V,1), indexes (V) i64,
+ *                         and optionally ndc depth (V,1) (torch_lib/projection.py:120-123, R11)
+ * T_camera_world: 16 values row-major (4,4); projection: [fx,fy,cx,cy].                        */
+int gs_project_workspace_bytes(int64_t n, size_t *bytes);
+int gs_project_cull_f32(const float *position, const float *log_scaling, const float *rotation,
+                        const float *alpha_logit, const float *T_camera_world, const float *projection,
+                        int64_t n, int32_t width, int32_t height, double near_plane, double far_plane,
+                        double blur_cov, double clamp_margin, double alpha_threshold,
+                        void *workspace, size_t workspace_bytes, int32_t *num_visible_host, void *stream);
+int gs_project_write_f32(const float *position, const float *log_scaling, const float *rotation,
+                         const float *alpha_logit, const float *T_camera_world, const float *projection,
+                         int64_t n, int32_t width, int32_t height, double near_plane, double far_plane,
+                         double blur_cov, double clamp_margin, const void *workspace,
+                         float *points, float *depth, int64_t *indexes, float *ndc_depth /* may be NULL */,
+                         void *stream);
+int gs_project_cull_f64(const double *position, const double *log_scaling, const double *rotation,
+                        const double *alpha_logit, const double *T_camera_world, const double *projection,
+                        int64_t n, int32_t width, int32_t height, double near_plane, double far_plane,
+                        double blur_cov, double clamp_margin, double alpha_threshold,
+                        void *workspace, size_t workspace_bytes, int32_t *num_visible_host, void *stream);
+int gs_project_write_f64(const double *position, const double *log_scaling, const double *rotation,
+                         const double *alpha_logit, const double *T_camera_world, const double *projection,
+                         int64_t n, int32_t width, int32_t height, double near_plane, double far_plane,
+                         double blur_cov, double clamp_margin, const void *workspace,
+                         double *points, double *depth, int64_t *indexes, double *ndc_depth,
+                         void *stream);
+
+/* ---- R1b: projection backward ------------------------------------------------------------------
+ * replaces indexed_project_kernel.grad (Taichi autodiff; perspective/projection.py:84-119,165-188).
+ * Hand-derived reverse chain.  All grad outputs must be zero-initialised by
+ * the caller; d_T_camera_world is (4,4) (rows 0-2 written), d_projection is (4).               */
+int gs_project_bwd_f32(const float *position, const float *log_scaling, const float *rotation,
+                       const float *alpha_logit, const float *T_camera_world, const float *projection,
+                       const int64_t *indexes, int64_t v, int32_t width, int32_t height,
+                       double blur_cov, double clamp_margin, const float *d_points, const float *d_depth,
+                       float *d_position, float *d_log_scaling, float *d_rotation, float *d_alpha_logit,
+                       float *d_T_camera_world, float *d_projection, void *stream);
+int gs_project_bwd_f64(const double *position, const double *log_scaling, const double *rotation,
+                       const double *alpha_logit, const double *T_camera_world, const double *projection,
+                       const int64_t *indexes, int64_t v, int32_t width, int32_t height,
+                       double blur_cov, double clamp_margin, const double *d_points, const double *d_depth,
+                       double *d_position, double *d_log_scaling, double *d_rotation, double *d_alpha_logit,
+                       double *d_T_camera_world, double *d_projection, void *stream);
+
+/* ---- R2: spherical harmonics at gathered indexes ----------------------------------------------
+ * replaces evaluate_sh_at_kernel (+ .grad) (indexed_spherical_harmonics.py:118-134,152-160).
+ * params (M,C,D), D=(degree+1)^2, degree 0..3; out (V,C) = clamp(Y(dir).params + 0.5, 0, 1).
+ * Backward accumulates (atomic) into zero-initialised d_params (M,C,D), d_positions (M,3),
+ * d_camera_pos (3); any of the three may be NULL.  unique_indexes!=0 promises no index repeats
+ * (true for the renderer's visible set) and enables plain vector stores into d_params.        */
+int gs_sh_fwd_f32(const float *params, const float *positions, const int64_t *indexes,
+                  const float *camera_pos, int64_t v, int32_t channels, int32_t degree, float *out,
+                  void *stream);
+int gs_sh_bwd_f32(const float *params, const float *positions, const int64_t *indexes,
+                  const float *camera_pos, const float *d_out, int64_t v, int32_t channels, int32_t degree,
+                  int32_t unique_indexes, float *d_params, float *d_positions, float *d_camera_pos,
+                  void *stream);
+int gs_sh_fwd_f64(const double *params, const double *positions, const int64_t *indexes,
+                  const double *camera_pos, int64_t v, int32_t channels, int32_t degree, double *out,
+                  void *stream);
+int gs_sh_bwd_f64(const double *params, const double *positions, const int64_t *indexes,
+                  const double *camera_pos, const double *d_out, int64_t v, int32_t channels, int32_t degree,
+                  int32_t unique_indexes, double *d_params, double *d_positions, double *d_camera_pos,
+                  void *stream);
+
+/* ---- R3-R7: tile mapper -------------------------------------------------------------------------
+ * gs_tile_count      replaces tile_overlaps_kernel (mapper/tile_mapper.py:75-86, grid_query.py:46-93)
+ * gs_tile_scan       replaces cuda_lib.full_cumsum (cuda_lib/full_cumsum.cu:16-47): cum (V+1) i32,
+ *                    total K written asynchronously to *total_host (no device-wide sync, D11)
+ * gs_tile_emit_keys  replaces generate_sort_keys_kernel (mapper/tile_mapper.py:35-66,114-146)
+ * gs_sort_pairs      replaces cuda_lib.radix_sort_pairs (cuda_lib/radix_sort_pairs.cu:7-70):
+ *                    stable LSD radix sort of (key, i32 value) on bits [begin_bit,end_bit)
+ * gs_tile_ranges     replaces find_ranges_kernel (mapper/tile_mapper.py:92-112); zero-fills ranges
+ * width_padded/height_padded: image size rounded up to the tile size (pad_to_tile, :20-24).    */
+int gs_tile_count(const float *gaussians, int64_t v, int32_t width_padded, int32_t height_padded,
+                  int32_t tile_size, double alpha_threshold, int32_t *counts, void *stream);
+int gs_tile_scan_workspace_bytes(int64_t v, size_t *bytes);
+int gs_tile_scan(const int32_t *counts, int64_t v, int32_t *cum /* (v+1) */, void *workspace,
+                 size_t workspace_bytes, int32_t *total_host, void *stream);
+int gs_tile_emit_keys(const float *gaussians, const float *depths, const int32_t *cum, int64_t v,
+                      int32_t width_padded, int32_t height_padded, int32_t tile_size,
+                      double alpha_threshold, int32_t use_depth16, void *keys /* u64 | u32 */,
+                      int32_t *overlap_to_point, void *stream);
+int gs_sort_pairs_workspace_bytes(int64_t k, int32_t key_bytes, size_t *bytes);
+int gs_sort_pairs(const void *keys_in, const int32_t *values_in, void *keys_out, int32_t *values_out,
+                  int64_t k, int32_t key_bytes /* 4 | 8 */, int32_t begin_bit, int32_t end_bit,
+                  void *workspace, size_t workspace_bytes, void *stream);
+int gs_tile_ranges(const void *sorted_keys, int64_t k, int32_t key_bytes, int32_t *tile_ranges /* (T,2) */,
+                   int64_t num_tiles, void *stream);
+
+/* ---- R8: rasteriser forward ---------------------------------------------------------------------
+ * replaces _forward_kernel (rasterizer/forward.py:22-135).  image (H,W,F), image_alpha (H,W),
+ * visibility (V) zero-initialised by the caller (NULL unless compute_visibility).            */
+int gs_raster_fwd_f32(const float *points, const float *features, const int32_t *tile_ranges,
+                      const int32_t *overlap_to_point, int64_t v, int64_t k, int32_t width, int32_t height,
+                      int32_t num_features, const gs_raster_config *config, float *image,
+                      float *image_alpha, float *visibility, void *stream);
+int gs_raster_fwd_f64(const double *points, const double *features, const int32_t *tile_ranges,
+                      const int32_t *overlap_to_point, int64_t v, int64_t k, int32_t width, int32_t height,
+                      int32_t num_features, const gs_raster_config *config, double *image,
+                      double *image_alpha, double *visibility, void *stream);
+
+/* ---- R9: rasteriser backward --------------------------------------------------------------------
+ * replaces _backward_kernel (rasterizer/backward.py:50-225).  grad_points (V,7) / grad_features
+ * (V,F) zero-initialised by the caller, NULL when the input does not require grad
+ * (points_requires_grad / features_requires_grad, backward.py:12-17); point_heuristic (V,2)
+ * accumulates in place (rasterizer/function.py:52-55,92), NULL unless compute_point_heuristic. */
+int gs_raster_bwd_f32(const float *points, const float *features, const int32_t *tile_ranges,
+                      const int32_t *overlap_to_point, const float *image, const float *grad_image,
+                      int64_t v, int64_t k, int32_t width, int32_t height, int32_t num_features,
+                      const gs_raster_config *config, float *grad_points, float *grad_features,
+                      float *point_heuristic, void *stream);
+int gs_raster_bwd_f64(const double *points, const double *features, const int32_t *tile_ranges,
+                      const int32_t *overlap_to_point, const double *image, const double *grad_image,
+                      int64_t v, int64_t k, int32_t width, int32_t height, int32_t num_features,
+                      const gs_raster_config *config, double *grad_points, double *grad_features,
+                      double *point_heuristic, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H */

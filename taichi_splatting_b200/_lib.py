@@ -1,0 +1,145 @@
+"""ctypes binding of libgsplat_b200.so (C ABI in include/gsplat_b200.h).
+
+The CUDA library IS the product: there is no CPU or pure-torch fallback.  Importing this module without
+the built library raises; calling an operator with non-CUDA tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_double, c_int32, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libgsplat_b200.so"
+
+P, I32, I64, D, SZ = c_void_p, c_int32, c_int64, c_double, c_size_t
+
+
+class RasterConfigC(ctypes.Structure):
+  """struct gs_raster_config"""
+  _fields_ = [
+      ("tile_size", c_int32), ("pixel_stride_x", c_int32), ("pixel_stride_y", c_int32),
+      ("antialias", c_int32), ("use_alpha_blending", c_int32), ("compute_visibility", c_int32),
+      ("compute_point_heuristic", c_int32), ("reserved", c_int32),
+      ("clamp_max_alpha", c_double), ("alpha_threshold", c_double), ("saturate_threshold", c_double),
+      ("forward_saturate_eps", c_double),
+  ]
+
+
+_PROJECT_CULL = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, D, P, SZ, P, P]
+_PROJECT_WRITE = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, P, P, P, P, P, P]
+_PROJECT_BWD = [P, P, P, P, P, P, P, I64, I32, I32, D, D, P, P, P, P, P, P, P, P, P]
+_SH_FWD = [P, P, P, P, I64, I32, I32, P, P]
+_SH_BWD = [P, P, P, P, P, I64, I32, I32, I32, P, P, P, P]
+_RASTER_FWD = [P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P]
+_RASTER_BWD = [P, P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P]
+
+SIGNATURES = {
+    "gs_version": ([], c_int32),
+    "gs_last_error_string": ([], ctypes.c_char_p),
+    "gs_project_workspace_bytes": ([I64, POINTER(SZ)], c_int32),
+    "gs_project_cull_f32": (_PROJECT_CULL, c_int32), "gs_project_cull_f64": (_PROJECT_CULL, c_int32),
+    "gs_project_write_f32": (_PROJECT_WRITE, c_int32), "gs_project_write_f64": (_PROJECT_WRITE, c_int32),
+    "gs_project_bwd_f32": (_PROJECT_BWD, c_int32), "gs_project_bwd_f64": (_PROJECT_BWD, c_int32),
+    "gs_sh_fwd_f32": (_SH_FWD, c_int32), "gs_sh_fwd_f64": (_SH_FWD, c_int32),
+    "gs_sh_bwd_f32": (_SH_BWD, c_int32), "gs_sh_bwd_f64": (_SH_BWD, c_int32),
+    "gs_tile_count": ([P, I64, I32, I32, I32, D, P, P], c_int32),
+    "gs_tile_scan_workspace_bytes": ([I64, POINTER(SZ)], c_int32),
+    "gs_tile_scan": ([P, I64, P, P, SZ, P, P], c_int32),
+    "gs_tile_emit_keys": ([P, P, P, I64, I32, I32, I32, D, I32, P, P, P], c_int32),
+    "gs_sort_pairs_workspace_bytes": ([I64, I32, POINTER(SZ)], c_int32),
+    "gs_sort_pairs": ([P, P, P, P, I64, I32, I32, I32, P, SZ, P], c_int32),
+    "gs_tile_ranges": ([P, I64, I32, P, I64, P], c_int32),
+    "gs_raster_fwd_f32": (_RASTER_FWD, c_int32), "gs_raster_fwd_f64": (_RASTER_FWD, c_int32),
+    "gs_raster_bwd_f32": (_RASTER_BWD, c_int32), "gs_raster_bwd_f64": (_RASTER_BWD, c_int32),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+  """Loads the library (never builds it: run `python -m taichi_splatting_b200.build` / __graft_entry__.build())."""
+  global _lib
+  if _lib is None:
+    if not LIB_PATH.exists():
+      raise RuntimeError(
+          f"{LIB_PATH} is missing: the CUDA extension is the only implementation of this package "
+          "(no CPU fallback). Build it with `python -m taichi_splatting_b200.build`.")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (argtypes, restype) in SIGNATURES.items():
+      fn = getattr(lib, name)
+      fn.argtypes = argtypes
+      fn.restype = restype
+    _lib = lib
+  return _lib
+
+
+def check(code: int, what: str) -> None:
+  if code != 0:
+    msg = load().gs_last_error_string().decode()
+    if code == -1:
+      raise ValueError(f"{what}: {msg}")
+    if code == -2:
+      raise NotImplementedError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: {msg} (code {code})")
+
+
+def call(name: str, *args) -> None:
+  check(getattr(load(), name)(*args), name)
+
+
+def suffix(dtype: torch.dtype) -> str:
+  if dtype == torch.float32:
+    return "f32"
+  if dtype == torch.float64:
+    return "f64"
+  raise NotImplementedError(f"dtype {dtype} not supported (float32, float64)")
+
+
+def require_cuda(**tensors) -> None:
+  """Reference convention: `assert arg.is_cuda` (cuda_lib/__init__.py:12-13).  There is no CPU path."""
+  for name, t in tensors.items():
+    assert t.is_cuda, f"{name}: device must be a CUDA device, got {t.device} (this package has no CPU path)"
+
+
+def ptr(t) -> int | None:
+  """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+  if t is None:
+    return None
+  assert t.is_cuda, f"expected a CUDA tensor, got device {t.device} (this package has no CPU path)"
+  assert t.is_contiguous(), "expected a contiguous tensor"
+  return t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+  return torch.cuda.current_stream(device).cuda_stream
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+  return torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=device)
+
+
+_host_words = {}
+
+
+def host_word(device) -> torch.Tensor:
+  """A pinned int32 word per device for the asynchronous V / K read-backs."""
+  key = (device.type, device.index)
+  if key not in _host_words:
+    _host_words[key] = torch.zeros((1,), dtype=torch.int32).pin_memory()
+  return _host_words[key]
+
+
+def read_host_word(word: torch.Tensor, device) -> int:
+  torch.cuda.current_stream(device).synchronize()
+  return int(word.item())
+
+
+def raster_config_c(config, forward_saturate_eps=None) -> RasterConfigC:
+  eps = getattr(config, "forward_saturate_eps", 0.0) if forward_saturate_eps is None else forward_saturate_eps
+  return RasterConfigC(
+      int(config.tile_size), int(config.pixel_stride[0]), int(config.pixel_stride[1]), int(config.antialias),
+      int(config.use_alpha_blending), int(config.compute_visibility), int(config.compute_point_heuristic), 0,
+      float(config.clamp_max_alpha), float(config.alpha_threshold), float(config.saturate_threshold), float(eps))

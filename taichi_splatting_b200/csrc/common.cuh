@@ -1,0 +1,72 @@
+// common.cuh -- shared helpers for libgsplat_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gsplat_b200.h"
+
+namespace gs {
+
+void set_error(const char *fmt, ...);
+
+#define GS_CHECK_ARG(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      gs::set_error(__VA_ARGS__);               \
+      return GS_ERR_INVALID_ARGUMENT;           \
+    }                                           \
+  } while (0)
+
+#define GS_CUDA(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      gs::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                    __LINE__);                                                         \
+      return GS_ERR_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+#define GS_LAUNCH_CHECK()                                                              \
+  do {                                                                                 \
+    cudaError_t _e = cudaPeekAtLastError();                                            \
+    if (_e != cudaSuccess) {                                                           \
+      gs::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),        \
+                    __FILE__, __LINE__);                                               \
+      return GS_ERR_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename real> struct math;
+template <> struct math<float> {
+  static __device__ __forceinline__ float exp(float x) { return ::expf(x); }
+  static __device__ __forceinline__ float fast_exp(float x) { return ::__expf(x); }
+  static __device__ __forceinline__ float log(float x) { return ::logf(x); }
+  static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
+  static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
+  static __device__ __forceinline__ float min(float a, float b) { return ::fminf(a, b); }
+  static __device__ __forceinline__ float max(float a, float b) { return ::fmaxf(a, b); }
+};
+template <> struct math<double> {
+  static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+  static __device__ __forceinline__ double fast_exp(double x) { return ::exp(x); }
+  static __device__ __forceinline__ double log(double x) { return ::log(x); }
+  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+  static __device__ __forceinline__ double min(double a, double b) { return ::fmin(a, b); }
+  static __device__ __forceinline__ double max(double a, double b) { return ::fmax(a, b); }
+};
+
+// Warp covers 8x4 pixels (same decomposition as rasterizer/tiling.py:34-51 with stride 1).
+__device__ __forceinline__ void tile_pixel(int tid, int tile_size, int &u, int &v) {
+  int warp_id = tid >> 5, lane = tid & 31;
+  int warps_wide = tile_size >> 3;
+  u = (warp_id % warps_wide) * 8 + (lane & 7);
+  v = (warp_id / warps_wide) * 4 + (lane >> 3);
+}
+
+}  // namespace gs

@@ -1,0 +1,243 @@
+// mapper.cu -- R3..R7: per-tile overlap binning, scan, (tile|depth) keys, radix sort, tile ranges.
+//
+// Semantics: taichi_lib/grid_query.py:9-93 (OBB-vs-tile query), mapper/tile_mapper.py:35-146 (keys, ranges),
+// cuda_lib/full_cumsum.cu, cuda_lib/radix_sort_pairs.cu (CUB scan / onesweep radix sort).
+// Integer outputs must be bit-exact against the CPU oracle, so the OBB query uses explicitly rounded
+// fp32 ops (__fmul_rn/__fadd_rn: no FMA contraction), IEEE sqrt/div, and a correctly rounded fp32 log
+// obtained through fp64 -- the same recipe as oracle/gs_oracle.c.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace gs {
+
+struct ObbQuery {
+  float inv00, inv01, inv10, inv11;
+  float relx, rely;
+  int minx, miny, spanx, spany;
+};
+
+__device__ __forceinline__ ObbQuery obb_grid_query(const float *__restrict__ g, int w_pad, int h_pad, int ts,
+                                                   float thr) {
+  ObbQuery q;
+  q.spanx = q.spany = 0; q.minx = q.miny = 0;
+  q.inv00 = q.inv01 = q.inv10 = q.inv11 = q.relx = q.rely = 0.f;
+  float mx = g[0], my = g[1], ax = g[2], ay = g[3], sx = g[4], sy = g[5], alpha = g[6];
+  if (!(alpha > thr)) return q;  // D18
+  float gscale = __fsqrt_rn(__fmul_rn(2.0f, (float)log((double)__fdiv_rn(alpha, thr))));
+  float scx = __fmul_rn(sx, gscale), scy = __fmul_rn(sy, gscale);
+  float a2x = -ay, a2y = ax;
+  float v1x = __fmul_rn(ax, scx), v1y = __fmul_rn(ay, scx), v2x = __fmul_rn(a2x, scy), v2y = __fmul_rn(a2y, scy);
+  float ex = __fsqrt_rn(__fadd_rn(__fmul_rn(v1x, v1x), __fmul_rn(v2x, v2x)));
+  float ey = __fsqrt_rn(__fadd_rn(__fmul_rn(v1y, v1y), __fmul_rn(v2y, v2y)));
+  float lox = __fsub_rn(mx, ex), loy = __fsub_rn(my, ey), hix = __fadd_rn(mx, ex), hiy = __fadd_rn(my, ey);
+  q.inv00 = __fdiv_rn(ax, scx); q.inv01 = __fdiv_rn(ay, scx);
+  q.inv10 = __fdiv_rn(a2x, scy); q.inv11 = __fdiv_rn(a2y, scy);
+  float fts = (float)ts;
+  int max_tx = (w_pad - 1) / ts, max_ty = (h_pad - 1) / ts;
+  float flx = floorf(__fdiv_rn(lox, fts)), fly = floorf(__fdiv_rn(loy, fts));
+  float chx = ceilf(__fdiv_rn(hix, fts)), chy = ceilf(__fdiv_rn(hiy, fts));
+  const float BIG = 1.0e9f;
+  if (!(flx > -BIG && flx < BIG && fly > -BIG && fly < BIG && chx > -BIG && chx < BIG && chy > -BIG && chy < BIG))
+    return q;
+  int min_tx = max((int)flx, 0), min_ty = max((int)fly, 0);
+  int max_bx = min(max((int)chx, min_tx + 1), max_tx + 1);
+  int max_by = min(max((int)chy, min_ty + 1), max_ty + 1);
+  q.minx = min_tx; q.miny = min_ty;
+  q.spanx = max_bx - min_tx; q.spany = max_by - min_ty;
+  q.relx = __fsub_rn((float)(min_tx * ts), mx);
+  q.rely = __fsub_rn((float)(min_ty * ts), my);
+  return q;
+}
+
+__device__ __forceinline__ bool test_tile(const ObbQuery &q, int u, int v, int ts) {
+  float lx = __fadd_rn(q.relx, (float)(u * ts)), ly = __fadd_rn(q.rely, (float)(v * ts));
+  float ux = __fadd_rn(lx, (float)ts), uy = __fadd_rn(ly, (float)ts);
+  // axis 0
+  float a0 = __fmul_rn(q.inv00, lx), a1 = __fmul_rn(q.inv00, ux);
+  float b0 = __fmul_rn(q.inv01, ly), b1 = __fmul_rn(q.inv01, uy);
+  float p0 = __fadd_rn(a0, b0), p1 = __fadd_rn(a1, b0), p2 = __fadd_rn(a1, b1), p3 = __fadd_rn(a0, b1);
+  float mn = fminf(fminf(p0, p1), fminf(p2, p3)), mxv = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+  if (mn > 1.0f || mxv < -1.0f) return false;
+  // axis 1
+  a0 = __fmul_rn(q.inv10, lx); a1 = __fmul_rn(q.inv10, ux);
+  b0 = __fmul_rn(q.inv11, ly); b1 = __fmul_rn(q.inv11, uy);
+  p0 = __fadd_rn(a0, b0); p1 = __fadd_rn(a1, b0); p2 = __fadd_rn(a1, b1); p3 = __fadd_rn(a0, b1);
+  mn = fminf(fminf(p0, p1), fminf(p2, p3)); mxv = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+  return !(mn > 1.0f || mxv < -1.0f);
+}
+
+__global__ void __launch_bounds__(128)
+tile_count_kernel(const float *__restrict__ gaussians, int64_t v, int w_pad, int h_pad, int ts, float thr,
+                  int32_t *__restrict__ counts) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= v) return;
+  ObbQuery q = obb_grid_query(gaussians + 7 * i, w_pad, h_pad, ts, thr);
+  int c = 0;
+  for (int u = 0; u < q.spanx; ++u)
+    for (int w = 0; w < q.spany; ++w) c += test_tile(q, u, w, ts) ? 1 : 0;
+  counts[i] = c;
+}
+
+template <typename key_t, bool DEPTH16>
+__global__ void __launch_bounds__(128)
+tile_emit_kernel(const float *__restrict__ gaussians, const float *__restrict__ depths,
+                 const int32_t *__restrict__ cum, int64_t v, int w_pad, int h_pad, int ts, float thr,
+                 key_t *__restrict__ keys, int32_t *__restrict__ overlap_to_point) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= v) return;
+  ObbQuery q = obb_grid_query(gaussians + 7 * i, w_pad, h_pad, ts, thr);
+  int tiles_wide = w_pad / ts;
+  int64_t k = cum[i];
+  float depth = depths[i];
+  uint32_t dbits;
+  if (DEPTH16) {
+    float c = fminf(fmaxf(depth, 0.0f), 1.0f);
+    dbits = (uint32_t)__fmul_rn(c, 65535.0f);
+  } else {
+    dbits = __float_as_uint(depth);
+  }
+  for (int u = 0; u < q.spanx; ++u)
+    for (int w = 0; w < q.spany; ++w)
+      if (test_tile(q, u, w, ts)) {
+        key_t tile_id = (key_t)((q.minx + u) + (q.miny + w) * tiles_wide);
+        keys[k] = DEPTH16 ? (key_t)((tile_id << 16) | dbits) : (key_t)((tile_id << (sizeof(key_t) * 4)) | dbits);
+        overlap_to_point[k] = (int32_t)i;
+        ++k;
+      }
+}
+
+__global__ void finish_scan_kernel(const int32_t *__restrict__ counts, int32_t *__restrict__ cum, int64_t v,
+                                   int32_t *__restrict__ total_dev) {
+  // cum[0..v-1] holds the exclusive scan; complete entry v (cuda_lib/full_cumsum.cu:6-10)
+  int32_t t = cum[v - 1] + counts[v - 1];
+  cum[v] = t;
+  *total_dev = t;
+}
+
+template <typename key_t>
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(const key_t *__restrict__ keys, int64_t k, int shift, int32_t *__restrict__ ranges) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= k) return;
+  const int max_tile = 65535;
+  int tile_id = (int)(keys[idx] >> shift);
+  int next_tile_id = max_tile;
+  if (idx + 1 < k) next_tile_id = (int)(keys[idx + 1] >> shift);
+  if (tile_id != next_tile_id) {
+    ranges[2 * tile_id + 1] = (int32_t)(idx + 1);
+    if (next_tile_id < max_tile) ranges[2 * next_tile_id] = (int32_t)(idx + 1);
+  }
+}
+
+}  // namespace gs
+
+extern "C" int gs_tile_count(const float *gaussians, int64_t v, int32_t w_pad, int32_t h_pad, int32_t ts,
+                             double alpha_threshold, int32_t *counts, void *stream) {
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_count: image %dx%d not padded to tile %d", w_pad, h_pad, ts);
+  GS_CHECK_ARG((int64_t)(w_pad / ts) * (h_pad / ts) < 65535, "tile dimensions (%d, %d) exceed maximum tile count (16 bit id), try increasing tile_size", h_pad / ts, w_pad / ts);
+  if (v == 0) return GS_OK;
+  gs::tile_count_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
+      gaussians, v, w_pad, h_pad, ts, (float)alpha_threshold, counts);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_tile_scan_workspace_bytes(int64_t v, size_t *bytes) {
+  size_t temp = 0;
+  if (v > 0) cub::DeviceScan::ExclusiveSum(nullptr, temp, (const int32_t *)nullptr, (int32_t *)nullptr, (int)v);
+  *bytes = gs::align_up(temp, 256) + 256;
+  return GS_OK;
+}
+
+extern "C" int gs_tile_scan(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
+                            int32_t *total_host, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CHECK_ARG(total_host != nullptr, "tile_scan: total_host is NULL");
+  GS_CHECK_ARG(v >= 0 && v < (int64_t(1) << 31), "tile_scan: v out of range");
+  if (v == 0) {
+    GS_CUDA(cudaMemsetAsync(cum, 0, sizeof(int32_t), stream));
+    *total_host = 0;
+    return GS_OK;
+  }
+  size_t need = 0;
+  gs_tile_scan_workspace_bytes(v, &need);
+  if (workspace_bytes < need) {
+    gs::set_error("tile_scan: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return GS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  int32_t *total_dev = (int32_t *)workspace;
+  void *temp = (char *)workspace + 256;
+  size_t temp_bytes = workspace_bytes - 256;
+  GS_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, cum, (int)v, stream));
+  gs::finish_scan_kernel<<<1, 1, 0, stream>>>(counts, cum, v, total_dev);
+  GS_LAUNCH_CHECK();
+  GS_CUDA(cudaMemcpyAsync(total_host, total_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  return GS_OK;
+}
+
+extern "C" int gs_tile_emit_keys(const float *gaussians, const float *depths, const int32_t *cum, int64_t v,
+                                 int32_t w_pad, int32_t h_pad, int32_t ts, double alpha_threshold,
+                                 int32_t use_depth16, void *keys, int32_t *overlap_to_point, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_emit_keys: image not padded to tile size");
+  if (v == 0) return GS_OK;
+  unsigned grid = (unsigned)gs::ceil_div(v, 128);
+  if (use_depth16)
+    gs::tile_emit_kernel<uint32_t, true><<<grid, 128, 0, stream>>>(gaussians, depths, cum, v, w_pad, h_pad, ts,
+                                                                   (float)alpha_threshold, (uint32_t *)keys, overlap_to_point);
+  else
+    gs::tile_emit_kernel<uint64_t, false><<<grid, 128, 0, stream>>>(gaussians, depths, cum, v, w_pad, h_pad, ts,
+                                                                    (float)alpha_threshold, (uint64_t *)keys, overlap_to_point);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_sort_pairs_workspace_bytes(int64_t k, int32_t key_bytes, size_t *bytes) {
+  size_t temp = 0;
+  if (k > 0) {
+    if (key_bytes == 8)
+      cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                      (const int32_t *)nullptr, (int32_t *)nullptr, (int)k);
+    else
+      cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                      (const int32_t *)nullptr, (int32_t *)nullptr, (int)k);
+  }
+  *bytes = gs::align_up(temp, 256) + 256;
+  return GS_OK;
+}
+
+extern "C" int gs_sort_pairs(const void *keys_in, const int32_t *values_in, void *keys_out, int32_t *values_out,
+                             int64_t k, int32_t key_bytes, int32_t begin_bit, int32_t end_bit, void *workspace,
+                             size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CHECK_ARG(key_bytes == 4 || key_bytes == 8, "sort_pairs: key_bytes must be 4 or 8 (got %d)", key_bytes);
+  GS_CHECK_ARG(k >= 0 && k < (int64_t(1) << 31), "sort_pairs: k out of range");
+  if (end_bit <= 0) end_bit = key_bytes * 8;  // radix_sort_pairs.cu:14
+  GS_CHECK_ARG(begin_bit >= 0 && begin_bit < end_bit && end_bit <= key_bytes * 8, "sort_pairs: bad bit range");
+  if (k == 0) return GS_OK;
+  size_t temp_bytes = workspace_bytes;
+  if (key_bytes == 8)
+    GS_CUDA(cub::DeviceRadixSort::SortPairs(workspace, temp_bytes, (const uint64_t *)keys_in, (uint64_t *)keys_out,
+                                            values_in, values_out, (int)k, begin_bit, end_bit, stream));
+  else
+    GS_CUDA(cub::DeviceRadixSort::SortPairs(workspace, temp_bytes, (const uint32_t *)keys_in, (uint32_t *)keys_out,
+                                            values_in, values_out, (int)k, begin_bit, end_bit, stream));
+  return GS_OK;
+}
+
+extern "C" int gs_tile_ranges(const void *sorted_keys, int64_t k, int32_t key_bytes, int32_t *tile_ranges,
+                              int64_t num_tiles, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CHECK_ARG(key_bytes == 4 || key_bytes == 8, "tile_ranges: key_bytes must be 4 or 8");
+  GS_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * num_tiles, stream));
+  if (k == 0) return GS_OK;
+  unsigned grid = (unsigned)gs::ceil_div(k, 256);
+  if (key_bytes == 8)
+    gs::tile_ranges_kernel<uint64_t><<<grid, 256, 0, stream>>>((const uint64_t *)sorted_keys, k, 32, tile_ranges);
+  else
+    gs::tile_ranges_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t *)sorted_keys, k, 16, tile_ranges);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}

@@ -1,0 +1,104 @@
+// raster_common.cuh -- per-pixel Gaussian evaluation shared by the rasteriser kernels.
+// Semantics: taichi_lib/generic.py:306-404 (gaussian_pdf[_with_grad], antialias variants).
+#pragma once
+#include "common.cuh"
+
+namespace gs {
+
+template <typename real>
+struct RasterParams {
+  int width, height, tiles_wide, num_features, tile_size;
+  int antialias, blend, vis, heur;
+  real clamp_max, thr, sat, fwd_eps;
+};
+
+template <typename real>
+inline RasterParams<real> make_params(const gs_raster_config *c, int width, int height, int F) {
+  RasterParams<real> p;
+  p.width = width; p.height = height; p.num_features = F; p.tile_size = c->tile_size;
+  p.tiles_wide = (width + c->tile_size - 1) / c->tile_size;
+  p.antialias = c->antialias; p.blend = c->use_alpha_blending;
+  p.vis = c->compute_visibility; p.heur = c->compute_point_heuristic;
+  p.clamp_max = (real)c->clamp_max_alpha; p.thr = (real)c->alpha_threshold;
+  p.sat = (real)c->saturate_threshold; p.fwd_eps = (real)c->forward_saturate_eps;
+  return p;
+}
+
+template <typename real>
+__device__ __forceinline__ real pdf_plain(real px, real py, const real *g) {
+  real dx = px - g[0], dy = py - g[1];
+  real tx = (dx * g[2] + dy * g[3]) / g[4];
+  real ty = (dy * g[2] - dx * g[3]) / g[5];
+  return math<real>::exp(real(-0.5) * (tx * tx + ty * ty));
+}
+
+template <typename real>
+__device__ __forceinline__ real pdf_plain_grad(real px, real py, const real *g, real *dmean, real *daxis,
+                                               real *dsigma) {
+  real dx = px - g[0], dy = py - g[1];
+  real ax = g[2], ay = g[3], sx = g[4], sy = g[5];
+  real tx = (dx * ax + dy * ay) / sx;
+  real ty = (dy * ax - dx * ay) / sy;
+  real tx2 = tx * tx, ty2 = ty * ty;
+  real p = math<real>::exp(real(-0.5) * (tx2 + ty2));
+  dsigma[0] = tx2 * p / sx; dsigma[1] = ty2 * p / sy;
+  real tx_s = tx / sx, ty_s = ty / sy;
+  daxis[0] = p * (-tx_s * dx - ty_s * dy);
+  daxis[1] = p * (-tx_s * dy + ty_s * dx);
+  dmean[0] = p * (tx_s * ax - ty_s * ay);
+  dmean[1] = p * (tx_s * ay + ty_s * ax);
+  return p;
+}
+
+template <typename real>
+__device__ __forceinline__ real s_sig(real x, real sigma) {
+  real z = x / sigma;
+  return real(1) / (real(1) + math<real>::exp(real(-1.6) * z - real(0.07) * z * z * z));
+}
+
+template <typename real>
+__device__ __forceinline__ real pdf_aa(real px, real py, const real *g) {
+  real dx = px - g[0], dy = py - g[1];
+  real sx = g[4], sy = g[5];
+  real tx = dx * g[2] + dy * g[3];
+  real ty = dy * g[2] - dx * g[3];
+  real Sx1 = s_sig(tx + real(0.5), sx), Sx2 = s_sig(tx - real(0.5), sx);
+  real Sy1 = s_sig(ty + real(0.5), sy), Sy2 = s_sig(ty - real(0.5), sy);
+  return real(6.283185307179586) * sx * (Sx1 - Sx2) * sy * (Sy1 - Sy2);
+}
+
+template <typename real>
+__device__ __forceinline__ void s_sig_grad(real x, real sigma, real &s, real &ds_dx, real &ds_dsig) {
+  real z = x / sigma;
+  s = real(1) / (real(1) + math<real>::exp(real(-1.6) * z - real(0.07) * z * z * z));
+  real d = (real(1.6) + real(0.21) * z * z) * s * (real(1) - s);
+  ds_dx = d / sigma;
+  ds_dsig = ds_dx * -z;
+}
+
+template <typename real>
+__device__ __forceinline__ real pdf_aa_grad(real px, real py, const real *g, real *dmean, real *daxis,
+                                            real *dsigma) {
+  real dx = px - g[0], dy = py - g[1];
+  real ax = g[2], ay = g[3], sx = g[4], sy = g[5];
+  real tx = dx * ax + dy * ay;
+  real ty = dy * ax - dx * ay;
+  real Sx1, dSx1, dSx1s, Sx2, dSx2, dSx2s, Sy1, dSy1, dSy1s, Sy2, dSy2, dSy2s;
+  s_sig_grad(tx + real(0.5), sx, Sx1, dSx1, dSx1s);
+  s_sig_grad(tx - real(0.5), sx, Sx2, dSx2, dSx2s);
+  s_sig_grad(ty + real(0.5), sy, Sy1, dSy1, dSy1s);
+  s_sig_grad(ty - real(0.5), sy, Sy2, dSy2, dSy2s);
+  real ix = sx * (Sx1 - Sx2), iy = sy * (Sy1 - Sy2);
+  const real tau = real(6.283185307179586);
+  real dSx = iy * sx * (dSx1 - dSx2);
+  real dSy = ix * sy * (dSy1 - dSy2);
+  dmean[0] = tau * (-dSx * ax + dSy * ay);
+  dmean[1] = tau * (-dSx * ay - dSy * ax);
+  dsigma[0] = tau * iy * (Sx1 - Sx2 + (dSx1s - dSx2s) * sx);
+  dsigma[1] = tau * ix * (Sy1 - Sy2 + (dSy1s - dSy2s) * sy);
+  daxis[0] = tau * (dSx * dx + dSy * dy);
+  daxis[1] = tau * (dSx * dy - dSy * dx);
+  return tau * ix * iy;
+}
+
+}  // namespace gs

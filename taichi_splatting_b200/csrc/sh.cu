@@ -1,0 +1,219 @@
+// sh.cu -- R2: real spherical harmonics (degree 0..3) evaluated at gathered indexes.
+//
+// Semantics: evaluate_sh_at_kernel (+ Taichi autodiff .grad), indexed_spherical_harmonics.py:118-160;
+// basis constants :38-106.  out[i,c] = clamp(sum_d Y_d(normalize(p[idx]-cam)) * params[idx,c,d] + 0.5, 0, 1).
+// Layout here: one thread per (visible point, channel) so the (M,C,D) coefficient rows are read and the
+// (V,C) colours written fully coalesced; the backward is hand-derived.
+#include "common.cuh"
+
+namespace gs {
+
+template <typename real, int DEG>
+__device__ __forceinline__ void rsh(real x, real y, real z, real *Y) {
+  Y[0] = real(0.282094791773878);
+  if constexpr (DEG >= 1) {
+    Y[1] = real(-0.48860251190292) * y;
+    Y[2] = real(0.48860251190292) * z;
+    Y[3] = real(-0.48860251190292) * x;
+  }
+  if constexpr (DEG >= 2) {
+    real x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, xz = x * z, yz = y * z;
+    Y[4] = real(1.09254843059208) * xy;
+    Y[5] = real(-1.09254843059208) * yz;
+    Y[6] = real(0.94617469575756) * z2 - real(0.31539156525252);
+    Y[7] = real(-1.09254843059208) * xz;
+    Y[8] = real(0.54627421529604) * x2 - real(0.54627421529604) * y2;
+    if constexpr (DEG >= 3) {
+      Y[9] = real(-0.590043589926644) * y * (real(3.0) * x2 - y2);
+      Y[10] = real(2.89061144264055) * xy * z;
+      Y[11] = real(0.304697199642977) * y * (real(1.5) - real(7.5) * z2);
+      Y[12] = real(1.24392110863372) * z * (real(1.5) * z2 - real(0.5)) - real(0.497568443453487) * z;
+      Y[13] = real(0.304697199642977) * x * (real(1.5) - real(7.5) * z2);
+      Y[14] = real(1.44530572132028) * z * (x2 - y2);
+      Y[15] = real(-0.590043589926644) * x * (x2 - real(3.0) * y2);
+    }
+  }
+}
+
+// d(dir) = sum_d g[d] * dY_d/d(dir)
+template <typename real, int DEG>
+__device__ __forceinline__ void rsh_vjp(real x, real y, real z, const real *g, real *d) {
+  d[0] = d[1] = d[2] = 0;
+  if constexpr (DEG >= 1) {
+    const real c1 = real(0.48860251190292);
+    d[1] += -c1 * g[1];
+    d[2] += c1 * g[2];
+    d[0] += -c1 * g[3];
+  }
+  if constexpr (DEG >= 2) {
+    const real c2 = real(1.09254843059208), c3 = real(0.94617469575756), c5 = real(0.54627421529604);
+    d[0] += c2 * y * g[4]; d[1] += c2 * x * g[4];
+    d[1] += -c2 * z * g[5]; d[2] += -c2 * y * g[5];
+    d[2] += 2 * c3 * z * g[6];
+    d[0] += -c2 * z * g[7]; d[2] += -c2 * x * g[7];
+    d[0] += 2 * c5 * x * g[8]; d[1] += -2 * c5 * y * g[8];
+  }
+  if constexpr (DEG >= 3) {
+    const real c6 = real(0.590043589926644), c7 = real(2.89061144264055), c8 = real(0.304697199642977),
+               c9 = real(1.24392110863372), c10 = real(0.497568443453487), c11 = real(1.44530572132028);
+    real x2 = x * x, y2 = y * y, z2 = z * z;
+    d[0] += -6 * c6 * x * y * g[9]; d[1] += -c6 * (3 * x2 - 3 * y2) * g[9];
+    d[0] += c7 * y * z * g[10]; d[1] += c7 * x * z * g[10]; d[2] += c7 * x * y * g[10];
+    d[1] += c8 * (real(1.5) - real(7.5) * z2) * g[11]; d[2] += -15 * c8 * y * z * g[11];
+    d[2] += (c9 * (real(4.5) * z2 - real(0.5)) - c10) * g[12];
+    d[0] += c8 * (real(1.5) - real(7.5) * z2) * g[13]; d[2] += -15 * c8 * x * z * g[13];
+    d[0] += 2 * c11 * x * z * g[14]; d[1] += -2 * c11 * y * z * g[14]; d[2] += c11 * (x2 - y2) * g[14];
+    d[0] += -c6 * (3 * x2 - 3 * y2) * g[15]; d[1] += 6 * c6 * x * y * g[15];
+  }
+}
+
+template <typename real, int DEG>
+__global__ void __launch_bounds__(256)
+sh_fwd_kernel(const real *__restrict__ params, const real *__restrict__ positions,
+              const int64_t *__restrict__ indexes, const real *__restrict__ camera_pos, int64_t total,
+              int channels, real *__restrict__ out) {
+  constexpr int D = (DEG + 1) * (DEG + 1);
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int64_t i = t / channels;
+  int c = (int)(t - i * channels);
+  int64_t idx = indexes[i];
+  real vx = positions[3 * idx] - camera_pos[0], vy = positions[3 * idx + 1] - camera_pos[1],
+       vz = positions[3 * idx + 2] - camera_pos[2];
+  real inv = real(1) / math<real>::sqrt(vx * vx + vy * vy + vz * vz);
+  real Y[D];
+  rsh<real, DEG>(vx * inv, vy * inv, vz * inv, Y);
+  const real *p = params + (idx * channels + c) * D;
+  real acc = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc += Y[d] * p[d];
+  acc += real(0.5);
+  out[t] = math<real>::min(math<real>::max(acc, real(0)), real(1));
+}
+
+template <typename real, int DEG>
+__global__ void __launch_bounds__(256)
+sh_bwd_kernel(const real *__restrict__ params, const real *__restrict__ positions,
+              const int64_t *__restrict__ indexes, const real *__restrict__ camera_pos,
+              const real *__restrict__ d_out, int64_t total, int channels, int unique,
+              real *__restrict__ d_params, real *__restrict__ d_positions, real *__restrict__ d_camera_pos) {
+  constexpr int D = (DEG + 1) * (DEG + 1);
+  __shared__ real red[3];
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  real dcam[3] = {0, 0, 0};
+  if (t < total) {
+    int64_t i = t / channels;
+    int c = (int)(t - i * channels);
+    int64_t idx = indexes[i];
+    real vx = positions[3 * idx] - camera_pos[0], vy = positions[3 * idx + 1] - camera_pos[1],
+         vz = positions[3 * idx + 2] - camera_pos[2];
+    real inv = real(1) / math<real>::sqrt(vx * vx + vy * vy + vz * vz);
+    real x = vx * inv, y = vy * inv, z = vz * inv;
+    real Y[D];
+    rsh<real, DEG>(x, y, z, Y);
+    const real *p = params + (idx * channels + c) * D;
+    real pre = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) pre += Y[d] * p[d];
+    pre += real(0.5);
+    real g = (pre >= real(0) && pre <= real(1)) ? d_out[t] : real(0);
+    if (d_params) {
+      real *dp = d_params + (idx * channels + c) * D;
+      if (unique) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) dp[d] = Y[d] * g;
+      } else if (g != real(0)) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) atomicAdd(dp + d, Y[d] * g);
+      }
+    }
+    if ((d_positions || d_camera_pos) && DEG >= 1 && g != real(0)) {
+      real gy[D], dd[3];
+#pragma unroll
+      for (int d = 0; d < D; ++d) gy[d] = p[d] * g;
+      rsh_vjp<real, DEG>(x, y, z, gy, dd);
+      real dot = x * dd[0] + y * dd[1] + z * dd[2];
+      real dv[3] = {(dd[0] - x * dot) * inv, (dd[1] - y * dot) * inv, (dd[2] - z * dot) * inv};
+      if (d_positions)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd(d_positions + 3 * idx + k, dv[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dcam[k] = -dv[k];
+    }
+  }
+  if (d_camera_pos) {
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) dcam[k] += __shfl_xor_sync(full, dcam[k], off);
+    if (threadIdx.x < 3) red[threadIdx.x] = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (dcam[k] != real(0)) atomicAdd(&red[k], dcam[k]);
+    __syncthreads();
+    if (threadIdx.x < 3 && red[threadIdx.x] != real(0)) atomicAdd(d_camera_pos + threadIdx.x, red[threadIdx.x]);
+  }
+}
+
+template <typename real>
+int sh_fwd(const real *params, const real *positions, const int64_t *indexes, const real *camera_pos, int64_t v,
+           int channels, int degree, real *out, cudaStream_t stream) {
+  GS_CHECK_ARG(degree >= 0 && degree <= 3, "sh: degree %d not in 0..3", degree);
+  GS_CHECK_ARG(channels >= 1, "sh: channels must be >= 1");
+  int64_t total = v * channels;
+  if (total == 0) return GS_OK;
+  unsigned grid = (unsigned)ceil_div(total, 256);
+  switch (degree) {
+    case 0: sh_fwd_kernel<real, 0><<<grid, 256, 0, stream>>>(params, positions, indexes, camera_pos, total, channels, out); break;
+    case 1: sh_fwd_kernel<real, 1><<<grid, 256, 0, stream>>>(params, positions, indexes, camera_pos, total, channels, out); break;
+    case 2: sh_fwd_kernel<real, 2><<<grid, 256, 0, stream>>>(params, positions, indexes, camera_pos, total, channels, out); break;
+    default: sh_fwd_kernel<real, 3><<<grid, 256, 0, stream>>>(params, positions, indexes, camera_pos, total, channels, out); break;
+  }
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+template <typename real>
+int sh_bwd(const real *params, const real *positions, const int64_t *indexes, const real *camera_pos,
+           const real *d_out, int64_t v, int channels, int degree, int unique, real *d_params, real *d_positions,
+           real *d_camera_pos, cudaStream_t stream) {
+  GS_CHECK_ARG(degree >= 0 && degree <= 3, "sh: degree %d not in 0..3", degree);
+  int64_t total = v * channels;
+  if (total == 0) return GS_OK;
+  unsigned grid = (unsigned)ceil_div(total, 256);
+#define GS_SH_BWD(DEG)                                                                                        \
+  sh_bwd_kernel<real, DEG><<<grid, 256, 0, stream>>>(params, positions, indexes, camera_pos, d_out, total,    \
+                                                     channels, unique, d_params, d_positions, d_camera_pos)
+  switch (degree) {
+    case 0: GS_SH_BWD(0); break;
+    case 1: GS_SH_BWD(1); break;
+    case 2: GS_SH_BWD(2); break;
+    default: GS_SH_BWD(3); break;
+  }
+#undef GS_SH_BWD
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+}  // namespace gs
+
+#define GS_SH_API(SUFFIX, real)                                                                                 \
+  extern "C" int gs_sh_fwd_##SUFFIX(const real *params, const real *positions, const int64_t *indexes,          \
+                                    const real *camera_pos, int64_t v, int32_t channels, int32_t degree,        \
+                                    real *out, void *stream) {                                                  \
+    return gs::sh_fwd<real>(params, positions, indexes, camera_pos, v, channels, degree, out,                   \
+                            (cudaStream_t)stream);                                                              \
+  }                                                                                                             \
+  extern "C" int gs_sh_bwd_##SUFFIX(const real *params, const real *positions, const int64_t *indexes,          \
+                                    const real *camera_pos, const real *d_out, int64_t v, int32_t channels,     \
+                                    int32_t degree, int32_t unique_indexes, real *d_params, real *d_positions,  \
+                                    real *d_camera_pos, void *stream) {                                         \
+    return gs::sh_bwd<real>(params, positions, indexes, camera_pos, d_out, v, channels, degree, unique_indexes, \
+                            d_params, d_positions, d_camera_pos, (cudaStream_t)stream);                         \
+  }
+
+GS_SH_API(f32, float)
+GS_SH_API(f64, double)

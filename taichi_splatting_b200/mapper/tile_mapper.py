@@ -1,0 +1,83 @@
+"""Tile mapper operator (reference: taichi_splatting/mapper/tile_mapper.py:20-224).
+
+count -> scan -> (tile|depth) keys -> radix sort -> ranges; device work in csrc/mapper.cu.  One host read
+(K, the total overlap count) per call, stream-scoped (the reference does two device-wide syncs, D11).
+"""
+import math
+from numbers import Integral
+from beartype.typing import Tuple
+
+import torch
+from beartype import beartype
+
+from .. import _lib
+from ..data_types import RasterConfig
+
+MAX_TILES = 65535
+
+
+def pad_to_tile(image_size: Tuple[Integral, Integral], tile_size: int):
+  return tuple(int(math.ceil(x / tile_size) * tile_size) for x in image_size)
+
+
+def key_bits(num_tiles: int, use_depth16: bool) -> int:
+  """Radix-sort bit range.  The reference sorts 48 (or 32) bits; bits above ceil(log2(T)) are zero for every
+  key, so sorting only the populated bits yields the identical order with fewer onesweep passes."""
+  tile_bits = max(1, (max(num_tiles, 1) - 1).bit_length())
+  return (16 if use_depth16 else 32) + tile_bits
+
+
+@beartype
+def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor, image_size: Tuple[Integral, Integral],
+                 config: RasterConfig, use_depth16: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+  """-> overlap_to_point (K,) int32 sorted by (tile, depth, index); tile_ranges (TH, TW, 2) int32."""
+  assert gaussians.ndim == 2 and gaussians.shape[1] == 7, f"gaussians must be Nx7 got {gaussians.shape}"
+  assert depth.ndim == 2 and depth.shape[1] == 1, f"depths must be Nx1, got {depth.shape}"
+  assert gaussians.shape[0] == depth.shape[0], f"size mismatch {gaussians.shape} vs {depth.shape}"
+  o2p, ranges, _, _ = map_to_tiles_full(gaussians, depth, image_size, config, use_depth16)
+  return o2p, ranges
+
+
+def map_to_tiles_full(gaussians, depth, image_size, config, use_depth16=False):
+  """As map_to_tiles, also returning the sorted keys and per-Gaussian counts (for tests / diagnostics)."""
+  _lib.require_cuda(gaussians=gaussians, depth=depth)
+  device = gaussians.device
+  ts = config.tile_size
+  w_pad, h_pad = pad_to_tile(image_size, ts)
+  tile_shape = (h_pad // ts, w_pad // ts)
+  num_tiles = tile_shape[0] * tile_shape[1]
+  assert num_tiles < MAX_TILES, \
+      f"tile dimensions {tile_shape} for image size {image_size} exceed maximum tile count (16 bit id), try increasing tile_size"
+
+  with torch.no_grad():
+    g = gaussians.detach().to(torch.float32).contiguous()   # the mapper is f32-only (reference :14)
+    d = depth.detach().to(torch.float32).contiguous().view(-1)
+    v = g.shape[0]
+    stream = _lib.stream_ptr(device)
+    key_dtype, key_bytes = (torch.int32, 4) if use_depth16 else (torch.int64, 8)
+    tile_ranges = torch.empty((*tile_shape, 2), dtype=torch.int32, device=device)
+
+    counts = torch.empty((v,), dtype=torch.int32, device=device)
+    cum = torch.empty((v + 1,), dtype=torch.int32, device=device)
+    _lib.call("gs_tile_count", _lib.ptr(g), v, w_pad, h_pad, ts, float(config.alpha_threshold),
+              _lib.ptr(counts), stream)
+    nbytes = _lib.c_size_t()
+    _lib.call("gs_tile_scan_workspace_bytes", v, nbytes)
+    ws = _lib.workspace(nbytes.value, device)
+    word = _lib.host_word(device)
+    _lib.call("gs_tile_scan", _lib.ptr(counts), v, _lib.ptr(cum), ws.data_ptr(), ws.numel(), word.data_ptr(), stream)
+    k = _lib.read_host_word(word, device)
+
+    keys = torch.empty((k,), dtype=key_dtype, device=device)
+    o2p = torch.empty((k,), dtype=torch.int32, device=device)
+    keys_sorted = torch.empty_like(keys)
+    o2p_sorted = torch.empty_like(o2p)
+    if k > 0:
+      _lib.call("gs_tile_emit_keys", _lib.ptr(g), _lib.ptr(d), _lib.ptr(cum), v, w_pad, h_pad, ts,
+                float(config.alpha_threshold), int(use_depth16), _lib.ptr(keys), _lib.ptr(o2p), stream)
+      _lib.call("gs_sort_pairs_workspace_bytes", k, key_bytes, nbytes)
+      ws = _lib.workspace(nbytes.value, device)
+      _lib.call("gs_sort_pairs", _lib.ptr(keys), _lib.ptr(o2p), _lib.ptr(keys_sorted), _lib.ptr(o2p_sorted), k,
+                key_bytes, 0, key_bits(num_tiles, use_depth16), ws.data_ptr(), ws.numel(), stream)
+    _lib.call("gs_tile_ranges", _lib.ptr(keys_sorted), k, key_bytes, _lib.ptr(tile_ranges), num_tiles, stream)
+    return o2p_sorted, tile_ranges, keys_sorted, counts

@@ -1,0 +1,98 @@
+"""Perspective projection operator (reference: taichi_splatting/perspective/projection.py:27-255).
+
+`apply` / `project_to_image` keep the reference's signatures and autograd contract; the device work is
+gs_project_cull / gs_project_write / gs_project_bwd in libgsplat_b200.so (csrc/projection.cu).
+"""
+from numbers import Integral
+from beartype.typing import Tuple
+
+import torch
+from beartype import beartype
+
+from .. import _lib
+from ..data_types import Gaussians3D, RasterConfig
+from .params import CameraParams
+
+
+class _ProjectFunction(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, position, log_scaling, rotation, alpha_logit, T_camera_world, projection, image_size,
+              depth_range, blur_cov, clamp_margin, alpha_threshold, want_ndc):
+    _lib.require_cuda(position=position, log_scaling=log_scaling, rotation=rotation, alpha_logit=alpha_logit,
+                      T_camera_world=T_camera_world, projection=projection)
+    dtype, device = position.dtype, position.device
+    sfx = _lib.suffix(dtype)
+    n = position.shape[0]
+    tensors = [t.detach().contiguous() for t in (position, log_scaling, rotation, alpha_logit,
+                                                 T_camera_world, projection)]
+    p = [_lib.ptr(t) for t in tensors]
+    w, h = int(image_size[0]), int(image_size[1])
+    near, far = float(depth_range[0]), float(depth_range[1])
+    stream = _lib.stream_ptr(device)
+
+    nbytes = _lib.c_size_t()
+    _lib.call("gs_project_workspace_bytes", n, nbytes)
+    ws = _lib.workspace(nbytes.value, device)
+    word = _lib.host_word(device)
+    _lib.call(f"gs_project_cull_{sfx}", *p, n, w, h, near, far, float(blur_cov), float(clamp_margin),
+              float(alpha_threshold), ws.data_ptr(), ws.numel(), word.data_ptr(), stream)
+    v = _lib.read_host_word(word, device)   # the one host sync of this operator (reference: torch.nonzero)
+
+    points = torch.empty((v, 7), dtype=dtype, device=device)
+    depth = torch.empty((v, 1), dtype=dtype, device=device)
+    indexes = torch.empty((v,), dtype=torch.int64, device=device)
+    ndc = torch.empty((v, 1), dtype=dtype, device=device) if want_ndc else None
+    _lib.call(f"gs_project_write_{sfx}", *p, n, w, h, near, far, float(blur_cov), float(clamp_margin),
+              ws.data_ptr(), _lib.ptr(points), _lib.ptr(depth), _lib.ptr(indexes), _lib.ptr(ndc), stream)
+
+    ctx.save_for_backward(*tensors, indexes)
+    ctx.image_size, ctx.blur_cov, ctx.clamp_margin = (w, h), float(blur_cov), float(clamp_margin)
+    ctx.mark_non_differentiable(indexes)
+    if want_ndc:
+      ctx.mark_non_differentiable(ndc)
+      return points, depth, indexes, ndc
+    return points, depth, indexes
+
+  @staticmethod
+  def backward(ctx, dpoints, ddepth, dindexes, *dndc):
+    position, log_scaling, rotation, alpha_logit, T_camera_world, projection, indexes = ctx.saved_tensors
+    device = position.device
+    sfx = _lib.suffix(position.dtype)
+    need = ctx.needs_input_grad
+    grads = [torch.zeros_like(t) if need[i] else None
+             for i, t in enumerate((position, log_scaling, rotation, alpha_logit, T_camera_world, projection))]
+    if any(need[:6]) and indexes.shape[0] > 0:
+      dpoints = dpoints.contiguous() if dpoints is not None else torch.zeros((indexes.shape[0], 7), dtype=position.dtype, device=device)
+      ddepth = ddepth.contiguous() if ddepth is not None else torch.zeros((indexes.shape[0], 1), dtype=position.dtype, device=device)
+      w, h = ctx.image_size
+      _lib.call(f"gs_project_bwd_{sfx}", *[_lib.ptr(t) for t in (position, log_scaling, rotation, alpha_logit,
+                                                                 T_camera_world, projection, indexes)],
+                indexes.shape[0], w, h, ctx.blur_cov, ctx.clamp_margin, _lib.ptr(dpoints), _lib.ptr(ddepth),
+                *[_lib.ptr(g) for g in grads], _lib.stream_ptr(device))
+    return (*grads, None, None, None, None, None, None)
+
+
+@beartype
+def apply(position: torch.Tensor, log_scaling: torch.Tensor, rotation: torch.Tensor, alpha_logit: torch.Tensor,
+          T_camera_world: torch.Tensor, projection: torch.Tensor, image_size: Tuple[Integral, Integral],
+          depth_range: Tuple[float, float], blur_cov: float = 0.0, clamp_margin: float = 0.15,
+          alpha_threshold: float = 1. / 255.) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+  """-> points (V,7) [mean, axis, sigma, alpha], depth (V,1) camera z, indexes (V,) int64 ascending."""
+  return _ProjectFunction.apply(position, log_scaling, rotation, alpha_logit, T_camera_world, projection,
+                                image_size, depth_range, blur_cov, clamp_margin, alpha_threshold, False)
+
+
+def apply_with_ndc(position, log_scaling, rotation, alpha_logit, T_camera_world, projection, image_size,
+                   depth_range, blur_cov=0.0, clamp_margin=0.15, alpha_threshold=1. / 255.):
+  """Same as `apply`, plus ndc depth (V,1) computed in the same kernel (fuses torch_lib ndc_depth, R11)."""
+  return _ProjectFunction.apply(position, log_scaling, rotation, alpha_logit, T_camera_world, projection,
+                                image_size, depth_range, blur_cov, clamp_margin, alpha_threshold, True)
+
+
+@beartype
+def project_to_image(gaussians: Gaussians3D, camera_params: CameraParams, config: RasterConfig
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+  """Project 3D Gaussians to packed 2D Gaussians (EWA), culling to the view (reference :220-255)."""
+  return apply(*gaussians.shape_tensors(), camera_params.T_camera_world, camera_params.projection,
+               camera_params.image_size, camera_params.depth_range, config.blur_cov, config.clamp_margin,
+               config.alpha_threshold)

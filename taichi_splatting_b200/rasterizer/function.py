@@ -1,0 +1,97 @@
+"""Rasteriser operator (reference: taichi_splatting/rasterizer/function.py:19-165).
+
+Same signatures / autograd contract as the reference; device work is gs_raster_fwd / gs_raster_bwd
+(csrc/raster_fwd.cu, raster_bwd.cu, raster_generic.cu)."""
+from numbers import Integral
+from beartype.typing import NamedTuple, Optional, Tuple
+
+import torch
+from beartype import beartype
+
+from .. import _lib
+from ..data_types import RasterConfig
+from ..mapper.tile_mapper import map_to_tiles
+
+RasterOut = NamedTuple('RasterOut', [
+    ('image', torch.Tensor),
+    ('image_weight', torch.Tensor),
+    ('point_heuristic', Optional[torch.Tensor]),
+    ('visibility', Optional[torch.Tensor]),
+])
+
+
+class _RasterFunction(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, gaussians, features, overlap_to_point, tile_overlap_ranges, image_size, config):
+    _lib.require_cuda(gaussians2d=gaussians, features=features, overlap_to_point=overlap_to_point,
+                      tile_overlap_ranges=tile_overlap_ranges)
+    dtype, device = gaussians.dtype, gaussians.device
+    sfx = _lib.suffix(dtype)
+    assert features.dtype == dtype, f"features dtype {features.dtype} != gaussians dtype {dtype}"
+    assert overlap_to_point.dtype == torch.int32 and tile_overlap_ranges.dtype == torch.int32
+    w, h = int(image_size[0]), int(image_size[1])
+    ts = config.tile_size
+    n_tiles = ((w + ts - 1) // ts) * ((h + ts - 1) // ts)
+    ranges = tile_overlap_ranges.contiguous().view(-1, 2)
+    assert ranges.shape[0] == n_tiles, f"tile_overlap_ranges has {ranges.shape[0]} tiles, image needs {n_tiles}"
+    g = gaussians.detach().contiguous()
+    f = features.detach().contiguous()
+    o2p = overlap_to_point.contiguous()
+    v, F = g.shape[0], f.shape[1]
+
+    image = torch.empty((h, w, F), dtype=dtype, device=device)
+    alpha = torch.empty((h, w), dtype=dtype, device=device)
+    heuristic = (torch.zeros((v, 2), dtype=dtype, device=device) if config.compute_point_heuristic
+                 else torch.empty((0, 2), dtype=dtype, device=device))
+    visibility = (torch.zeros((v,), dtype=dtype, device=device) if config.compute_visibility
+                  else torch.empty((0,), dtype=dtype, device=device))
+    cfg = _lib.raster_config_c(config)
+    _lib.call(f"gs_raster_fwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0],
+              w, h, F, cfg, _lib.ptr(image), _lib.ptr(alpha),
+              _lib.ptr(visibility) if config.compute_visibility else None, _lib.stream_ptr(device))
+
+    ctx.config, ctx.image_size = config, (w, h)
+    ctx.heuristic = heuristic
+    ctx.save_for_backward(g, f, image, o2p, ranges)
+    ctx.mark_non_differentiable(alpha, heuristic, visibility)
+    return image, alpha, heuristic, visibility
+
+  @staticmethod
+  def backward(ctx, grad_image, grad_alpha, grad_heuristic, grad_visibility):
+    g, f, image, o2p, ranges = ctx.saved_tensors
+    config, (w, h) = ctx.config, ctx.image_size
+    sfx = _lib.suffix(g.dtype)
+    need_g, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    grad_g = torch.zeros_like(g) if need_g else None
+    grad_f = torch.zeros_like(f) if need_f else None
+    if need_g or need_f or config.compute_point_heuristic:
+      cfg = _lib.raster_config_c(config)
+      _lib.call(f"gs_raster_bwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), _lib.ptr(image),
+                _lib.ptr(grad_image.contiguous()), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
+                _lib.ptr(grad_g), _lib.ptr(grad_f),
+                _lib.ptr(ctx.heuristic) if config.compute_point_heuristic else None, _lib.stream_ptr(g.device))
+    return grad_g, grad_f, None, None, None, None
+
+
+@beartype
+def rasterize_with_tiles(gaussians2d: torch.Tensor, features: torch.Tensor, overlap_to_point: torch.Tensor,
+                         tile_overlap_ranges: torch.Tensor, image_size: Tuple[Integral, Integral],
+                         config: RasterConfig) -> RasterOut:
+  """Rasterise packed 2D Gaussians (N,7) with features (N,F) given tile overlap information.
+  Returns RasterOut(image (H,W,F), image_weight (H,W), point_heuristic (N,2), visibility (N,))."""
+  assert gaussians2d.ndim == 2 and gaussians2d.shape[1] == 7, f"gaussians2d must be Nx7, got {gaussians2d.shape}"
+  assert features.ndim == 2 and features.shape[0] == gaussians2d.shape[0], \
+      f"Size mismatch: got {gaussians2d.shape}, {features.shape}"
+  return RasterOut(*_RasterFunction.apply(gaussians2d, features, overlap_to_point, tile_overlap_ranges,
+                                          image_size, config))
+
+
+def rasterize(gaussians2d: torch.Tensor, depth: torch.Tensor, features: torch.Tensor,
+              image_size: Tuple[Integral, Integral], config: RasterConfig, use_depth16: bool = False) -> RasterOut:
+  """map_to_tiles + rasterize_with_tiles (reference :133-165)."""
+  assert gaussians2d.shape[0] == depth.shape[0] == features.shape[0], \
+      f"Size mismatch: got {gaussians2d.shape}, {depth.shape}, {features.shape}"
+  overlap_to_point, tile_overlap_ranges = map_to_tiles(gaussians2d, depth, image_size=image_size, config=config,
+                                                       use_depth16=use_depth16)
+  return rasterize_with_tiles(gaussians2d, features, tile_overlap_ranges=tile_overlap_ranges.view(-1, 2),
+                              overlap_to_point=overlap_to_point, image_size=image_size, config=config)

@@ -1,0 +1,336 @@
+"""GPU parity tests: every C-ABI stage (through the Python operators) against the CPU oracle and the
+reference-generated golden vectors.  Run on the B200 box: `pytest tests -m gpu`.
+
+Bars (BASELINE.json north_star): tile-overlap counts / keys / sort order / ranges BIT-EXACT;
+forward image, depth and backward gradients within 1e-5 relative fp32, measured here as
+max|gpu - oracle_fp64| / max|oracle_fp64| per tensor (TOL_F32) -- the fp64 oracle is the ground truth,
+an fp32 CPU oracle run is itself only ~1e-6 from it.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cbind, pipeline, random_data, torch_ops
+from oracle.cbind import OracleConfig
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ts():
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import taichi_splatting_b200 as ts
+  from taichi_splatting_b200 import _lib
+  assert _lib.load().gs_version() >= 100   # fails loudly if the CUDA library is missing
+  return ts
+
+
+def rel_err(a, b):
+  a = a.detach().cpu().double().numpy() if hasattr(a, "detach") else np.asarray(a, np.float64)
+  b = b.detach().cpu().double().numpy() if hasattr(b, "detach") else np.asarray(b, np.float64)
+  assert a.shape == b.shape, (a.shape, b.shape)
+  if a.size == 0:
+    return 0.0
+  return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def to_cfg(ts, oc: OracleConfig, **kw):
+  d = {k: getattr(oc, k) for k in oc.__dataclass_fields__}
+  d.update(kw)
+  return ts.RasterConfig(**d)
+
+
+# --------------------------------------------------------------------------------------- projection (R1, R1b)
+PROJ_NAMES = ["position", "log_scaling", "rotation", "alpha_logit", "T_camera_world", "projection"]
+
+
+def test_projection_golden(ts, golden_dir):
+  z = np.load(f"{golden_dir}/projection.npz")
+  prefixes = sorted({"_".join(k.split("_")[:2]) for k in z.files})
+  for p in prefixes:
+    c = {k[len(p) + 1:]: z[k] for k in z.files if k.startswith(p + "_")}
+    ins = [torch.from_numpy(c[f"in_{k}"]).to(DEV).requires_grad_(True) for k in PROJ_NAMES]
+    f64 = ins[0].dtype == torch.float64
+    pts, depth, idx = ts.perspective.apply(*ins, tuple(int(v) for v in c["image_size"]),
+                                           tuple(float(v) for v in c["depth_range"]), blur_cov=float(c["blur_cov"]))
+    assert np.array_equal(idx.cpu().numpy(), c["indexes"]), p
+    tol = 1e-11 if f64 else TOL_F32
+    assert rel_err(pts, c["points"]) < tol, (p, rel_err(pts, c["points"]))
+    assert rel_err(depth, c["depth"]) < tol
+    (pts.mean() + depth.mean()).backward()
+    for k, t in zip(PROJ_NAMES, ins):
+      e = rel_err(t.grad, c[f"grad_{k}"])
+      assert e < (1e-9 if f64 else 2e-4), (p, k, e)   # fp32: reference torch_lib fp32 is itself ~1e-4 off fp64
+
+
+def test_projection_vs_oracle_random(ts):
+  for seed in range(6):
+    torch.manual_seed(seed)
+    cam = random_data.random_camera()
+    g = random_data.random_3d_gaussians(3000, cam, margin=0.4, scale_factor=0.7)
+    args64 = [x.double() for x in (g.position, g.log_scaling, g.rotation, g.alpha_logit, cam.T_camera_world, cam.projection)]
+    ref = [a.clone().requires_grad_(True) for a in args64]
+    rp, rd, ri = torch_ops.project(*ref, cam.image_size, cam.depth_range, blur_cov=0.3)
+    w = torch.rand(rp.shape, dtype=torch.float64)
+    ((rp * w).sum() + rd.sum()).backward()
+    ins = [a.float().to(DEV).requires_grad_(True) for a in args64]
+    pts, depth, idx = ts.perspective.apply(*ins, cam.image_size, cam.depth_range, blur_cov=0.3)
+    assert torch.equal(idx.cpu(), ri), seed
+    assert rel_err(pts, rp) < TOL_F32 and rel_err(depth, rd) < TOL_F32
+    ((pts * w.float().to(DEV)).sum() + depth.sum()).backward()
+    for a, b, name in zip(ins, ref, PROJ_NAMES):
+      assert rel_err(a.grad, b.grad) < 5e-5, (seed, name, rel_err(a.grad, b.grad))
+
+
+def test_projection_edge_cases(ts):
+  cam = random_data.fixed_camera((64, 48))
+  empty = [torch.zeros((0, k), device=DEV) for k in (3, 3, 4, 1)]
+  pts, depth, idx = ts.perspective.apply(*empty, cam.T_camera_world.to(DEV), cam.projection.to(DEV), cam.image_size, cam.depth_range)
+  assert pts.shape == (0, 7) and depth.shape == (0, 1) and idx.shape == (0,) and idx.dtype == torch.int64
+  # everything behind the camera -> nothing visible
+  pos = torch.tensor([[0., 0., -5.], [0., 0., 1000.]], device=DEV)
+  pts, depth, idx = ts.perspective.apply(pos, torch.zeros_like(pos), torch.tensor([[0., 0, 0, 1]] * 2, device=DEV),
+                                         torch.zeros((2, 1), device=DEV), cam.T_camera_world.to(DEV),
+                                         cam.projection.to(DEV), cam.image_size, cam.depth_range)
+  assert idx.numel() == 0
+  with pytest.raises(AssertionError):
+    ts.perspective.apply(*[e.cpu() for e in empty], cam.T_camera_world, cam.projection, cam.image_size, cam.depth_range)
+
+
+# --------------------------------------------------------------------------------------- spherical harmonics (R2)
+def test_sh_golden(ts, golden_dir):
+  z = np.load(f"{golden_dir}/spherical_harmonics.npz")
+  for seed in range(12):
+    g = lambda k: z[f"sh_{seed}_{k}"]
+    params = torch.from_numpy(g("in_params")).to(DEV).requires_grad_(True)
+    points = torch.from_numpy(g("in_points")).to(DEV).requires_grad_(True)
+    cam = torch.from_numpy(g("in_camera_pos")).to(DEV).requires_grad_(True)
+    out = ts.evaluate_sh_at(params, points, torch.from_numpy(g("indexes")).to(DEV), cam)
+    tol = 1e-12 if params.dtype == torch.float64 else TOL_F32
+    assert rel_err(out, g("out")) < tol
+    out.mean().backward()
+    assert rel_err(params.grad, g("grad_params")) < tol
+    assert rel_err(points.grad, g("grad_points")) < max(tol, 1e-11) * 5
+    assert rel_err(cam.grad, g("grad_camera_pos")) < max(tol, 1e-11) * 5
+
+
+def test_sh_degrees_and_unique(ts):
+  torch.manual_seed(0)
+  for degree in range(4):
+    n, D = 5000, (degree + 1)**2
+    params = (torch.randn(n, 3, D, dtype=torch.float64) * 0.2)
+    points = torch.randn(n, 3, dtype=torch.float64)
+    cam = torch.randn(3, dtype=torch.float64)
+    idx = torch.randperm(n)[:n // 2].sort().values
+    ref_p = params.clone().requires_grad_(True)
+    ref = torch_ops.evaluate_sh_at(ref_p, points, idx, cam)
+    w = torch.rand_like(ref)
+    (ref * w).sum().backward()
+    for unique in (False, True):
+      p = params.float().to(DEV).requires_grad_(True)
+      out = ts.evaluate_sh_at(p, points.float().to(DEV), idx.to(DEV), cam.float().to(DEV), unique_indexes=unique)
+      assert rel_err(out, ref) < TOL_F32
+      (out * w.float().to(DEV)).sum().backward()
+      assert rel_err(p.grad, ref_p.grad) < TOL_F32
+
+
+# --------------------------------------------------------------------------------------- tile mapper (R3-R7)
+def _mapper_case(ts, n, size, seed, scale_factor, use_depth16=False, tile_size=16):
+  from taichi_splatting_b200.mapper.tile_mapper import map_to_tiles_full
+  torch.manual_seed(seed)
+  g = random_data.random_2d_gaussians(n, size, scale_factor=scale_factor, alpha_range=(0.02, 0.98))
+  pts = random_data.packed_2d(g)
+  oc = OracleConfig(tile_size=tile_size)
+  o2p_ref, ranges_ref, keys_ref, counts_ref = cbind.map_to_tiles(pts.numpy(), g.depths.numpy(), size, oc,
+                                                                 use_depth16=use_depth16, return_keys=True)
+  o2p, ranges, keys, counts = map_to_tiles_full(pts.to(DEV), g.depths.to(DEV), size, to_cfg(ts, oc), use_depth16)
+  assert np.array_equal(counts.cpu().numpy(), counts_ref), "overlap counts differ"
+  k = keys.cpu().numpy()
+  k = k.astype(np.uint32).astype(np.uint64) if use_depth16 else k.view(np.uint64)
+  assert np.array_equal(k, keys_ref), "sorted keys differ"
+  assert np.array_equal(o2p.cpu().numpy(), o2p_ref), "sort order differs"
+  assert np.array_equal(ranges.cpu().numpy(), ranges_ref), "tile ranges differ"
+  return len(o2p_ref)
+
+
+@pytest.mark.parametrize("n,size,sf,ts_", [(1, (64, 48), 1.0, 16), (500, (200, 120), 1.5, 16), (20000, (640, 360), 1.0, 16),
+                                           (20000, (333, 517), 3.0, 8), (100000, (1024, 1024), 1.0, 16),
+                                           (5000, (512, 512), 20.0, 32)])
+def test_mapper_bit_exact(ts, n, size, sf, ts_):
+  assert _mapper_case(ts, n, size, seed=n, scale_factor=sf, tile_size=ts_) > 0
+
+
+def test_mapper_depth16_and_edge_cases(ts):
+  _mapper_case(ts, 5000, (320, 200), 3, 1.0, use_depth16=True)
+  cfg = ts.RasterConfig()
+  o2p, ranges = ts.map_to_tiles(torch.zeros((0, 7), device=DEV), torch.zeros((0, 1), device=DEV), (64, 48), cfg)
+  assert o2p.shape == (0,) and o2p.dtype == torch.int32 and ranges.shape == (3, 4, 2) and not ranges.any()
+  pts = torch.tensor([[10, 10, 1, 0, 3, 3, 0.001], [-500, -500, 1, 0, 3, 3, 0.9]], device=DEV)
+  o2p, ranges = ts.map_to_tiles(pts, torch.tensor([[0.5], [0.2]], device=DEV), (64, 48), cfg)
+  ref_o2p, ref_ranges = cbind.map_to_tiles(pts.cpu().numpy(), np.array([[0.5], [0.2]], np.float32), (64, 48), OracleConfig())
+  assert np.array_equal(o2p.cpu().numpy(), ref_o2p) and np.array_equal(ranges.cpu().numpy(), ref_ranges)
+  with pytest.raises(AssertionError):   # reference: assert T < 65535 (tile_mapper.py:177-178)
+    ts.map_to_tiles(pts, torch.zeros((2, 1), device=DEV), (8192, 8192), cfg)
+
+
+def test_mapper_full_size_properties(ts):
+  """cfg3-sized (1M points, 2048^2) run checked through size-independent properties."""
+  from taichi_splatting_b200.mapper.tile_mapper import map_to_tiles_full
+  torch.manual_seed(0)
+  n, size = 1_000_000, (2048, 2048)
+  g = random_data.random_2d_gaussians(n, size, scale_factor=1.0)
+  pts, depth = random_data.packed_2d(g).to(DEV), g.depths.to(DEV)
+  o2p, ranges, keys, counts = map_to_tiles_full(pts, depth, size, ts.RasterConfig())
+  K = int(counts.sum().item())
+  assert o2p.shape[0] == K == keys.shape[0] and K > n
+  assert bool((keys[1:] >= keys[:-1]).all())                               # sortedness
+  same = keys[1:] == keys[:-1]
+  assert bool((o2p[1:][same] > o2p[:-1][same]).all())                      # stability
+  r = ranges.view(-1, 2).long()
+  lens = r[:, 1] - r[:, 0]
+  assert int(lens.sum().item()) == K                                       # ranges partition the list
+  nz = r[lens > 0]
+  assert bool((nz[1:, 0] == nz[:-1, 1]).all()) and int(nz[0, 0]) == 0 and int(nz[-1, 1]) == K
+  tile_of = (keys >> 32)
+  assert bool((torch.bincount(tile_of, minlength=r.shape[0]) == lens).all())
+  assert bool((torch.bincount(o2p.long(), minlength=n) == counts).all())   # checksum of checksums
+
+
+# --------------------------------------------------------------------------------------- rasteriser (R8, R9)
+def _raster_case(n, size, seed, scale_factor, channels=3, alpha_range=(0.1, 0.9), tile_size=16):
+  torch.manual_seed(seed)
+  g = random_data.random_2d_gaussians(n, size, num_channels=channels, scale_factor=scale_factor, alpha_range=alpha_range)
+  pts = random_data.packed_2d(g)
+  oc = OracleConfig(tile_size=tile_size)
+  o2p, ranges = cbind.map_to_tiles(pts.numpy(), g.depths.numpy(), size, oc)
+  return pts, g.feature, o2p, ranges
+
+
+@pytest.mark.parametrize("n,size,sf,ch,tsz,dtype", [
+    (300, (64, 64), 1.0, 3, 16, torch.float32),      # single batch per tile
+    (6000, (100, 70), 2.0, 3, 16, torch.float32),    # >256 overlaps per tile: multi-batch, ragged edges
+    (4000, (128, 96), 1.5, 1, 16, torch.float32),
+    (4000, (128, 96), 1.5, 4, 16, torch.float32),
+    (4000, (128, 96), 1.5, 2, 16, torch.float32),
+    (3000, (90, 50), 1.5, 3, 8, torch.float32),      # generic kernel: tile 8
+    (3000, (90, 50), 1.5, 5, 32, torch.float32),     # generic kernel: tile 32, F=5
+    (2000, (64, 64), 1.5, 3, 16, torch.float64),     # generic kernel: fp64
+])
+@pytest.mark.parametrize("antialias", [False, True])
+def test_raster_forward_backward_vs_oracle(ts, n, size, sf, ch, tsz, dtype, antialias):
+  pts, feat, o2p, ranges = _raster_case(n, size, n + ch, sf, channels=ch, tile_size=tsz)
+  oc = OracleConfig(tile_size=tsz, antialias=antialias, compute_visibility=True, compute_point_heuristic=True)
+  img_ref, alpha_ref, vis_ref = cbind.raster_forward(pts, feat, ranges, o2p, size, oc, dtype=np.float64)
+  rng = np.random.default_rng(0)
+  R = rng.uniform(size=img_ref.shape)
+  gp_ref, gf_ref, heur_ref = cbind.raster_backward(pts, feat, ranges, o2p, img_ref, R, size, oc, dtype=np.float64)
+
+  tol = 1e-11 if dtype == torch.float64 else TOL_F32
+  for eps in (0.0, 1e-6):
+    cfg = to_cfg(ts, oc, forward_saturate_eps=eps)
+    p = pts.to(DEV, dtype).requires_grad_(True)
+    f = feat.to(DEV, dtype).requires_grad_(True)
+    out = ts.rasterize_with_tiles(p, f, torch.from_numpy(o2p).to(DEV), torch.from_numpy(ranges).to(DEV).view(-1, 2), size, cfg)
+    ftol = tol if eps == 0.0 else max(tol, 2e-6)
+    assert rel_err(out.image, img_ref) < ftol, rel_err(out.image, img_ref)
+    assert rel_err(out.image_weight, alpha_ref) < ftol
+    assert rel_err(out.visibility, vis_ref) < ftol * 4, rel_err(out.visibility, vis_ref)
+    (out.image * torch.from_numpy(R).to(DEV, dtype)).sum().backward()
+    btol = tol * (3 if eps == 0.0 else 30)
+    for c0, c1, name in ((0, 2, "mean"), (2, 4, "axis"), (4, 6, "sigma"), (6, 7, "alpha")):
+      e = rel_err(p.grad[:, c0:c1], gp_ref[:, c0:c1])
+      assert e < btol, (name, eps, e)
+    assert rel_err(f.grad, gf_ref) < btol, rel_err(f.grad, gf_ref)
+    assert rel_err(out.point_heuristic, heur_ref) < btol * 3, rel_err(out.point_heuristic, heur_ref)
+
+
+def test_raster_gradcheck_fp64(ts):
+  # the reference's own pin: tests/test_rasterizer.py:30-90 (one 8x8 tile, n<50, fp64 gradcheck)
+  for antialias in (False, True):
+    config = ts.RasterConfig(tile_size=8, pixel_stride=(1, 1), antialias=antialias, saturate_threshold=2.0,
+                             forward_saturate_eps=0.0)
+    for seed in range(4):
+      torch.random.manual_seed(seed)
+      n = torch.randint(1, 50, (1,)).item()
+      channels = torch.randint(1, 4, (1,)).item()
+      g = random_data.random_2d_gaussians(n, (8, 8), num_channels=channels, scale_factor=1.0, alpha_range=(0.2, 0.8))
+      g2d = random_data.packed_2d(g).to(DEV, torch.float64)
+      o2p = torch.arange(0, n, device=DEV, dtype=torch.int32)
+      ranges = torch.tensor([[0, n]], device=DEV, dtype=torch.int32)
+
+      def render(mean, axis, sigma, alpha, colors):
+        packed = torch.cat([mean, axis, sigma, alpha], dim=-1)
+        return ts.rasterize_with_tiles(packed, colors, overlap_to_point=o2p, tile_overlap_ranges=ranges,
+                                       image_size=(8, 8), config=config).image
+
+      inputs = (g2d[:, 0:2].clone().requires_grad_(True), g2d[:, 2:4].clone().requires_grad_(True),
+                g2d[:, 4:6].clone().requires_grad_(True), g2d[:, 6:7].clone().requires_grad_(True),
+                g.feature.to(DEV, torch.float64).requires_grad_(True))
+      torch.autograd.gradcheck(render, inputs, eps=1e-6, nondet_tol=1e-9)
+
+
+def test_visibility_equals_feature_gradient(ts):
+  # the reference's own pin: tests/test_visibility.py:34-64
+  rng = np.random.default_rng(0)
+  for i in range(5):
+    torch.manual_seed(i)
+    n = int(rng.integers(1, 10000))
+    g = random_data.random_2d_gaussians(n, (320, 200), scale_factor=0.2, alpha_range=(0.2, 1.0))
+    g2d = random_data.packed_2d(g).to(DEV, torch.float64)
+    feat = g.feature.to(DEV, torch.float64).requires_grad_(True)
+    config = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True, saturate_threshold=2.0,
+                             forward_saturate_eps=0.0)
+    raster = ts.rasterize(g2d, g.depths.clamp(0, 1).to(DEV), feat, (320, 200), config)
+    raster.image.sum().backward()
+    assert torch.allclose(feat.grad[:, 0], raster.visibility, rtol=1e-9, atol=1e-12)
+
+
+def test_raster_quantile_mode_median_depth(ts):
+  pts, feat, o2p, ranges = _raster_case(5000, (128, 96), 11, 1.5, channels=1)
+  oc = OracleConfig(use_alpha_blending=False, saturate_threshold=0.25)
+  img_ref, alpha_ref, _ = cbind.raster_forward(pts, feat, ranges, o2p, (128, 96), oc, dtype=np.float64)
+  out = ts.rasterize_with_tiles(pts.to(DEV), feat.to(DEV), torch.from_numpy(o2p).to(DEV),
+                                torch.from_numpy(ranges).to(DEV).view(-1, 2), (128, 96), to_cfg(ts, oc))
+  # the selected splat can flip where the cumulative weight is within rounding of the threshold
+  mism = (np.abs(out.image.cpu().numpy() - img_ref) > 1e-6).mean()
+  assert mism < 1e-3, mism
+  assert np.array_equal(out.image_weight.cpu().numpy(), alpha_ref.astype(np.float32))
+
+
+# --------------------------------------------------------------------------------------- whole path
+@pytest.mark.parametrize("use_sh", [False, True])
+def test_render_gaussians_vs_oracle_pipeline(ts, use_sh):
+  torch.manual_seed(5)
+  size = (256, 192)
+  cam = random_data.fixed_camera(size)
+  g = random_data.random_3d_gaussians(20000, cam, scale_factor=1.5, margin=0.1, sh_degree=3 if use_sh else None)
+  oc = OracleConfig(compute_visibility=True, compute_point_heuristic=True)
+  rng = np.random.default_rng(1)
+  R = rng.uniform(size=(size[1], size[0], 3))
+  g64 = type(g)(**{k: v.double() for k, v in vars(g).items()})
+  cam64 = random_data.make_camera(cam.T_camera_world.double(), cam.projection.double(), size, cam.near_plane, cam.far_plane)
+  ref = pipeline.render_forward_backward(g64, cam64, oc, use_sh=use_sh, grad_image=R, raster_dtype=np.float64)
+
+  gauss = ts.Gaussians3D(**{k: v.to(DEV).requires_grad_(True) for k, v in vars(g).items()})
+  camera = ts.perspective.CameraParams(projection=cam.projection.to(DEV).requires_grad_(True),
+                                       T_camera_world=cam.T_camera_world.to(DEV).requires_grad_(True),
+                                       near_plane=cam.near_plane, far_plane=cam.far_plane, image_size=size)
+  out = ts.render_gaussians(gauss, camera, to_cfg(ts, oc), use_sh=use_sh, render_median_depth=True)
+  assert torch.equal(out.points.idx.cpu(), ref.indexes)
+  # the depth keys come from fp32 ndc on both sides; compare the sorted overlap list exactly
+  o2p_gpu, _ = ts.map_to_tiles(out.points.gaussians2d, torch.from_numpy(ref.ndc.float().numpy()).to(DEV), size, to_cfg(ts, oc))
+  assert rel_err(out.image, ref.image) < 5e-5, rel_err(out.image, ref.image)
+  assert rel_err(out.image_weight, ref.alpha) < 5e-5
+  assert rel_err(out.points.visibility, ref.visibility) < 2e-4
+  assert out.median_depth_image.shape == (size[1], size[0])
+  (out.image * torch.from_numpy(R).float().to(DEV)).sum().backward()
+  for k in ("position", "log_scaling", "rotation", "alpha_logit", "feature"):
+    e = rel_err(getattr(gauss, k).grad, ref.grads[k])
+    assert e < 2e-4, (k, e)
+  assert rel_err(camera.T_camera_world.grad, ref.grads["T_camera_world"]) < 2e-3
+  assert rel_err(camera.projection.grad, ref.grads["projection"]) < 2e-3
+  assert rel_err(out.points.prune_cost, ref.heuristic[:, 0]) < 1e-3
