@@ -86,8 +86,50 @@ def check(code: int, what: str) -> None:
     raise RuntimeError(f"{what}: {msg} (code {code})")
 
 
+# Hand-written kernels each entry point launches (CUB scan / onesweep launches are not counted).
+OWN_KERNELS = {
+    "gs_project_cull_f32": 1, "gs_project_cull_f64": 1, "gs_project_write_f32": 1, "gs_project_write_f64": 1,
+    "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
+    "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
+    "gs_tile_ranges": 1, "gs_raster_fwd_f32": 1, "gs_raster_fwd_f64": 1, "gs_raster_bwd_f32": 1,
+    "gs_raster_bwd_f64": 1,
+}
+
+
+class Profiler:
+  """Optional per-entry-point CUDA-event timing on the launching stream (used by bench.py only)."""
+
+  def __init__(self, only=None):
+    self.only = only          # None: every entry point; else a set of names
+    self.records = []         # (name, start_event, end_event)
+    self.launches = 0
+
+  def stage_ms(self):
+    out = {}
+    for name, a, b in self.records:
+      out.setdefault(name, []).append(a.elapsed_time(b))
+    return out
+
+
+profiler = None   # set to a Profiler() to enable
+
+
 def call(name: str, *args) -> None:
-  check(getattr(load(), name)(*args), name)
+  fn = getattr(load(), name)
+  prof = profiler
+  if prof is None:
+    check(fn(*args), name)
+    return
+  prof.launches += OWN_KERNELS.get(name, 0)
+  if prof.only is not None and name not in prof.only:
+    check(fn(*args), name)
+    return
+  stream = torch.cuda.current_stream()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record(stream)
+  check(fn(*args), name)
+  b.record(stream)
+  prof.records.append((name, a, b))
 
 
 def suffix(dtype: torch.dtype) -> str:
