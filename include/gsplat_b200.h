@@ -156,6 +156,15 @@ int gs_raster_fwd_f32(const float *points, const float *features, const int32_t 
                       const int32_t *overlap_to_point, int64_t v, int64_t k, int32_t width, int32_t height,
                       int32_t num_features, const gs_raster_config *config, float *image,
                       float *image_alpha, float *visibility, void *stream);
+/* Fused variant: also writes median_image (H,W): depth of the first splat at which the accumulated weight
+ * reaches 1 - median_threshold, i.e. the output of the reference's second, non-blending raster pass
+ * over features=depths (renderer.py:77-82, forward.py:107-112) without re-walking the tile lists.
+ * fp32, tile_size 16, no antialias, 1..4 features only (GS_ERR_UNSUPPORTED otherwise).          */
+int gs_raster_fwd_median_f32(const float *points, const float *features, const float *depths,
+                             const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t v, int64_t k,
+                             int32_t width, int32_t height, int32_t num_features, const gs_raster_config *config,
+                             double median_threshold, float *image, float *image_alpha, float *visibility,
+                             float *median_image, void *stream);
 int gs_raster_fwd_f64(const double *points, const double *features, const int32_t *tile_ranges,
                       const int32_t *overlap_to_point, int64_t v, int64_t k, int32_t width, int32_t height,
                       int32_t num_features, const gs_raster_config *config, double *image,

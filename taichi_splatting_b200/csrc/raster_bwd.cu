@@ -6,14 +6,19 @@
 //
 // B200 design (not the reference's):
 //   * same CTA / warp-rectangle / staged-record / per-warp hit-list structure as raster_fwd.cu;
-//   * per (pixel, splat) only seven splat-independent moments are formed
-//       {G p tx, G p ty, G p tx dx, G p tx dy, G p ty dx, G p ty dy, p dL/dalpha}
-//     (G = alpha * dL/dalpha); the seven parameter gradients are linear in their sums, so the
-//     multiplication by axis / 1/sigma happens once per (splat, tile) at flush time;
-//   * the warp reduction is a transposed butterfly: 16 values x 32 lanes are reduced with
-//     8+4+2+1+1 = 16 shuffles (instead of 16 x 5), leaving one finished sum in every second lane,
-//     which then issues ONE conflict-free shared-memory atomic instruction per warp;
-//   * one global float atomic per (splat, tile, component) at the end of each 256-splat batch.
+//   * per (pixel, splat) the only splat-independent quantities formed are the six tile-local moments of
+//     Gp = alpha_point * dL/dalpha * pdf  over the pixel offset l from the tile centre,
+//         {1, lx, ly, lx^2, lx ly, ly^2} * Gp,
+//     plus weight * dL/dimage (feature gradient) and the two densification heuristics.  All seven
+//     parameter gradients are linear in the moment sums (the pdf is exp of a quadratic form in the pixel
+//     position), so axis / sigma / mean enter once per (splat, tile) at flush time, and
+//     dL/dalpha_point = M0 / alpha_point;
+//   * because the moment multipliers {1, lx, ...} are per-lane constants, each lane keeps them in a
+//     lane-dependent (XOR-permuted) register order, which makes the transposed-butterfly warp reduction
+//     select-free: v[r] += shfl_xor(v[r + half], off).  8 moments cost 7+2 shuffles, 4 feature slots 3+3,
+//     the 2 heuristics 1+4 -- against 5 shuffles per value for a plain tree;
+//   * the inner loop is branch-free; one shared-memory atomic instruction per (warp, splat); one global
+//     float atomic per (splat, tile, component) at the end of each 256-splat batch.
 #include "raster_common.cuh"
 
 namespace gs {
@@ -26,7 +31,6 @@ int raster_bwd_generic(const real *points, const real *features, const int32_t *
 
 constexpr int kTileB = 16;
 constexpr int kBatchB = 256;
-constexpr int kAccStride = 17;  // 16 slots + 1 pad: conflict-free both for the warp atomics and the flush
 constexpr float kExpScaleB = 0.84932180028801904f;
 
 __device__ __forceinline__ float ex2_approx_b(float x) {
@@ -34,48 +38,45 @@ __device__ __forceinline__ float ex2_approx_b(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
+// accumulator slots per staged splat: [M0, Lx, Ly, Lxx, Lxy, Lyy | f0..f(F-1) | h0, h1], odd stride
+template <int F> struct AccLayout {
+  static constexpr int kFeat = 6, kHeur = 6 + F, kUsed = 8 + F, kStride = kUsed | 1;
+};
+
+template <int F>
 struct BwdSmem {
   float4 a[kBatchB];  // mean.x, mean.y, (axis/sx)*k
   float4 b[kBatchB];  // (perp/sy)*k, alpha, unused
   float4 f[kBatchB];
-  float acc[kBatchB * kAccStride];
+  float acc[kBatchB * AccLayout<F>::kStride];
   unsigned char mask[kBatchB];
-  unsigned char list[8][kBatchB];
+  unsigned short list[8][kBatchB];
   int warp_done[8];
 };
 
-// 16 values per lane -> lane l (even) ends with the warp-wide sum of value (l >> 1) in v[0].
-__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
-  const unsigned full = 0xffffffffu;
-#pragma unroll
-  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      float send = upper ? v[i] : v[i + half];
-      float keep = upper ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(full, send, off);
-    }
-  }
-  v[0] += __shfl_xor_sync(full, v[0], 1);
-}
-
-// slots: 0..6 moments, 7..7+F-1 feature grads, 14,15 heuristics
 template <int F, bool GP, bool GF, bool HEUR>
-__global__ void __launch_bounds__(kBatchB)
+__global__ void __launch_bounds__(kBatchB, 3)
 raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ features,
                   const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
                   const float *__restrict__ image, const float *__restrict__ grad_image, RasterParams<float> P,
                   float *__restrict__ grad_points, float *__restrict__ grad_features,
                   float *__restrict__ heuristic) {
-  __shared__ BwdSmem sm;
+  using L = AccLayout<F>;
+  __shared__ BwdSmem<F> sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
   const int tile_x0 = (tile % P.tiles_wide) * kTileB, tile_y0 = (tile / P.tiles_wide) * kTileB;
-  const int px = tile_x0 + (warp & 1) * 8 + (lane & 7), py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
+  const int lxi = (warp & 1) * 8 + (lane & 7), lyi = (warp >> 1) * 4 + (lane >> 3);
+  const int px = tile_x0 + lxi, py = tile_y0 + lyi;
   const bool in_bounds = px < P.width && py < P.height;
   const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+  const float clamp_max = P.clamp_max, thr = P.thr, sat = P.sat;
 
   float remaining[F], gpix[F];
 #pragma unroll
@@ -88,6 +89,49 @@ raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
     for (int c = 0; c < F; ++c) { remaining[c] = img[c]; gpix[c] = gi[c]; }
     total_weight = 0.f;
   }
+
+  // ---- lane-constant, XOR-permuted multipliers (see header) ----
+  const int b16 = (lane >> 4) & 1, b8 = (lane >> 3) & 1, b4 = (lane >> 2) & 1;
+  const int mA = (b16 << 2) | (b8 << 1) | b4;   // this lane ends up owning moment index mA
+  const int mB = (b16 << 1) | b8;               // ... and feature slot mB
+  // coefA[p] = c[p ^ mA], gpixB[p] = gpix[p ^ mB]: XOR by a bit = conditional swap of register pairs
+  float coefA[8];
+  {
+    const float lx = (float)lxi - 7.5f, ly = (float)lyi - 7.5f;   // pixel centre relative to the tile centre
+    coefA[0] = 1.f; coefA[1] = lx; coefA[2] = ly; coefA[3] = lx * lx; coefA[4] = lx * ly; coefA[5] = ly * ly;
+    coefA[6] = 0.f; coefA[7] = 0.f;
+#pragma unroll
+    for (int bit = 1; bit <= 4; bit <<= 1) {
+      const bool sw = (mA & bit) != 0;
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if ((p & bit) == 0) {
+          float lo = coefA[p], hi = coefA[p | bit];
+          coefA[p] = sw ? hi : lo;
+          coefA[p | bit] = sw ? lo : hi;
+        }
+    }
+  }
+  float gpixB[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) gpixB[p] = p < F ? gpix[p < F ? p : 0] : 0.f;
+#pragma unroll
+  for (int bit = 1; bit <= 2; bit <<= 1) {
+    const bool sw = (mB & bit) != 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if ((p & bit) == 0) {
+        float lo = gpixB[p], hi = gpixB[p | bit];
+        gpixB[p] = sw ? hi : lo;
+        gpixB[p | bit] = sw ? lo : hi;
+      }
+  }
+  // which accumulator slot this lane adds after the reductions (-1: none)
+  int my_slot = -1;
+  if ((lane & 3) == 0) my_slot = GP && mA < 6 ? mA : -1;
+  else if ((lane & 3) == 1 && b4 == 0) my_slot = GF && mB < F ? L::kFeat + mB : -1;
+  else if ((lane & 3) == 2 && b4 == 0 && b8 == 0) my_slot = HEUR ? L::kHeur + b16 : -1;
+  const int my_role = lane & 3;
 
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
   if (lane == 0) sm.warp_done[warp] = 0;
@@ -103,20 +147,20 @@ raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
     }
     // ---- stage (thread j owns splat j of the batch, and flushes it at the end) ----
     int my_id = -1;
-    float s_ax = 0.f, s_ay = 0.f, s_isx = 0.f, s_isy = 0.f;
+    float s_mx = 0.f, s_my = 0.f, s_ax = 0.f, s_ay = 0.f, s_isx = 0.f, s_isy = 0.f, s_alpha = 1.f;
     if (tid < nb) {
       my_id = overlap_to_point[base + tid];
       const float *g = points + 7 * (int64_t)my_id;
       float mx = g[0], my = g[1], ax = g[2], ay = g[3], sx = g[4], sy = g[5], alpha = g[6];
       float isx = 1.0f / sx, isy = 1.0f / sy;
-      s_ax = ax; s_ay = ay; s_isx = isx; s_isy = isy;
+      s_mx = mx; s_my = my; s_ax = ax; s_ay = ay; s_isx = isx; s_isy = isy; s_alpha = alpha;
       float ux = ax * isx * kExpScaleB, uy = ay * isx * kExpScaleB;
       float wx = -ay * isy * kExpScaleB, wy = ax * isy * kExpScaleB;
       sm.a[tid] = make_float4(mx, my, ux, uy);
       sm.b[tid] = make_float4(wx, wy, alpha, 0.f);
       unsigned mask = 0;
-      if (alpha > P.thr) {
-        float rc = sqrtf(2.0f * __logf(alpha / P.thr)) * 1.001f + 0.01f;
+      if (alpha > thr) {
+        float rc = sqrtf(2.0f * __logf(alpha / thr)) * 1.001f + 0.01f;
         float rcs = rc * kExpScaleB;
         float e1x = ax * sx, e1y = ay * sx, e2x = ay * sy, e2y = ax * sy;
         float ex = rc * sqrtf(e1x * e1x + e2x * e2x), ey = rc * sqrtf(e1y * e1y + e2y * e2y);
@@ -140,87 +184,110 @@ raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
       if (F > 3) fv.w = fp[3];
       sm.f[tid] = fv;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) sm.acc[tid * kAccStride + c] = 0.f;
+      for (int c = 0; c < L::kUsed; ++c) sm.acc[tid * L::kStride + c] = 0.f;
     }
     __syncthreads();
 
     // ---- per-warp ordered hit list ----
     int nhit = 0;
-    if (!__all_sync(0xffffffffu, total_weight >= P.sat)) {
+    if (!__all_sync(0xffffffffu, total_weight >= sat)) {
       for (int c = 0; c < nb; c += 32) {
         int j = c + lane;
         bool hit = j < nb && ((sm.mask[j] >> warp) & 1);
         unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) sm.list[warp][nhit + __popc(bal & ((1u << lane) - 1))] = (unsigned char)j;
+        if (hit) sm.list[warp][nhit + __popc(bal & ((1u << lane) - 1))] = (unsigned short)j;
         nhit += __popc(bal);
       }
       __syncwarp();
     }
 
-    // ---- gradient sweep ----
+    // ---- gradient sweep (branch-free body) ----
+    const unsigned full = 0xffffffffu;
+#pragma unroll 2
     for (int h = 0; h < nhit; ++h) {
       const int j = sm.list[warp][h];
       const float4 A = sm.a[j], B = sm.b[j];
+      const float4 fv = sm.f[j];
+      const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
       float dx = fx - A.x, dy = fy - A.y;
       float tx = dx * A.z + dy * A.w, ty = dx * B.x + dy * B.y;
       float ga = ex2_approx_b(-(tx * tx + ty * ty));
       float alpha = B.z * ga;
-      const bool has_grad = alpha > P.thr && total_weight < P.sat;
-      float v[16];
+      const bool has_grad = alpha > thr && total_weight < sat;
+      alpha = fminf(alpha, clamp_max);
+      float T_i = 1.0f - total_weight;
+      float weight = has_grad ? alpha * T_i : 0.f;
+      total_weight += weight;
+      float inv_1ma = rcp_approx(1.0f - alpha);
+      float alpha_grad = 0.f;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = 0.f;
-      if (has_grad) {
-        alpha = fminf(alpha, P.clamp_max);
-        const float4 fv = sm.f[j];
-        const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
-        float T_i = 1.0f - total_weight;
-        float weight = alpha * T_i;
-        total_weight += weight;
-        float inv_1ma = __fdividef(1.0f, 1.0f - alpha);
-        float alpha_grad = 0.f;
-#pragma unroll
-        for (int c = 0; c < F; ++c) {
-          remaining[c] -= feat[c] * weight;
-          float diff = feat[c] * T_i - remaining[c] * inv_1ma;
-          alpha_grad += diff * gpix[c];
-          if (GF) v[7 + c] = weight * gpix[c];
-        }
-        float G = B.z * alpha_grad;
-        if (GP || HEUR) {
-          float Gp = G * ga;
-          float a1 = Gp * tx, a2 = Gp * ty;  // scaled by k (tx, ty carry the exp scale)
-          v[0] = a1; v[1] = a2;
-          v[2] = a1 * dx; v[3] = a1 * dy; v[4] = a2 * dx; v[5] = a2 * dy;
-          v[6] = ga * alpha_grad;
-          if (HEUR) {
-            // |G dp/dmean|_1 with dp/dmean = p (tx u + ty w); A.zw, B.xy and a1, a2 each carry one k
-            const float inv_k2 = 1.0f / (kExpScaleB * kExpScaleB);
-            v[14] = G * G;
-            v[15] = (fabsf(a1 * A.z + a2 * B.x) + fabsf(a1 * A.w + a2 * B.y)) * inv_k2;
-          }
-        }
+      for (int c = 0; c < F; ++c) {
+        remaining[c] = fmaf(-feat[c], weight, remaining[c]);
+        float diff = fmaf(-remaining[c], inv_1ma, feat[c] * T_i);
+        alpha_grad = fmaf(diff, gpix[c], alpha_grad);
       }
-      if (__any_sync(0xffffffffu, has_grad)) {
-        warp_transpose_reduce16(v, lane);
-        if ((lane & 1) == 0 && v[0] != 0.f) atomicAdd(&sm.acc[j * kAccStride + (lane >> 1)], v[0]);
+      float G = has_grad ? B.z * alpha_grad : 0.f;
+      float Gp = G * ga;
+
+      float add_val = 0.f;
+      if (GP) {   // six moments (two spare slots) : 7 + 2 shuffles
+        float v0 = Gp * coefA[0], v1 = Gp * coefA[1], v2 = Gp * coefA[2], v3 = Gp * coefA[3];
+        float v4 = Gp * coefA[4], v5 = Gp * coefA[5], v6 = Gp * coefA[6], v7 = Gp * coefA[7];
+        v0 += __shfl_xor_sync(full, v4, 16); v1 += __shfl_xor_sync(full, v5, 16);
+        v2 += __shfl_xor_sync(full, v6, 16); v3 += __shfl_xor_sync(full, v7, 16);
+        v0 += __shfl_xor_sync(full, v2, 8); v1 += __shfl_xor_sync(full, v3, 8);
+        v0 += __shfl_xor_sync(full, v1, 4);
+        v0 += __shfl_xor_sync(full, v0, 2);
+        v0 += __shfl_xor_sync(full, v0, 1);
+        add_val = v0;
       }
-      if (__all_sync(0xffffffffu, total_weight >= P.sat)) break;
+      if (GF) {           // weight * dL/dimage : 3 + 3 shuffles
+        float v0 = weight * gpixB[0], v1 = weight * gpixB[1], v2 = weight * gpixB[2], v3 = weight * gpixB[3];
+        v0 += __shfl_xor_sync(full, v2, 16); v1 += __shfl_xor_sync(full, v3, 16);
+        v0 += __shfl_xor_sync(full, v1, 8);
+        v0 += __shfl_xor_sync(full, v0, 4);
+        v0 += __shfl_xor_sync(full, v0, 2);
+        v0 += __shfl_xor_sync(full, v0, 1);
+        add_val = my_role == 1 ? v0 : add_val;
+      }
+      if (HEUR) {         // [ (alpha dL/dalpha)^2 , |alpha dL/dalpha dpdf/dmean|_1 ] : 1 + 4 shuffles
+        const float inv_k2 = 1.0f / (kExpScaleB * kExpScaleB);
+        float a1 = Gp * tx, a2 = Gp * ty;   // each carries one exp-scale factor k, as do A.zw / B.xy
+        float h0 = G * G;
+        float h1 = (fabsf(a1 * A.z + a2 * B.x) + fabsf(a1 * A.w + a2 * B.y)) * inv_k2;
+        float v0 = b16 ? h1 : h0, v1 = b16 ? h0 : h1;
+        v0 += __shfl_xor_sync(full, v1, 16);
+        v0 += __shfl_xor_sync(full, v0, 8);
+        v0 += __shfl_xor_sync(full, v0, 4);
+        v0 += __shfl_xor_sync(full, v0, 2);
+        v0 += __shfl_xor_sync(full, v0, 1);
+        add_val = my_role == 2 ? v0 : add_val;
+      }
+      if (my_slot >= 0 && add_val != 0.f) atomicAdd(&sm.acc[j * L::kStride + my_slot], add_val);
+      if (__all_sync(full, total_weight >= sat)) break;
     }
-    if (__all_sync(0xffffffffu, total_weight >= P.sat) && lane == 0) sm.warp_done[warp] = 1;
+    if (__all_sync(full, total_weight >= sat) && lane == 0) sm.warp_done[warp] = 1;
 
     // ---- flush: one thread per staged splat ----
     __syncthreads();
     if (tid < nb) {
-      float S[16];
+      float S[L::kUsed];
       bool any = false;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { S[c] = sm.acc[tid * kAccStride + c]; any |= (S[c] != 0.f); }
+      for (int c = 0; c < L::kUsed; ++c) { S[c] = sm.acc[tid * L::kStride + c]; any |= (S[c] != 0.f); }
       if (any) {
         if (GP) {
-          const float inv_k = 1.0f / kExpScaleB;
-          float S1 = S[0] * inv_k, S2 = S[1] * inv_k, S3 = S[2] * inv_k, S4 = S[3] * inv_k, S5 = S[4] * inv_k,
-                S6 = S[5] * inv_k;
-          float ux = s_ax * s_isx, uy = s_ay * s_isx, wx = -s_ay * s_isy, wy = s_ax * s_isy;
+          // shift the tile-centred moments to the splat mean: d = l + c
+          const float cx = (float)tile_x0 + 8.0f - s_mx, cy = (float)tile_y0 + 8.0f - s_my;
+          const float M0 = S[0], Lx = S[1], Ly = S[2], Lxx = S[3], Lxy = S[4], Lyy = S[5];
+          const float Mx = fmaf(cx, M0, Lx), My = fmaf(cy, M0, Ly);
+          const float Mxx = Lxx + cx * (2.0f * Lx + cx * M0);
+          const float Myy = Lyy + cy * (2.0f * Ly + cy * M0);
+          const float Mxy = Lxy + cx * Ly + cy * Lx + cx * cy * M0;
+          const float ux = s_ax * s_isx, uy = s_ay * s_isx, wx = -s_ay * s_isy, wy = s_ax * s_isy;
+          const float S1 = ux * Mx + uy * My, S2 = wx * Mx + wy * My;             // sum Gp tx, sum Gp ty
+          const float S3 = ux * Mxx + uy * Mxy, S4 = ux * Mxy + uy * Myy;         // sum Gp tx dx, sum Gp tx dy
+          const float S5 = wx * Mxx + wy * Mxy, S6 = wx * Mxy + wy * Myy;         // sum Gp ty dx, sum Gp ty dy
           float *gp = grad_points + 7 * (int64_t)my_id;
           atomicAdd(gp + 0, S1 * ux + S2 * wx);
           atomicAdd(gp + 1, S1 * uy + S2 * wy);
@@ -228,16 +295,16 @@ raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
           atomicAdd(gp + 3, -s_isx * S4 + s_isy * S5);
           atomicAdd(gp + 4, s_isx * (ux * S3 + uy * S4));
           atomicAdd(gp + 5, s_isy * (wx * S5 + wy * S6));
-          atomicAdd(gp + 6, S[6]);
+          atomicAdd(gp + 6, M0 / s_alpha);
         }
         if (GF) {
           float *gf = grad_features + (int64_t)F * my_id;
 #pragma unroll
-          for (int c = 0; c < F; ++c) atomicAdd(gf + c, S[7 + c]);
+          for (int c = 0; c < F; ++c) atomicAdd(gf + c, S[L::kFeat + c]);
         }
         if (HEUR) {
-          atomicAdd(heuristic + 2 * (int64_t)my_id, S[14]);
-          atomicAdd(heuristic + 2 * (int64_t)my_id + 1, S[15]);
+          atomicAdd(heuristic + 2 * (int64_t)my_id, S[L::kHeur]);
+          atomicAdd(heuristic + 2 * (int64_t)my_id + 1, S[L::kHeur + 1]);
         }
       }
     }

