@@ -101,7 +101,7 @@ def algorithmic_bytes(N, V, K, P, T, F, D):
 def run_ours(args):
   import torch.distributed as dist
   import taichi_splatting_b200 as ts
-  from taichi_splatting_b200 import _lib
+  from taichi_splatting_b200 import _lib, parallel
   from taichi_splatting_b200.benchmarks import scenes
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -137,11 +137,9 @@ def run_ours(args):
     loss = out.image.sum()
     loss.backward()
     if world > 1:
-      # the single exchange of the view-parallel path: sum per-Gaussian gradients over views
-      works = [dist.all_reduce(t.grad, async_op=True) for t in (gauss.position, gauss.log_scaling, gauss.rotation,
-                                                                  gauss.alpha_logit, gauss.feature)]
-      for wk in works:
-        wk.wait()
+      # the single exchange of the view-parallel path: sum per-Gaussian gradients over views (NCCL all-reduce)
+      parallel.allreduce_gradients((gauss.position, gauss.log_scaling, gauss.rotation, gauss.alpha_logit,
+                                    gauss.feature), bucket=False)
     return out, loss
 
   def barrier():

@@ -86,6 +86,11 @@ int gs_project_write_f64(const double *position, const double *log_scaling, cons
                          double *points, double *depth, int64_t *indexes, double *ndc_depth,
                          void *stream);
 
+/* camera position in world space, -A^-1 t for T_camera_world = [A t; 0 0 0 1]: replaces
+ * torch.inverse(T_camera_world)[0:3, 3] (perspective/params.py:78-80) on the SH path (renderer.py:53). */
+int gs_camera_position_f32(const float *T_camera_world, float *camera_pos, void *stream);
+int gs_camera_position_f64(const double *T_camera_world, double *camera_pos, void *stream);
+
 /* ---- R1b: projection backward ------------------------------------------------------------------
  * replaces indexed_project_kernel.grad (Taichi autodiff; perspective/projection.py:84-119,165-188).
  * Hand-derived reverse chain.  All grad outputs must be zero-initialised by

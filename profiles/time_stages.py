@@ -43,3 +43,23 @@ for k, v in prof.stage_ms().items():
   if med > 0.004:
     print(f"{k:32s} median {med:8.4f} ms   min {v[0]:8.4f}")
 print(f"sum of stage medians {tot:.4f} ms; wall per step {a.elapsed_time(b) / steps:.4f} ms")
+
+# ---- timeline of one step: where the GPU idles between our launches ----
+prof = _lib.Profiler()
+_lib.profiler = prof
+t0 = torch.cuda.Event(enable_timing=True)
+t1 = torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+t0.record()
+step()
+t1.record()
+torch.cuda.synchronize()
+_lib.profiler = None
+prev_end = 0.0
+print("timeline (ms from step start): name start end gap_before")
+for name, a_, b_ in prof.records:
+  s, e = t0.elapsed_time(a_), t0.elapsed_time(b_)
+  if e - s > 0.004 or s - prev_end > 0.02:
+    print(f"  {name:28s} {s:8.3f} {e:8.3f}  gap {s - prev_end:7.3f}")
+  prev_end = e
+print(f"  step end {t0.elapsed_time(t1):8.3f}  gap {t0.elapsed_time(t1) - prev_end:7.3f}")

@@ -43,6 +43,7 @@ SIGNATURES = {
     "gs_project_cull_f32": (_PROJECT_CULL, c_int32), "gs_project_cull_f64": (_PROJECT_CULL, c_int32),
     "gs_project_write_f32": (_PROJECT_WRITE, c_int32), "gs_project_write_f64": (_PROJECT_WRITE, c_int32),
     "gs_project_bwd_f32": (_PROJECT_BWD, c_int32), "gs_project_bwd_f64": (_PROJECT_BWD, c_int32),
+    "gs_camera_position_f32": ([P, P, P], c_int32), "gs_camera_position_f64": ([P, P, P], c_int32),
     "gs_sh_fwd_f32": (_SH_FWD, c_int32), "gs_sh_fwd_f64": (_SH_FWD, c_int32),
     "gs_sh_bwd_f32": (_SH_BWD, c_int32), "gs_sh_bwd_f64": (_SH_BWD, c_int32),
     "gs_tile_count": ([P, I64, I32, I32, I32, D, P, P], c_int32),
@@ -90,7 +91,7 @@ def check(code: int, what: str) -> None:
 # Hand-written kernels each entry point launches (CUB scan / onesweep launches are not counted).
 OWN_KERNELS = {
     "gs_project_cull_f32": 1, "gs_project_cull_f64": 1, "gs_project_write_f32": 1, "gs_project_write_f64": 1,
-    "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
+    "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_camera_position_f32": 1, "gs_camera_position_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
     "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
     "gs_tile_ranges": 1, "gs_raster_fwd_f32": 1, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 1, "gs_raster_bwd_f32": 1,
     "gs_raster_bwd_f64": 1,

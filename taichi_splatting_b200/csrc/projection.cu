@@ -309,6 +309,20 @@ project_bwd_kernel(const real *__restrict__ position, const real *__restrict__ l
   }
 }
 
+// camera position = -A^-1 t for T_camera_world = [A t; 0 1]  (perspective/params.py:78-80 uses torch.inverse)
+template <typename real>
+__global__ void camera_position_kernel(const real *__restrict__ T, real *__restrict__ out) {
+  real a = T[0], b = T[1], c = T[2], d = T[4], e = T[5], f = T[6], g = T[8], h = T[9], i = T[10];
+  real tx = T[3], ty = T[7], tz = T[11];
+  real c00 = e * i - f * h, c01 = c * h - b * i, c02 = b * f - c * e;
+  real c10 = f * g - d * i, c11 = a * i - c * g, c12 = c * d - a * f;
+  real c20 = d * h - e * g, c21 = b * g - a * h, c22 = a * e - b * d;
+  real inv_det = real(1) / (a * c00 + b * c10 + c * c20);
+  out[0] = -(c00 * tx + c01 * ty + c02 * tz) * inv_det;
+  out[1] = -(c10 * tx + c11 * ty + c12 * tz) * inv_det;
+  out[2] = -(c20 * tx + c21 * ty + c22 * tz) * inv_det;
+}
+
 template <typename real>
 int project_cull(const real *position, const real *log_scaling, const real *rotation, const real *alpha_logit,
                  const real *T, const real *proj, int64_t n, int32_t width, int32_t height, double near_plane,
@@ -408,6 +422,17 @@ extern "C" int gs_project_workspace_bytes(int64_t n, size_t *bytes) {
                                  height, blur_cov, clamp_margin, d_points, d_depth, d_position, d_log_scaling,    \
                                  d_rotation, d_alpha_logit, d_T, d_projection, (cudaStream_t)stream);             \
   }
+
+extern "C" int gs_camera_position_f32(const float *T_camera_world, float *camera_pos, void *stream) {
+  gs::camera_position_kernel<float><<<1, 1, 0, (cudaStream_t)stream>>>(T_camera_world, camera_pos);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+extern "C" int gs_camera_position_f64(const double *T_camera_world, double *camera_pos, void *stream) {
+  gs::camera_position_kernel<double><<<1, 1, 0, (cudaStream_t)stream>>>(T_camera_world, camera_pos);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
 
 GS_PROJECT_API(f32, float)
 GS_PROJECT_API(f64, double)

@@ -1,0 +1,149 @@
+"""Multi-GPU sharding of the render path (new design: the reference has no distributed code).
+
+One process per GPU (`torch.distributed`, NCCL over NVLink/NVSwitch; gloo on CPU for the host-logic tests).
+The path shards two natural ways, both with exactly ONE collective, in the backward pass:
+
+  view-parallel   the cloud is replicated, rank r renders its own camera(s); no communication in the
+                  forward; the backward ends with an all-reduce(sum) of the per-Gaussian parameter gradients
+                  (`allreduce_gradients`).
+  tile-sharded    one view, the tile grid is cut into `world` contiguous tile-id ranges holding equal
+                  numbers of (tile, Gaussian) overlaps (`partition_tiles`); every rank projects / bins / sorts
+                  the whole (cheap, O(N)) front end, rasterises only its own tiles, and the gradients of the
+                  packed 2D Gaussians and features are summed across ranks (`reduce_across_ranks`, an identity
+                  in the forward) before the replicated projection / SH backward.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world_info(group=None) -> Tuple[int, int]:
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_rank(group), dist.get_world_size(group)
+  return 0, 1
+
+
+# ------------------------------------------------------------------------------------------ view-parallel
+def views_for_rank(num_views: int, rank: int, world: int) -> List[int]:
+  """Round-robin assignment of camera views to ranks."""
+  return list(range(rank, num_views, world))
+
+
+def allreduce_gradients(tensors: Sequence[torch.Tensor], group=None, bucket: bool = True) -> None:
+  """Sum the `.grad` of every tensor over all ranks, in place: the single exchange of the view-parallel path.
+
+  With `bucket` the gradients travel as one flat buffer (one collective launch; NVSwitch makes the cost
+  latency- not link-bound, so fewer, larger messages win); tensors without a gradient contribute zeros."""
+  rank, world = world_info(group)
+  if world == 1:
+    return
+  grads = []
+  for t in tensors:
+    if t.grad is None:
+      t.grad = torch.zeros_like(t)
+    grads.append(t.grad)
+  if not bucket or len(grads) == 1:
+    works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in grads]
+    for w in works:
+      w.wait()
+    return
+  flat = torch.cat([g.reshape(-1) for g in grads])
+  dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+  offset = 0
+  for g in grads:
+    n = g.numel()
+    g.copy_(flat[offset:offset + n].view_as(g))
+    offset += n
+
+
+# ------------------------------------------------------------------------------------------ tile-sharded
+def partition_tiles(tile_ranges: torch.Tensor, world: int) -> torch.Tensor:
+  """Cut the tile grid into `world` contiguous tile-id ranges with (nearly) equal overlap counts.
+
+  tile_ranges: (T,2) or (TH,TW,2) int32 start/end offsets into the sorted overlap list.
+  Returns a (world+1,) int64 CPU tensor of tile-id boundaries: rank r owns tiles [b[r], b[r+1])."""
+  r = tile_ranges.reshape(-1, 2).to(torch.int64)
+  counts = (r[:, 1] - r[:, 0]).clamp_min(0)
+  T = counts.shape[0]
+  csum = torch.cumsum(counts, 0)
+  total = int(csum[-1].item()) if T > 0 else 0
+  bounds = [0]
+  for k in range(1, world):
+    if total == 0:
+      b = (T * k) // world
+    else:
+      target = (total * k + world - 1) // world
+      b = int(torch.searchsorted(csum, torch.tensor(target, device=csum.device, dtype=csum.dtype)).item()) + 1
+    bounds.append(min(max(b, bounds[-1]), T))
+  bounds.append(T)
+  return torch.tensor(bounds, dtype=torch.int64)
+
+
+def mask_tile_ranges(tile_ranges: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+  """Copy of `tile_ranges` with every tile outside [lo, hi) emptied, so a rank's rasteriser CTAs for foreign
+  tiles retire immediately (their pixels stay zero and receive no gradient)."""
+  flat = tile_ranges.reshape(-1, 2)
+  out = torch.zeros_like(flat)
+  out[lo:hi] = flat[lo:hi]
+  return out.view_as(tile_ranges)
+
+
+class _ReduceGradAcrossRanks(torch.autograd.Function):
+  """Identity in the forward; all-reduce(sum) of the incoming gradients in the backward."""
+
+  @staticmethod
+  def forward(ctx, group, *tensors):
+    ctx.group = group
+    return tuple(t.view_as(t) for t in tensors)
+
+  @staticmethod
+  def backward(ctx, *grads):
+    _, world = world_info(ctx.group)
+    if world > 1:
+      grads = [g.contiguous() for g in grads]
+      works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group, async_op=True) for g in grads]
+      for w in works:
+        w.wait()
+    return (None, *grads)
+
+
+def reduce_across_ranks(*tensors: torch.Tensor, group=None):
+  """Mark tensors whose gradients must be summed over ranks (tile-sharded path: packed 2D Gaussians, features)."""
+  return _ReduceGradAcrossRanks.apply(group, *tensors)
+
+
+def render_tile_sharded(gaussians, camera_params, config, use_sh: bool = False, group=None):
+  """Single view split over ranks by tile ranges.  Returns (Rendering, (tile_lo, tile_hi)); the rendering's image
+  holds this rank's tiles only (zeros elsewhere), so a per-pixel loss can be evaluated locally and summed."""
+  from .mapper.tile_mapper import map_to_tiles
+  from .perspective.projection import apply_with_ndc, camera_position
+  from .rasterizer.function import rasterize_with_tiles
+  from .rendering import RenderedPoints, Rendering
+  from .spherical_harmonics import evaluate_sh_at
+
+  rank, world = world_info(group)
+  g2d, depths, indexes, ndc = apply_with_ndc(
+      *gaussians.shape_tensors(), camera_params.T_camera_world, camera_params.projection, camera_params.image_size,
+      camera_params.depth_range, config.blur_cov, config.clamp_margin, config.alpha_threshold)
+  if use_sh:
+    features = evaluate_sh_at(gaussians.feature, gaussians.position.detach(), indexes,
+                              camera_position(camera_params.T_camera_world), unique_indexes=True)
+  else:
+    features = gaussians.feature[indexes]
+  overlap_to_point, tile_ranges = map_to_tiles(g2d, ndc, camera_params.image_size, config)
+  bounds = partition_tiles(tile_ranges, world)
+  lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+  local_ranges = mask_tile_ranges(tile_ranges, lo, hi)
+  g2d_r, features_r = reduce_across_ranks(g2d, features, group=group)
+  raster = rasterize_with_tiles(g2d_r, features_r, overlap_to_point, local_ranges.view(-1, 2),
+                                camera_params.image_size, config)
+  points = RenderedPoints(idx=indexes, depths=depths, gaussians2d=g2d,
+                          _visibility=raster.visibility if config.compute_visibility else None,
+                          _prune_cost=raster.point_heuristic[:, 0] if config.compute_point_heuristic else None,
+                          _split_score=raster.point_heuristic[:, 1] if config.compute_point_heuristic else None,
+                          features=features)
+  return Rendering(image=raster.image, image_weight=raster.image_weight, points=points, camera=camera_params,
+                   config=config), (lo, hi)

@@ -89,6 +89,16 @@ def apply_with_ndc(position, log_scaling, rotation, alpha_logit, T_camera_world,
                                 image_size, depth_range, blur_cov, clamp_margin, alpha_threshold, True)
 
 
+def camera_position(T_camera_world: torch.Tensor) -> torch.Tensor:
+  """World-space camera centre of a (4,4) view matrix, computed on the device in one tiny kernel (no gradient).
+  Same value as CameraParams.camera_position (torch.inverse) without the LU kernels and their host sync."""
+  _lib.require_cuda(T_camera_world=T_camera_world)
+  T = T_camera_world.detach().contiguous()
+  out = torch.empty((3,), dtype=T.dtype, device=T.device)
+  _lib.call(f"gs_camera_position_{_lib.suffix(T.dtype)}", _lib.ptr(T), _lib.ptr(out), _lib.stream_ptr(T.device))
+  return out
+
+
 @beartype
 def project_to_image(gaussians: Gaussians3D, camera_params: CameraParams, config: RasterConfig
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

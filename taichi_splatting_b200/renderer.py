@@ -6,7 +6,7 @@ from beartype import beartype
 from .data_types import Gaussians3D, RasterConfig
 from .mapper.tile_mapper import map_to_tiles
 from .perspective import CameraParams
-from .perspective.projection import apply_with_ndc
+from .perspective.projection import apply_with_ndc, camera_position
 from .rasterizer.function import rasterize_with_tiles, rasterize_with_tiles_and_median
 from .rendering import RenderedPoints, Rendering, ndc_depth
 from .spherical_harmonics import evaluate_sh_at
@@ -25,7 +25,7 @@ def render_gaussians(gaussians: Gaussians3D, camera_params: CameraParams, config
 
   if use_sh:
     features = evaluate_sh_at(gaussians.feature, gaussians.position.detach(), indexes,
-                              camera_params.camera_position, unique_indexes=True)
+                              camera_position(camera_params.T_camera_world), unique_indexes=True)
   else:
     features = gaussians.feature[indexes]
     assert len(features.shape) == 2, f"Features must be (N, C) if use_sh=False, got {features.shape}"
