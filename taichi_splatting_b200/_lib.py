@@ -6,13 +6,14 @@ the built library raises; calling an operator with non-CUDA tensors raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, c_double, c_int32, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libgsplat_b200.so"
+LIB_PATH = _PKG / f"libgsplat_b200{os.environ.get('GS_BUILD_VARIANT', '')}.so"
 
 P, I32, I64, D, SZ = c_void_p, c_int32, c_int64, c_double, c_size_t
 

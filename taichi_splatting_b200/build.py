@@ -16,13 +16,14 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OBJ = PKG / "csrc" / "build"
-LIB = PKG / "libgsplat_b200.so"
+VARIANT = os.environ.get("GS_BUILD_VARIANT", "")          # experiments: alternate .so + extra -D flags
+OBJ = PKG / "csrc" / ("build" + VARIANT)
+LIB = PKG / f"libgsplat_b200{VARIANT}.so"
 SOURCES = ["api.cu", "projection.cu", "sh.cu", "mapper.cu", "raster_generic.cu", "raster_fwd.cu", "raster_bwd.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("GS_BUILD_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -38,7 +38,8 @@ struct Projected {
   real J00, J02, J11, J12;
   real qh[4], qnorm, s[3], Rq[3][3];
   real A[3][3], M[2][3];
-  real a, b, c, tr, gap, sg, sigma[2], u[2], unorm, v1[2], alpha;
+  real a, b, c, tr, gap, sg, sigma[2], u[2], unorm, v1[2], alpha, sgn;
+  bool swapped;           // eigenvector taken from (b, c - l2) instead of (a - l2, b)
 };
 
 template <typename real>
@@ -84,22 +85,36 @@ __device__ __forceinline__ void project_one(const Camera<real> &cam, const real 
     o.M[0][j] = o.J00 * o.A[0][j] + o.J02 * o.A[2][j];
     o.M[1][j] = o.J11 * o.A[1][j] + o.J12 * o.A[2][j];
   }
-  o.a = o.M[0][0] * o.M[0][0] + o.M[0][1] * o.M[0][1] + o.M[0][2] * o.M[0][2] + blur;
+  real a0 = o.M[0][0] * o.M[0][0] + o.M[0][1] * o.M[0][1] + o.M[0][2] * o.M[0][2];
+  real c0 = o.M[1][0] * o.M[1][0] + o.M[1][1] * o.M[1][1] + o.M[1][2] * o.M[1][2];
+  o.a = a0 + blur;
   o.b = o.M[0][0] * o.M[1][0] + o.M[0][1] * o.M[1][1] + o.M[0][2] * o.M[1][2];
-  o.c = o.M[1][0] * o.M[1][0] + o.M[1][1] * o.M[1][1] + o.M[1][2] * o.M[1][2] + blur;
-  // eig (generic.py:217-230)
+  o.c = c0 + blur;
+  // eig (generic.py:217-230), same eigenvalues in a cancellation-free form: det(M M^T) is the sum of the squared
+  // 2x2 minors of M (Cauchy-Binet), gap = tr^2 - 4 det = (a-c)^2 + 4 b^2, lambda2 = det / lambda1.  The reference's
+  // (tr - sqrt(gap)) / 2 loses all fp32 digits for elongated splats.
+  real m01 = o.M[0][0] * o.M[1][1] - o.M[0][1] * o.M[1][0];
+  real m02 = o.M[0][0] * o.M[1][2] - o.M[0][2] * o.M[1][0];
+  real m12 = o.M[0][1] * o.M[1][2] - o.M[0][2] * o.M[1][1];
+  real det = m01 * m01 + m02 * m02 + m12 * m12 + blur * (a0 + c0) + blur * blur;
   o.tr = o.a + o.c;
-  real det = o.a * o.c - o.b * o.b;
-  o.gap = o.tr * o.tr - 4 * det;
-  o.sg = m::sqrt(m::max(o.gap, real(0)));
-  real l1 = (o.tr + o.sg) * real(0.5), l2 = (o.tr - o.sg) * real(0.5);
+  real dac = o.a - o.c;
+  o.gap = dac * dac + 4 * o.b * o.b;
+  o.sg = m::sqrt(o.gap);
+  real l1 = (o.tr + o.sg) * real(0.5), l2 = det / l1;
   o.sigma[0] = m::sqrt(l1); o.sigma[1] = m::sqrt(l2);
-  o.u[0] = o.a - l2; o.u[1] = o.b;
+  // major eigenvector.  The reference normalises (a - l2, b) (generic.py:227), which is 0/0 for an axis-aligned
+  // covariance with a < c (D17) and ill-conditioned near it.  (a - l2, b) and (b, c - l2) are parallel; for a < c
+  // the second is the well-conditioned one, scaled by sign(b) so that v1.x >= 0 exactly as in the reference.
+  o.swapped = o.a < o.c;
+  o.sgn = (o.swapped && o.b < 0) ? real(-1) : real(1);
+  o.u[0] = o.swapped ? o.b : o.a - l2;
+  o.u[1] = o.swapped ? o.c - l2 : o.b;
   o.unorm = m::sqrt(o.u[0] * o.u[0] + o.u[1] * o.u[1]);
   if (o.unorm > 0) {
-    o.v1[0] = o.u[0] / o.unorm; o.v1[1] = o.u[1] / o.unorm;
-  } else {  // D17: axis-aligned / isotropic covariance, 0/0 in the reference
-    o.v1[0] = o.a >= o.c ? real(1) : real(0); o.v1[1] = o.a >= o.c ? real(0) : real(1);
+    o.v1[0] = o.sgn * o.u[0] / o.unorm; o.v1[1] = o.sgn * o.u[1] / o.unorm;
+  } else {  // isotropic covariance: any axis is an eigenvector
+    o.v1[0] = real(1); o.v1[1] = real(0);
   }
   o.alpha = real(1) / (real(1) + m::exp(-logit));
 }
@@ -213,17 +228,21 @@ project_bwd_kernel(const real *__restrict__ position, const real *__restrict__ l
     real d_u[2] = {0, 0};
     if (o.unorm > 0) {
       real dot = o.v1[0] * d_v1[0] + o.v1[1] * d_v1[1];
-      d_u[0] = (d_v1[0] - o.v1[0] * dot) / o.unorm;
-      d_u[1] = (d_v1[1] - o.v1[1] * dot) / o.unorm;
+      d_u[0] = o.sgn * (d_v1[0] - o.v1[0] * dot) / o.unorm;
+      d_u[1] = o.sgn * (d_v1[1] - o.v1[1] * dot) / o.unorm;
     }
-    real d_a = d_u[0], d_b = d_u[1];
-    d_l2 -= d_u[0];
+    real d_a = 0, d_b = 0, d_c_direct = 0;
+    if (o.swapped) {   // u = (b, c - l2)
+      d_b = d_u[0]; d_c_direct = d_u[1]; d_l2 -= d_u[1];
+    } else {           // u = (a - l2, b)
+      d_a = d_u[0]; d_b = d_u[1]; d_l2 -= d_u[0];
+    }
     real d_tr = (d_l1 + d_l2) * real(0.5), d_sg = (d_l1 - d_l2) * real(0.5);
     real d_gap = o.gap > 0 ? d_sg / (2 * o.sg) : real(0);
     d_tr += 2 * o.tr * d_gap;
     real d_det = -4 * d_gap;
     d_a += d_tr + o.c * d_det;
-    real d_c = d_tr + o.a * d_det;
+    real d_c = d_c_direct + d_tr + o.a * d_det;
     d_b += -2 * o.b * d_det;
 
     real dM[2][3];

@@ -60,8 +60,11 @@ struct BwdSmem {
   int warp_done[8];
 };
 
+#ifndef GS_BWD_MIN_BLOCKS
+#define GS_BWD_MIN_BLOCKS 4
+#endif
 template <int F, bool GP, bool GF, bool HEUR>
-__global__ void __launch_bounds__(kBatchB, 3)
+__global__ void __launch_bounds__(kBatchB, GS_BWD_MIN_BLOCKS)
 raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ features,
                   const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
                   const float *__restrict__ image, const float *__restrict__ grad_image, RasterParams<float> P,

@@ -93,8 +93,11 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
   v[0] += __shfl_xor_sync(full, v[0], 1);
 }
 
+#ifndef GS_FWD_MIN_BLOCKS
+#define GS_FWD_MIN_BLOCKS 3
+#endif
 template <int F, bool VIS, bool BLEND, bool MEDIAN>
-__global__ void __launch_bounds__(kBatch)
+__global__ void __launch_bounds__(kBatch, GS_FWD_MIN_BLOCKS)
 raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ features,
                   const float *__restrict__ depths, const int32_t *__restrict__ ranges,
                   const int32_t *__restrict__ overlap_to_point, RasterParams<float> P, float median_lim,

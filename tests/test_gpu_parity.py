@@ -78,6 +78,11 @@ def test_projection_vs_oracle_random(ts):
     ref = [a.clone().requires_grad_(True) for a in args64]
     rp, rd, ri = torch_ops.project(*ref, cam.image_size, cam.depth_range, blur_cov=0.3)
     w = torch.rand(rp.shape, dtype=torch.float64)
+    # d(axis, sigma)/d(cov) is singular at an isotropic covariance (eig, generic.py:217-230: 1/sqrt(gap), 1/|u|);
+    # nearly round splats are ill-conditioned in fp32 for the reference too, so they carry no axis/sigma loss here
+    s1, s2 = rp[:, 4].detach(), rp[:, 5].detach()
+    round_ = (s1 * s1 - s2 * s2) / (s1 * s1 + s2 * s2) < 0.05
+    w[round_, 2:6] = 0
     ((rp * w).sum() + rd.sum()).backward()
     ins = [a.float().to(DEV).requires_grad_(True) for a in args64]
     pts, depth, idx = ts.perspective.apply(*ins, cam.image_size, cam.depth_range, blur_cov=0.3)
@@ -87,7 +92,13 @@ def test_projection_vs_oracle_random(ts):
     for a, b, name in zip(ins, ref, PROJ_NAMES):
       # fp32 reverse chain (eigen-decomposition, 1/z^2 terms) vs the fp64 truth; the fp64 instantiation of the
       # same kernel matches the reference to 1e-9 (test_projection_golden)
-      assert rel_err(a.grad, b.grad) < 5e-3, (seed, name, rel_err(a.grad, b.grad))
+      e = rel_err(a.grad, b.grad)
+      if e >= 5e-3:
+        d = (a.grad.cpu().double() - b.grad).abs().reshape(a.grad.shape[0], -1).max(1).values if a.grad.ndim > 1 else None
+        worst = int(d.argmax()) if d is not None else -1
+        print("worst row", worst, a.grad[worst].tolist() if worst >= 0 else None, b.grad[worst].tolist() if worst >= 0 else None,
+              [x[worst].tolist() for x in args64[:4]] if worst >= 0 else None)
+      assert e < 5e-3, (seed, name, e)
 
 
 def test_projection_edge_cases(ts):
@@ -339,3 +350,35 @@ def test_render_gaussians_vs_oracle_pipeline(ts, use_sh):
   assert rel_err(camera.T_camera_world.grad, ref.grads["T_camera_world"]) < 1e-2
   assert rel_err(camera.projection.grad, ref.grads["projection"]) < 1e-2
   assert rel_err(out.points.prune_cost, ref.heuristic[:, 0]) < 1e-3
+
+
+def test_fused_render_equals_operator_composition(ts):
+  """render_gaussians (one fused autograd node) vs the reference-style operator chain: same kernels, so outputs are
+  identical and gradients agree to atomic-order rounding; also gradients through points.depths / features."""
+  from taichi_splatting_b200.renderer import render_gaussians_unfused
+  torch.manual_seed(9)
+  size = (200, 136)
+  cam = random_data.fixed_camera(size, yaw_deg=3.0)
+  for use_sh in (False, True):
+    g = random_data.random_3d_gaussians(15000, cam, scale_factor=1.5, margin=0.3, sh_degree=2 if use_sh else None)
+    cfg = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True)
+    R = torch.rand((size[1], size[0], 3), device=DEV)
+    results = []
+    for fn in (ts.render_gaussians, render_gaussians_unfused):
+      gauss = ts.Gaussians3D(**{k: v.to(DEV).requires_grad_(True) for k, v in vars(g).items()})
+      camera = ts.perspective.CameraParams(projection=cam.projection.to(DEV).requires_grad_(True),
+                                           T_camera_world=cam.T_camera_world.to(DEV).requires_grad_(True),
+                                           near_plane=cam.near_plane, far_plane=cam.far_plane, image_size=size)
+      out = fn(gauss, camera, cfg, use_sh=use_sh, render_median_depth=True)
+      loss = (out.image * R).sum() + 0.1 * out.points.depths.sum() + 0.01 * (out.points.features ** 2).sum()
+      loss.backward()
+      results.append((out, gauss, camera))
+    (a, ga, ca), (b, gb, cb) = results
+    assert torch.equal(a.points.idx, b.points.idx) and torch.equal(a.image, b.image)
+    assert torch.equal(a.image_weight, b.image_weight) and torch.equal(a.median_depth_image, b.median_depth_image)
+    assert rel_err(a.points.visibility, b.points.visibility) < 1e-6
+    for k in ("position", "log_scaling", "rotation", "alpha_logit", "feature"):
+      assert rel_err(getattr(ga, k).grad, getattr(gb, k).grad) < 1e-5, k
+    assert rel_err(ca.T_camera_world.grad, cb.T_camera_world.grad) < 1e-4
+    assert rel_err(ca.projection.grad, cb.projection.grad) < 1e-4
+    assert rel_err(a.points.split_score, b.points.split_score) < 1e-5
