@@ -15,8 +15,8 @@
 //     dL/dalpha_point = M0 / alpha_point;
 //   * because the moment multipliers {1, lx, ...} are per-lane constants, each lane keeps them in a
 //     lane-dependent (XOR-permuted) register order, which makes the transposed-butterfly warp reduction
-//     select-free: v[r] += shfl_xor(v[r + half], off).  8 moments cost 7+2 shuffles, 4 feature slots 3+3,
-//     the 2 heuristics 1+4 -- against 5 shuffles per value for a plain tree;
+//     select-free: v[r] += shfl_xor(v[r + half], off); the three value types (8 moment slots, 4 feature slots,
+//     2 heuristics) then share one 3-shuffle tail -- 15 shuffles for 11 sums, against 5 per value for a tree;
 //   * the inner loop is branch-free; one shared-memory atomic instruction per (warp, splat); one global
 //     float atomic per (splat, tile, component) at the end of each 256-splat batch.
 #include "raster_common.cuh"
@@ -130,11 +130,13 @@ raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
       }
   }
   // which accumulator slot this lane adds after the reductions (-1: none)
+  const int b2 = (lane >> 1) & 1;
   int my_slot = -1;
-  if ((lane & 3) == 0) my_slot = GP && mA < 6 ? mA : -1;
-  else if ((lane & 3) == 1 && b4 == 0) my_slot = GF && mB < F ? L::kFeat + mB : -1;
-  else if ((lane & 3) == 2 && b4 == 0 && b8 == 0) my_slot = HEUR ? L::kHeur + b16 : -1;
-  const int my_role = lane & 3;
+  if ((lane & 1) == 0) {
+    if (b2 == 0) my_slot = GP && mA < 6 ? mA : -1;                          // moments
+    else if (b4 == 0) my_slot = GF && mB < F ? L::kFeat + mB : -1;          // feature gradients
+    else if (b8 == 0) my_slot = HEUR ? L::kHeur + b16 : -1;                 // heuristics
+  }
 
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
   if (lane == 0) sm.warp_done[warp] = 0;
@@ -232,40 +234,35 @@ raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
       float G = has_grad ? B.z * alpha_grad : 0.f;
       float Gp = G * ga;
 
-      float add_val = 0.f;
-      if (GP) {   // six moments (two spare slots) : 7 + 2 shuffles
+      // type-specific halving stages (select-free thanks to the XOR-permuted multipliers) ...
+      float ra = 0.f, rb = 0.f, rc = 0.f;
+      if (GP) {   // six moments (two spare slots): 4 + 2 + 1 shuffles -> sum over 8 lanes of moment mA
         float v0 = Gp * coefA[0], v1 = Gp * coefA[1], v2 = Gp * coefA[2], v3 = Gp * coefA[3];
         float v4 = Gp * coefA[4], v5 = Gp * coefA[5], v6 = Gp * coefA[6], v7 = Gp * coefA[7];
         v0 += __shfl_xor_sync(full, v4, 16); v1 += __shfl_xor_sync(full, v5, 16);
         v2 += __shfl_xor_sync(full, v6, 16); v3 += __shfl_xor_sync(full, v7, 16);
         v0 += __shfl_xor_sync(full, v2, 8); v1 += __shfl_xor_sync(full, v3, 8);
-        v0 += __shfl_xor_sync(full, v1, 4);
-        v0 += __shfl_xor_sync(full, v0, 2);
-        v0 += __shfl_xor_sync(full, v0, 1);
-        add_val = v0;
+        ra = v0 + __shfl_xor_sync(full, v1, 4);
       }
-      if (GF) {           // weight * dL/dimage : 3 + 3 shuffles
+      if (GF) {   // weight * dL/dimage: 2 + 1 shuffles -> sum over 4 lanes of feature slot mB
         float v0 = weight * gpixB[0], v1 = weight * gpixB[1], v2 = weight * gpixB[2], v3 = weight * gpixB[3];
         v0 += __shfl_xor_sync(full, v2, 16); v1 += __shfl_xor_sync(full, v3, 16);
-        v0 += __shfl_xor_sync(full, v1, 8);
-        v0 += __shfl_xor_sync(full, v0, 4);
-        v0 += __shfl_xor_sync(full, v0, 2);
-        v0 += __shfl_xor_sync(full, v0, 1);
-        add_val = my_role == 1 ? v0 : add_val;
+        rb = v0 + __shfl_xor_sync(full, v1, 8);
       }
-      if (HEUR) {         // [ (alpha dL/dalpha)^2 , |alpha dL/dalpha dpdf/dmean|_1 ] : 1 + 4 shuffles
+      if (HEUR) {  // [(alpha dL/dalpha)^2, |alpha dL/dalpha dpdf/dmean|_1]: 1 + 1 shuffles -> sum over 4 lanes
         const float inv_k2 = 1.0f / (kExpScaleB * kExpScaleB);
         float a1 = Gp * tx, a2 = Gp * ty;   // each carries one exp-scale factor k, as do A.zw / B.xy
         float h0 = G * G;
         float h1 = (fabsf(a1 * A.z + a2 * B.x) + fabsf(a1 * A.w + a2 * B.y)) * inv_k2;
         float v0 = b16 ? h1 : h0, v1 = b16 ? h0 : h1;
         v0 += __shfl_xor_sync(full, v1, 16);
-        v0 += __shfl_xor_sync(full, v0, 8);
-        v0 += __shfl_xor_sync(full, v0, 4);
-        v0 += __shfl_xor_sync(full, v0, 2);
-        v0 += __shfl_xor_sync(full, v0, 1);
-        add_val = my_role == 2 ? v0 : add_val;
+        rc = v0 + __shfl_xor_sync(full, v0, 8);
       }
+      // ... then ONE shared tail for the three partial results: at each remaining lane bit two value types are
+      // exchanged transposed (keep one, send the other), so 3 shuffles finish all of them.
+      float x = (b4 ? rc : rb) + __shfl_xor_sync(full, b4 ? rb : rc, 4);   // b4=0 lanes: features, b4=1: heuristics
+      float y = (b2 ? x : ra) + __shfl_xor_sync(full, b2 ? ra : x, 2);      // b2=0 lanes: moments,  b2=1: x
+      const float add_val = y + __shfl_xor_sync(full, y, 1);
       if (my_slot >= 0 && add_val != 0.f) atomicAdd(&sm.acc[j * L::kStride + my_slot], add_val);
       if (__all_sync(full, total_weight >= sat)) break;
     }
