@@ -1,0 +1,96 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): torchrun-style workers over NCCL.
+
+ * tile-sharded single view: union of the per-rank image strips == single-GPU image, and every rank ends with the
+   single-GPU parameter gradients (the one all-reduce of packed-2D / feature gradients).
+ * view-parallel: all-reduced gradients == sum of the per-view single-GPU gradients.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    return s.getsockname()[1]
+
+
+def _scene(ts, dev, yaw=0.0):
+  from taichi_splatting_b200.benchmarks import scenes
+  size = (320, 208)
+  cam = scenes.benchmark_camera(size, yaw_deg=yaw).to(device=dev)
+  cloud = scenes.random_3d_gaussians(30000, scenes.benchmark_camera(size), scale_factor=1.5, sh_degree=1, seed=3)
+  return cloud.to(dev).requires_grad_(True), cam, size
+
+
+def _rel(a, b):
+  return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _worker(rank, world, port, results):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.cuda.set_device(rank)
+  dev = torch.device("cuda", rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+  try:
+    import taichi_splatting_b200 as ts
+    from taichi_splatting_b200 import parallel
+    cfg = ts.RasterConfig()
+    names = ("position", "log_scaling", "rotation", "alpha_logit", "feature")
+    R = torch.rand((208, 320, 3), generator=torch.Generator().manual_seed(0)).to(dev)
+
+    # ---- single-GPU reference on every rank ----
+    cloud, cam, size = _scene(ts, dev)
+    ref = ts.render_gaussians(cloud, cam, cfg, use_sh=True)
+    (ref.image * R).sum().backward()
+    ref_grads = {k: getattr(cloud, k).grad.clone() for k in names}
+
+    # ---- tile-sharded ----
+    cloud2, cam2, _ = _scene(ts, dev)
+    out, (lo, hi) = parallel.render_tile_sharded(cloud2, cam2, cfg, use_sh=True)
+    (out.image * R).sum().backward()
+    full = out.image.detach().clone()
+    dist.all_reduce(full)                       # strips are disjoint, so the sum is the union
+    assert _rel(full, ref.image.detach()) < 1e-6, _rel(full, ref.image.detach())
+    for k in names:
+      assert _rel(getattr(cloud2, k).grad, ref_grads[k]) < 2e-5, (k, _rel(getattr(cloud2, k).grad, ref_grads[k]))
+    assert 0 <= lo <= hi
+
+    # ---- view-parallel ----
+    per_view = []
+    for r in range(world):
+      c, cm, _ = _scene(ts, dev, yaw=2.0 * r)
+      o = ts.render_gaussians(c, cm, cfg, use_sh=True)
+      (o.image * R).sum().backward()
+      per_view.append({k: getattr(c, k).grad for k in names})
+    c, cm, _ = _scene(ts, dev, yaw=2.0 * rank)
+    o = ts.render_gaussians(c, cm, cfg, use_sh=True)
+    (o.image * R).sum().backward()
+    parallel.allreduce_gradients([getattr(c, k) for k in names])
+    for k in names:
+      want = sum(pv[k] for pv in per_view)
+      assert _rel(getattr(c, k).grad, want) < 2e-5, (k, _rel(getattr(c, k).grad, want))
+    results[rank] = "ok"
+  finally:
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharding_matches_single_gpu():
+  if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+    pytest.skip("needs >= 2 CUDA devices")
+  world, port = 2, _free_port()
+  ctx = mp.get_context("spawn")
+  results = ctx.Manager().dict()
+  procs = [ctx.Process(target=_worker, args=(r, world, port, results)) for r in range(world)]
+  for p in procs:
+    p.start()
+  for p in procs:
+    p.join(timeout=600)
+    assert p.exitcode == 0
+  assert dict(results) == {0: "ok", 1: "ok"}
