@@ -154,6 +154,26 @@ int gs_sort_pairs(const void *keys_in, const int32_t *values_in, void *keys_out,
 int gs_tile_ranges(const void *sorted_keys, int64_t k, int32_t key_bytes, int32_t *tile_ranges /* (T,2) */,
                    int64_t num_tiles, void *stream);
 
+/* Two-level ordering: identical final order to gs_tile_emit_keys + gs_sort_pairs(48 bits), with the depth passes
+ * run on the V Gaussians instead of the K overlaps (an LSD sort over tile|depth == stable sort by depth, then
+ * stable sort by tile; every overlap of a Gaussian shares its depth):
+ *   gs_depth_order           order (V) i32 = Gaussian indexes sorted by (depth bits, index)
+ *   gs_tile_count_ordered    counts[r] for Gaussian order[r]
+ *   gs_tile_emit_ordered     tile_keys (K) u32 = tile id, overlap_to_point (K), emitted in depth order
+ *   gs_sort_pairs(tile_keys, 4 bytes, bits [0, ceil(log2 T)))  -- stable
+ *   gs_tile_ranges_from_tiles                                                                          */
+int gs_depth_order_workspace_bytes(int64_t v, size_t *bytes);
+int gs_depth_order(const float *depths, int64_t v, int32_t use_depth16, int32_t *order, void *workspace,
+                   size_t workspace_bytes, void *stream);
+int gs_tile_count_ordered(const float *gaussians, const int32_t *order, int64_t v, int32_t width_padded,
+                          int32_t height_padded, int32_t tile_size, double alpha_threshold, int32_t *counts,
+                          void *stream);
+int gs_tile_emit_ordered(const float *gaussians, const int32_t *order, const int32_t *cum, int64_t v,
+                         int32_t width_padded, int32_t height_padded, int32_t tile_size, double alpha_threshold,
+                         uint32_t *tile_keys, int32_t *overlap_to_point, void *stream);
+int gs_tile_ranges_from_tiles(const uint32_t *sorted_tiles, int64_t k, int32_t *tile_ranges, int64_t num_tiles,
+                              void *stream);
+
 /* ---- R8: rasteriser forward ---------------------------------------------------------------------
  * replaces _forward_kernel (rasterizer/forward.py:22-135).  image (H,W,F), image_alpha (H,W),
  * visibility (V) zero-initialised by the caller (NULL unless compute_visibility).            */

@@ -54,6 +54,11 @@ SIGNATURES = {
     "gs_sort_pairs_workspace_bytes": ([I64, I32, POINTER(SZ)], c_int32),
     "gs_sort_pairs": ([P, P, P, P, I64, I32, I32, I32, P, SZ, P], c_int32),
     "gs_tile_ranges": ([P, I64, I32, P, I64, P], c_int32),
+    "gs_depth_order_workspace_bytes": ([I64, POINTER(SZ)], c_int32),
+    "gs_depth_order": ([P, I64, I32, P, P, SZ, P], c_int32),
+    "gs_tile_count_ordered": ([P, P, I64, I32, I32, I32, D, P, P], c_int32),
+    "gs_tile_emit_ordered": ([P, P, P, I64, I32, I32, I32, D, P, P, P], c_int32),
+    "gs_tile_ranges_from_tiles": ([P, I64, P, I64, P], c_int32),
     "gs_raster_fwd_f32": (_RASTER_FWD, c_int32), "gs_raster_fwd_f64": (_RASTER_FWD, c_int32),
     "gs_raster_fwd_median_f32": ([P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_f32": (_RASTER_BWD, c_int32), "gs_raster_bwd_f64": (_RASTER_BWD, c_int32),
@@ -94,7 +99,8 @@ OWN_KERNELS = {
     "gs_project_cull_f32": 1, "gs_project_cull_f64": 1, "gs_project_write_f32": 1, "gs_project_write_f64": 1,
     "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_camera_position_f32": 1, "gs_camera_position_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
     "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
-    "gs_tile_ranges": 1, "gs_raster_fwd_f32": 1, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 1, "gs_raster_bwd_f32": 1,
+    "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1,
+    "gs_tile_ranges_from_tiles": 1, "gs_raster_fwd_f32": 1, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 1, "gs_raster_bwd_f32": 1,
     "gs_raster_bwd_f64": 1,
 }
 

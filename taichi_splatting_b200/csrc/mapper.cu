@@ -108,6 +108,52 @@ tile_emit_kernel(const float *__restrict__ gaussians, const float *__restrict__ 
       }
 }
 
+// ---- two-level ordering (same final order as the reference's 48-bit LSD sort, far less sort traffic) -----------
+// An LSD radix sort over (tile | depth) is a stable sort by depth followed by a stable sort by tile.  All overlaps
+// of one Gaussian share its depth, so the depth passes can run on the V Gaussians BEFORE the expansion to K
+// overlaps: sort (depth bits, index) once, emit the overlaps in that order with the tile id as the only key, then
+// a stable sort on ceil(log2 T) bits finishes it.  Ties keep ascending Gaussian index in both schemes.
+template <bool DEPTH16>
+__global__ void depth_key_kernel(const float *__restrict__ depths, int64_t v, uint32_t *__restrict__ keys,
+                                 int32_t *__restrict__ ids) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= v) return;
+  float d = depths[i];
+  keys[i] = DEPTH16 ? (uint32_t)__fmul_rn(fminf(fmaxf(d, 0.0f), 1.0f), 65535.0f) : __float_as_uint(d);
+  ids[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(128)
+tile_count_ordered_kernel(const float *__restrict__ gaussians, const int32_t *__restrict__ order, int64_t v, int w_pad,
+                          int h_pad, int ts, float thr, int32_t *__restrict__ counts) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= v) return;
+  ObbQuery q = obb_grid_query(gaussians + 7 * (int64_t)order[r], w_pad, h_pad, ts, thr);
+  int c = 0;
+  for (int u = 0; u < q.spanx; ++u)
+    for (int w = 0; w < q.spany; ++w) c += test_tile(q, u, w, ts) ? 1 : 0;
+  counts[r] = c;
+}
+
+__global__ void __launch_bounds__(128)
+tile_emit_ordered_kernel(const float *__restrict__ gaussians, const int32_t *__restrict__ order,
+                         const int32_t *__restrict__ cum, int64_t v, int w_pad, int h_pad, int ts, float thr,
+                         uint32_t *__restrict__ tile_keys, int32_t *__restrict__ overlap_to_point) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= v) return;
+  int32_t i = order[r];
+  ObbQuery q = obb_grid_query(gaussians + 7 * (int64_t)i, w_pad, h_pad, ts, thr);
+  int tiles_wide = w_pad / ts;
+  int64_t k = cum[r];
+  for (int u = 0; u < q.spanx; ++u)
+    for (int w = 0; w < q.spany; ++w)
+      if (test_tile(q, u, w, ts)) {
+        tile_keys[k] = (uint32_t)((q.minx + u) + (q.miny + w) * tiles_wide);
+        overlap_to_point[k] = i;
+        ++k;
+      }
+}
+
 __global__ void finish_scan_kernel(const int32_t *__restrict__ counts, int32_t *__restrict__ cum, int64_t v,
                                    int32_t *__restrict__ total_dev) {
   // cum[0..v-1] holds the exclusive scan; complete entry v (cuda_lib/full_cumsum.cu:6-10)
@@ -238,6 +284,73 @@ extern "C" int gs_tile_ranges(const void *sorted_keys, int64_t k, int32_t key_by
     gs::tile_ranges_kernel<uint64_t><<<grid, 256, 0, stream>>>((const uint64_t *)sorted_keys, k, 32, tile_ranges);
   else
     gs::tile_ranges_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t *)sorted_keys, k, 16, tile_ranges);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_depth_order_workspace_bytes(int64_t v, size_t *bytes) {
+  size_t temp = 0;
+  if (v > 0)
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, (int)v);
+  size_t n = gs::align_up((size_t)(v > 0 ? v : 0) * 4, 256);
+  *bytes = 3 * n + gs::align_up(temp, 256) + 256;   // keys in/out, ids in, cub temp
+  return GS_OK;
+}
+
+extern "C" int gs_depth_order(const float *depths, int64_t v, int32_t use_depth16, int32_t *order, void *workspace,
+                              size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CHECK_ARG(v >= 0 && v < (int64_t(1) << 31), "depth_order: v out of range");
+  if (v == 0) return GS_OK;
+  size_t need = 0;
+  gs_depth_order_workspace_bytes(v, &need);
+  if (workspace_bytes < need) {
+    gs::set_error("depth_order: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return GS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  size_t n = gs::align_up((size_t)v * 4, 256);
+  uint32_t *keys_in = (uint32_t *)workspace, *keys_out = (uint32_t *)((char *)workspace + n);
+  int32_t *ids_in = (int32_t *)((char *)workspace + 2 * n);
+  void *temp = (char *)workspace + 3 * n;
+  size_t temp_bytes = workspace_bytes - 3 * n;
+  unsigned grid = (unsigned)gs::ceil_div(v, 256);
+  if (use_depth16) gs::depth_key_kernel<true><<<grid, 256, 0, stream>>>(depths, v, keys_in, ids_in);
+  else gs::depth_key_kernel<false><<<grid, 256, 0, stream>>>(depths, v, keys_in, ids_in);
+  GS_LAUNCH_CHECK();
+  GS_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, ids_in, order, (int)v, 0,
+                                          use_depth16 ? 16 : 32, stream));
+  return GS_OK;
+}
+
+extern "C" int gs_tile_count_ordered(const float *gaussians, const int32_t *order, int64_t v, int32_t w_pad,
+                                     int32_t h_pad, int32_t ts, double alpha_threshold, int32_t *counts, void *stream) {
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_count: image %dx%d not padded to tile %d", w_pad, h_pad, ts);
+  GS_CHECK_ARG((int64_t)(w_pad / ts) * (h_pad / ts) < 65535, "tile dimensions (%d, %d) exceed maximum tile count (16 bit id), try increasing tile_size", h_pad / ts, w_pad / ts);
+  if (v == 0) return GS_OK;
+  gs::tile_count_ordered_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
+      gaussians, order, v, w_pad, h_pad, ts, (float)alpha_threshold, counts);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_tile_emit_ordered(const float *gaussians, const int32_t *order, const int32_t *cum, int64_t v,
+                                    int32_t w_pad, int32_t h_pad, int32_t ts, double alpha_threshold,
+                                    uint32_t *tile_keys, int32_t *overlap_to_point, void *stream) {
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_emit: image not padded to tile size");
+  if (v == 0) return GS_OK;
+  gs::tile_emit_ordered_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
+      gaussians, order, cum, v, w_pad, h_pad, ts, (float)alpha_threshold, tile_keys, overlap_to_point);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_tile_ranges_from_tiles(const uint32_t *sorted_tiles, int64_t k, int32_t *tile_ranges,
+                                         int64_t num_tiles, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * num_tiles, stream));
+  if (k == 0) return GS_OK;
+  gs::tile_ranges_kernel<uint32_t><<<(unsigned)gs::ceil_div(k, 256), 256, 0, stream>>>(sorted_tiles, k, 0, tile_ranges);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

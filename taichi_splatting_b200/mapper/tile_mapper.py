@@ -34,13 +34,86 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor, image_size: Tuple
   assert gaussians.ndim == 2 and gaussians.shape[1] == 7, f"gaussians must be Nx7 got {gaussians.shape}"
   assert depth.ndim == 2 and depth.shape[1] == 1, f"depths must be Nx1, got {depth.shape}"
   assert gaussians.shape[0] == depth.shape[0], f"size mismatch {gaussians.shape} vs {depth.shape}"
-  o2p, ranges, _, _ = map_to_tiles_full(gaussians, depth, image_size, config, use_depth16)
+  _lib.require_cuda(gaussians=gaussians, depth=depth)
+  with torch.no_grad():
+    g = gaussians.detach().to(torch.float32).contiguous()   # the mapper is f32-only (reference :14)
+    d = depth.detach().to(torch.float32).contiguous().view(-1)
+    o2p, ranges, _, _, _ = bin_and_sort(g, d, image_size, config, use_depth16)
   return o2p, ranges
 
 
-def map_to_tiles_full(gaussians, depth, image_size, config, use_depth16=False):
-  """As map_to_tiles, also returning the sorted keys and per-Gaussian counts (for tests / diagnostics)."""
+def tile_bits(num_tiles: int) -> int:
+  return max(1, (max(num_tiles, 1) - 1).bit_length())
+
+
+def bin_and_sort(g: torch.Tensor, d: torch.Tensor, image_size, config, use_depth16: bool = False):
+  """The two-level ordering on contiguous fp32 inputs g (V,7), d (V,) -> (overlap_to_point (K,), tile_ranges
+  (TH,TW,2), sorted tile ids (K,) int32, order (V,) int32, counts in depth order (V,) int32).
+
+  Same final order as the reference's single 48-bit LSD radix sort over (tile | depth) (tile_mapper.py:148-157):
+  such a sort is a stable sort by depth followed by a stable sort by tile, and all overlaps of one Gaussian share
+  its depth, so the depth passes run on the V Gaussians before the expansion to K overlaps (gs_depth_order), the
+  overlaps are emitted in that order keyed by tile id only, and one stable sort on ceil(log2 T) bits finishes it."""
+  device = g.device
+  ts = config.tile_size
+  w_pad, h_pad = pad_to_tile(image_size, ts)
+  tile_shape = (h_pad // ts, w_pad // ts)
+  num_tiles = tile_shape[0] * tile_shape[1]
+  assert num_tiles < MAX_TILES, \
+      f"tile dimensions {tile_shape} for image size {image_size} exceed maximum tile count (16 bit id), try increasing tile_size"
+  v = g.shape[0]
+  call, ptr = _lib.call, _lib.ptr
+  stream = _lib.stream_ptr(device)
+  thr = float(config.alpha_threshold)
+  nbytes = _lib.c_size_t()
+
+  order = torch.empty((v,), dtype=torch.int32, device=device)
+  call("gs_depth_order_workspace_bytes", v, nbytes)
+  ws = _lib.workspace(nbytes.value, device)
+  call("gs_depth_order", ptr(d), v, int(use_depth16), ptr(order), ws.data_ptr(), ws.numel(), stream)
+  counts = torch.empty((v,), dtype=torch.int32, device=device)
+  cum = torch.empty((v + 1,), dtype=torch.int32, device=device)
+  call("gs_tile_count_ordered", ptr(g), ptr(order), v, w_pad, h_pad, ts, thr, ptr(counts), stream)
+  call("gs_tile_scan_workspace_bytes", v, nbytes)
+  ws2 = _lib.workspace(nbytes.value, device)
+  word = _lib.host_word(device)
+  call("gs_tile_scan", ptr(counts), v, ptr(cum), ws2.data_ptr(), ws2.numel(), word.data_ptr(), stream)
+  tile_ranges = torch.empty((*tile_shape, 2), dtype=torch.int32, device=device)
+  k = _lib.read_host_word(word, device)     # the one host read of the mapper (reference: two device-wide syncs)
+
+  tiles = torch.empty((2, k), dtype=torch.int32, device=device)
+  o2p = torch.empty((2, k), dtype=torch.int32, device=device)
+  if k > 0:
+    call("gs_tile_emit_ordered", ptr(g), ptr(order), ptr(cum), v, w_pad, h_pad, ts, thr, ptr(tiles[0]), ptr(o2p[0]), stream)
+    call("gs_sort_pairs_workspace_bytes", k, 4, nbytes)
+    ws3 = _lib.workspace(nbytes.value, device)
+    call("gs_sort_pairs", ptr(tiles[0]), ptr(o2p[0]), ptr(tiles[1]), ptr(o2p[1]), k, 4, 0, tile_bits(num_tiles),
+         ws3.data_ptr(), ws3.numel(), stream)
+  call("gs_tile_ranges_from_tiles", ptr(tiles[1]), k, ptr(tile_ranges), num_tiles, stream)
+  return o2p[1], tile_ranges, tiles[1], order, counts
+
+
+def map_to_tiles_full(gaussians, depth, image_size, config, use_depth16=False, two_level=True):
+  """As map_to_tiles, also returning the sorted (tile | depth) keys and per-Gaussian counts (tests / diagnostics).
+  two_level=False runs the reference's own sequence (count, scan, 64-bit keys, one 48-bit sort, ranges)."""
   _lib.require_cuda(gaussians=gaussians, depth=depth)
+  if two_level:
+    with torch.no_grad():
+      g = gaussians.detach().to(torch.float32).contiguous()
+      d = depth.detach().to(torch.float32).contiguous().view(-1)
+      o2p, tile_ranges, tiles, order, counts_sorted = bin_and_sort(g, d, image_size, config, use_depth16)
+      counts = torch.empty_like(counts_sorted)
+      counts[order.long()] = counts_sorted
+      if use_depth16:
+        dbits = (d.clamp(0, 1) * 65535.0).to(torch.int32)
+        keys = (tiles << 16) | dbits[o2p.long()]
+      else:
+        keys = (tiles.to(torch.int64) << 32) | (d.view(torch.int32)[o2p.long()].to(torch.int64) & 0xFFFFFFFF)
+      return o2p, tile_ranges, keys, counts
+  return _map_to_tiles_single_sort(gaussians, depth, image_size, config, use_depth16)
+
+
+def _map_to_tiles_single_sort(gaussians, depth, image_size, config, use_depth16=False):
   device = gaussians.device
   ts = config.tile_size
   w_pad, h_pad = pad_to_tile(image_size, ts)

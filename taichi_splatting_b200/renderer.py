@@ -7,7 +7,7 @@ from beartype import beartype
 
 from . import _lib
 from .data_types import Gaussians3D, RasterConfig
-from .mapper.tile_mapper import MAX_TILES, key_bits, map_to_tiles, pad_to_tile
+from .mapper.tile_mapper import bin_and_sort, map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import apply_with_ndc, camera_position
 from .rasterizer.function import fused_median_supported, rasterize_with_tiles, rasterize_with_tiles_and_median
@@ -70,36 +70,11 @@ class _RenderFunction(torch.autograd.Function):
       features = feature_c[indexes]
     F = features.shape[1]
 
-    # ---- tile mapper (fp32 only, like the reference) ----
-    ts_ = config.tile_size
-    w_pad, h_pad = pad_to_tile((w, h), ts_)
-    tile_shape = (h_pad // ts_, w_pad // ts_)
-    num_tiles = tile_shape[0] * tile_shape[1]
-    assert num_tiles < MAX_TILES, \
-        f"tile dimensions {tile_shape} for image size {(w, h)} exceed maximum tile count (16 bit id), try increasing tile_size"
+    # ---- tile mapper (fp32 only, like the reference): two-level ordering, one host read (K) ----
     g32 = g2d if dtype == torch.float32 else g2d.float()
-    d32 = ndc if dtype == torch.float32 else ndc.float()
-    counts = torch.empty((v,), dtype=torch.int32, device=device)
-    cum = torch.empty((v + 1,), dtype=torch.int32, device=device)
-    call("gs_tile_count", ptr(g32), v, w_pad, h_pad, ts_, thr, ptr(counts), stream)
-    call("gs_tile_scan_workspace_bytes", v, nbytes)
-    ws = _lib.workspace(nbytes.value, device)
-    call("gs_tile_scan", ptr(counts), v, ptr(cum), ws.data_ptr(), ws.numel(), word.data_ptr(), stream)
-    tile_ranges = torch.empty((*tile_shape, 2), dtype=torch.int32, device=device)
-    key_dtype, key_bytes = (torch.int32, 4) if use_depth16 else (torch.int64, 8)
-    k = _lib.read_host_word(word, device)
-
-    keys = torch.empty((2, k), dtype=key_dtype, device=device)
-    o2p = torch.empty((2, k), dtype=torch.int32, device=device)
-    if k > 0:
-      call("gs_tile_emit_keys", ptr(g32), ptr(d32), ptr(cum), v, w_pad, h_pad, ts_, thr, int(use_depth16), ptr(keys[0]),
-           ptr(o2p[0]), stream)
-      call("gs_sort_pairs_workspace_bytes", k, key_bytes, nbytes)
-      ws = _lib.workspace(nbytes.value, device)
-      call("gs_sort_pairs", ptr(keys[0]), ptr(o2p[0]), ptr(keys[1]), ptr(o2p[1]), k, key_bytes, 0,
-           key_bits(num_tiles, use_depth16), ws.data_ptr(), ws.numel(), stream)
-    call("gs_tile_ranges", ptr(keys[1]), k, key_bytes, ptr(tile_ranges), num_tiles, stream)
-    overlap_to_point = o2p[1]
+    d32 = (ndc if dtype == torch.float32 else ndc.float()).view(-1)
+    overlap_to_point, tile_ranges, _, _, _ = bin_and_sort(g32, d32, (w, h), config, use_depth16)
+    k = overlap_to_point.shape[0]
     ranges = tile_ranges.view(-1, 2)
 
     # ---- rasteriser (+ fused median depth) ----

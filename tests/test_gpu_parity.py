@@ -38,6 +38,20 @@ def rel_err(a, b):
   return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def assert_close_up_to_threshold_flips(a, b, tol, what, max_bad_frac=1e-4, flip_tol=2e-2):
+  """Large cases: `alpha > 1/255` is a hard threshold, so an evaluation whose alpha lies within fp32 rounding of it
+  can fall on the other side than in the fp64 oracle (the generic fp64 kernels agree with the oracle to 1e-15 on
+  the same data).  A flip moves one pixel / one splat row by ~alpha_threshold * T * |feature|; all other entries
+  must meet `tol`, flipped ones `flip_tol`, and there may be at most `max_bad_frac` of them."""
+  a = a.detach().cpu().double().numpy() if hasattr(a, "detach") else np.asarray(a, np.float64)
+  b = b.detach().cpu().double().numpy() if hasattr(b, "detach") else np.asarray(b, np.float64)
+  scale = max(np.abs(b).max(), 1e-30)
+  err = np.abs(a - b) / scale
+  bad = err > tol
+  assert bad.mean() <= max_bad_frac, (what, "fraction over tolerance", float(bad.mean()), float(err.max()))
+  assert err.max() < flip_tol, (what, "max error", float(err.max()))
+
+
 def to_cfg(ts, oc: OracleConfig, **kw):
   d = {k: getattr(oc, k) for k in oc.__dataclass_fields__}
   d.update(kw)
@@ -162,13 +176,16 @@ def _mapper_case(ts, n, size, seed, scale_factor, use_depth16=False, tile_size=1
   oc = OracleConfig(tile_size=tile_size)
   o2p_ref, ranges_ref, keys_ref, counts_ref = cbind.map_to_tiles(pts.numpy(), g.depths.numpy(), size, oc,
                                                                  use_depth16=use_depth16, return_keys=True)
-  o2p, ranges, keys, counts = map_to_tiles_full(pts.to(DEV), g.depths.to(DEV), size, to_cfg(ts, oc), use_depth16)
-  assert np.array_equal(counts.cpu().numpy(), counts_ref), "overlap counts differ"
-  k = keys.cpu().numpy()
-  k = k.astype(np.uint32).astype(np.uint64) if use_depth16 else k.view(np.uint64)
-  assert np.array_equal(k, keys_ref), "sorted keys differ"
-  assert np.array_equal(o2p.cpu().numpy(), o2p_ref), "sort order differs"
-  assert np.array_equal(ranges.cpu().numpy(), ranges_ref), "tile ranges differ"
+  # both the two-level ordering (default) and the reference's own count/scan/emit/48-bit-sort sequence
+  for two_level in (True, False):
+    o2p, ranges, keys, counts = map_to_tiles_full(pts.to(DEV), g.depths.to(DEV), size, to_cfg(ts, oc), use_depth16,
+                                                  two_level=two_level)
+    assert np.array_equal(counts.cpu().numpy(), counts_ref), "overlap counts differ"
+    k = keys.cpu().numpy()
+    k = k.astype(np.uint32).astype(np.uint64) if use_depth16 else k.view(np.uint64)
+    assert np.array_equal(k, keys_ref), f"sorted keys differ (two_level={two_level})"
+    assert np.array_equal(o2p.cpu().numpy(), o2p_ref), f"sort order differs (two_level={two_level})"
+    assert np.array_equal(ranges.cpu().numpy(), ranges_ref), f"tile ranges differ (two_level={two_level})"
   return len(o2p_ref)
 
 
@@ -382,3 +399,105 @@ def test_fused_render_equals_operator_composition(ts):
     assert rel_err(ca.T_camera_world.grad, cb.T_camera_world.grad) < 1e-4
     assert rel_err(ca.projection.grad, cb.projection.grad) < 1e-4
     assert rel_err(a.points.split_score, b.points.split_score) < 1e-5
+
+
+# --------------------------------------------------------------------------------------- BASELINE.json configs
+def test_cfg1_fit_image_shape(ts):
+  """configs[0]: 2000 2D Gaussians at 256x256 (examples/fit_image_gaussians.py:264 inputs), forward + backward."""
+  torch.manual_seed(0)
+  size = (256, 256)
+  g = random_data.random_2d_gaussians(2000, size, alpha_range=(0.5, 1.0), scale_factor=0.5)
+  pts = random_data.packed_2d(g)
+  oc = OracleConfig(compute_visibility=True, compute_point_heuristic=True)
+  o2p, ranges = cbind.map_to_tiles(pts.numpy(), g.depths.numpy(), size, oc)
+  img_ref, alpha_ref, vis_ref = cbind.raster_forward(pts, g.feature, ranges, o2p, size, oc, dtype=np.float64)
+  target = np.random.default_rng(0).uniform(size=img_ref.shape)
+  gp_ref, gf_ref, _ = cbind.raster_backward(pts, g.feature, ranges, o2p, img_ref, 2 * (img_ref - target), size, oc, dtype=np.float64)
+  p = pts.to(DEV).requires_grad_(True)
+  f = g.feature.to(DEV).requires_grad_(True)
+  out = ts.rasterize(p, g.depths.to(DEV), f, size, to_cfg(ts, oc, forward_saturate_eps=0.0))
+  assert rel_err(out.image, img_ref) < TOL_F32 and rel_err(out.visibility, vis_ref) < 4 * TOL_F32
+  ((out.image - torch.from_numpy(target).float().to(DEV))**2).sum().backward()   # the example's MSE loss
+  assert rel_err(p.grad, gp_ref) < 5e-5 and rel_err(f.grad, gf_ref) < 5e-5
+
+
+def test_cfg2_full_size_vs_oracle(ts):
+  """configs[1]: 100 k Gaussians, 1024x1024, SH degree 0 (plain RGB features).  The whole path is checked stage by
+  stage ON THE SAME DATA: every stage's GPU output is compared with the oracle evaluated on that stage's actual GPU
+  inputs, so fp32 rounding of one stage cannot flip a depth order or a borderline tile in the next comparison."""
+  torch.manual_seed(0)
+  size = (1024, 1024)
+  cam = random_data.fixed_camera(size)
+  g = random_data.random_3d_gaussians(100_000, cam, scale_factor=1.0)
+  oc = OracleConfig()
+  cfg = to_cfg(ts, oc, forward_saturate_eps=0.0)
+  names = ("position", "log_scaling", "rotation", "alpha_logit")
+  # R1: projection vs fp64 oracle
+  ins = [getattr(g, k).to(DEV).requires_grad_(True) for k in names]
+  Tcw, proj = cam.T_camera_world.to(DEV), cam.projection.to(DEV)
+  pts, depth, idx = ts.perspective.apply(*ins, Tcw, proj, size, cam.depth_range, blur_cov=oc.blur_cov)
+  ref_in = [getattr(g, k).double().requires_grad_(True) for k in names]
+  rp, rd, ri = torch_ops.project(*ref_in, cam.T_camera_world.double(), cam.projection.double(), size, cam.depth_range,
+                                 blur_cov=oc.blur_cov)
+  assert torch.equal(idx.cpu(), ri) and idx.shape[0] == 100_000
+  assert rel_err(pts, rp) < TOL_F32 and rel_err(depth, rd) < TOL_F32
+  # R3-R7: mapper, bit-exact on the GPU's own fp32 points / ndc depths
+  ndc = ts.rendering.ndc_depth(depth.detach(), cam.near_plane, cam.far_plane)
+  o2p, ranges = ts.map_to_tiles(pts.detach(), ndc, size, cfg)
+  o2p_ref, ranges_ref = cbind.map_to_tiles(pts.detach().cpu().numpy(), ndc.cpu().numpy(), size, oc)
+  assert np.array_equal(o2p.cpu().numpy(), o2p_ref) and np.array_equal(ranges.cpu().numpy(), ranges_ref)
+  assert 500_000 < o2p_ref.shape[0] < 700_000                     # K ~ 0.61 M (SURVEY 8a)
+  # R8 / R9: raster forward + backward vs fp64 oracle on the same points / order
+  feats = g.feature[idx.cpu()].to(DEV).requires_grad_(True)
+  p2 = pts.detach().requires_grad_(True)
+  out = ts.rasterize_with_tiles(p2, feats, o2p, ranges.view(-1, 2), size, cfg)
+  img_ref, alpha_ref, _ = cbind.raster_forward(p2, feats, ranges_ref, o2p_ref, size, oc, dtype=np.float64)
+  assert_close_up_to_threshold_flips(out.image, img_ref, TOL_F32, "image")
+  assert_close_up_to_threshold_flips(out.image_weight, alpha_ref, TOL_F32, "alpha")
+  out.image.sum().backward()
+  gp_ref, gf_ref, _ = cbind.raster_backward(p2, feats, ranges_ref, o2p_ref, img_ref, np.ones_like(img_ref), size, oc, dtype=np.float64)
+  assert_close_up_to_threshold_flips(p2.grad, gp_ref, 3 * TOL_F32, "grad_points")
+  assert_close_up_to_threshold_flips(feats.grad, gf_ref, 3 * TOL_F32, "grad_features")
+  # R1b: projection backward with the raster gradients as upstream
+  torch.autograd.backward([pts], [p2.grad])
+  torch.autograd.backward([rp], [torch.from_numpy(gp_ref)])
+  for a, b, k in zip(ins, ref_in, names):
+    assert rel_err(a.grad, b.grad) < 5e-3, (k, rel_err(a.grad, b.grad))
+  # and the fused renderer produces the same image as the operator chain
+  gauss = ts.Gaussians3D(**{k: v.to(DEV) for k, v in vars(g).items()})
+  camera = ts.perspective.CameraParams(projection=proj, T_camera_world=Tcw, near_plane=cam.near_plane,
+                                       far_plane=cam.far_plane, image_size=size)
+  assert torch.equal(ts.render_gaussians(gauss, camera, cfg).image, out.image.detach())
+
+
+def test_cfg3_full_size_properties(ts):
+  """configs[2] (the benchmark workload: 1 M Gaussians, 2048x2048, SH deg 3, visibility + heuristics + median depth)
+  checked through size-independent properties of the compositing."""
+  from taichi_splatting_b200.benchmarks import scenes
+  size = (2048, 2048)
+  cam = scenes.benchmark_camera(size)
+  cloud = scenes.random_3d_gaussians(1_000_000, cam, sh_degree=3, seed=0).to(DEV).requires_grad_(True)
+  cfg = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True, saturate_threshold=2.0, forward_saturate_eps=0.0)
+  out = ts.render_gaussians(cloud, cam.to(device=DEV), cfg, use_sh=True, render_median_depth=True)
+  w = out.image_weight
+  assert float(w.min()) >= 0 and float(w.max()) <= 1.0 and bool(torch.isfinite(out.image).all())
+  # checksum of checksums: sum over splats of visibility == sum over pixels of accumulated weight
+  assert abs(float(out.points.visibility.double().sum()) / float(w.double().sum()) - 1) < 1e-5
+  # with the backward saturation skip disabled, d(sum image)/d colour == visibility (tests/test_visibility.py:34-64)
+  feats = out.points.features.detach().requires_grad_(True)
+  g2d = out.points.gaussians2d.detach()
+  o2p, ranges = ts.map_to_tiles(g2d, ts.rendering.ndc_depth(out.points.depths.detach(), cam.near_plane, cam.far_plane), size, cfg)
+  r1 = ts.rasterize_with_tiles(g2d, feats, o2p, ranges.view(-1, 2), size, cfg)
+  assert torch.equal(r1.image, out.image.detach())                    # operator path == fused path, bit for bit
+  r1.image.sum().backward()
+  assert rel_err(feats.grad[:, 0], r1.visibility) < 1e-5
+  assert float(r1.point_heuristic.min()) >= 0
+  # compositing is linear in the features: doubling them doubles the image exactly (power-of-two scaling)
+  r2 = ts.rasterize_with_tiles(g2d, 2 * feats.detach(), o2p, ranges.view(-1, 2), size, cfg)
+  assert torch.equal(r2.image, 2 * r1.image.detach()) and torch.equal(r2.image_weight, r1.image_weight)
+  # median depth lies within the depth range of the visible set wherever the accumulated weight reached 0.75
+  med = out.median_depth_image
+  hit = med > 0
+  assert bool(((w >= 0.75) == hit).float().mean() > 0.9999)
+  dmin, dmax = float(out.points.depths.detach().min()), float(out.points.depths.detach().max())
+  assert float(med[hit].min()) >= dmin and float(med[hit].max()) <= dmax
