@@ -29,6 +29,9 @@ int raster_bwd_generic(const real *points, const real *features, const int32_t *
                        const gs_raster_config *cfg, real *grad_points, real *grad_features, real *heuristic,
                        cudaStream_t stream);
 
+#ifndef GS_BWD_UNROLL
+#define GS_BWD_UNROLL 1
+#endif
 constexpr int kTileB = 16;
 constexpr int kBatchB = 256;
 constexpr float kExpScaleB = 0.84932180028801904f;
@@ -208,7 +211,8 @@ raster_bwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
 
     // ---- gradient sweep (branch-free body) ----
     const unsigned full = 0xffffffffu;
-#pragma unroll 2
+    constexpr int kUnrollB = GS_BWD_UNROLL;
+#pragma unroll kUnrollB
     for (int h = 0; h < nhit; ++h) {
       const int j = sm.list[warp][h];
       const float4 A = sm.a[j], B = sm.b[j];

@@ -28,7 +28,10 @@ int raster_fwd_generic(const real *points, const real *features, const int32_t *
 
 constexpr int kTile = 16;
 constexpr int kBatch = 256;
-constexpr int kUnroll = 16;
+#ifndef GS_FWD_UNROLL
+#define GS_FWD_UNROLL 16
+#endif
+constexpr int kUnroll = GS_FWD_UNROLL;
 constexpr float kExpScale = 0.84932180028801904f;  // sqrt(0.5 * log2(e)):  exp(-0.5 r^2) = 2^-(k r)^2
 
 __device__ __forceinline__ float ex2_approx(float x) {
