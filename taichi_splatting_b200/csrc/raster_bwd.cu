@@ -19,6 +19,9 @@
 //     2 heuristics) then share one 3-shuffle tail -- 15 shuffles for 11 sums, against 5 per value for a tree;
 //   * the inner loop is branch-free; one shared-memory atomic instruction per (warp, splat); one global
 //     float atomic per (splat, tile, component) at the end of each 256-splat batch.
+#include <stdlib.h>
+#include <string.h>
+
 #include "raster_common.cuh"
 
 namespace gs {
@@ -337,6 +340,32 @@ static int launch_bwd(const float *points, const float *features, const int32_t 
   return GS_OK;
 }
 
+// raster_bwd_t.cu: same contract, shared-memory transpose instead of per-splat shuffle reduction
+template <int F>
+int launch_bwd_transpose(const float *points, const float *features, const int32_t *ranges, const int32_t *o2p,
+                         const float *image, const float *grad_image, const RasterParams<float> &P, int tiles,
+                         float *grad_points, float *grad_features, float *heuristic, cudaStream_t stream);
+
+static bool use_transpose_kernel() {
+  static int choice = -1;
+  if (choice < 0) {
+    const char *e = getenv("GS_BWD_KERNEL");   // "shuffle" | "transpose" (A/B switch for profiling)
+    choice = (e != nullptr && strcmp(e, "shuffle") == 0) ? 0 : 1;
+  }
+  return choice == 1;
+}
+
+template <int F>
+static int launch_bwd_any(const float *points, const float *features, const int32_t *ranges, const int32_t *o2p,
+                          const float *image, const float *grad_image, const RasterParams<float> &P, int tiles,
+                          float *grad_points, float *grad_features, float *heuristic, cudaStream_t stream) {
+  if (use_transpose_kernel())
+    return launch_bwd_transpose<F>(points, features, ranges, o2p, image, grad_image, P, tiles, grad_points,
+                                   grad_features, heuristic, stream);
+  return launch_bwd<F>(points, features, ranges, o2p, image, grad_image, P, tiles, grad_points, grad_features,
+                       heuristic, stream);
+}
+
 }  // namespace gs
 
 extern "C" int gs_raster_bwd_f32(const float *points, const float *features, const int32_t *tile_ranges,
@@ -353,10 +382,10 @@ extern "C" int gs_raster_bwd_f32(const float *points, const float *features, con
     gs::RasterParams<float> P = gs::make_params<float>(cfg, width, height, F);
     int tiles = P.tiles_wide * ((height + gs::kTileB - 1) / gs::kTileB);
     switch (F) {
-      case 1: return gs::launch_bwd<1>(points, features, tile_ranges, overlap_to_point, image, grad_image, P, tiles, grad_points, grad_features, point_heuristic, stream);
-      case 2: return gs::launch_bwd<2>(points, features, tile_ranges, overlap_to_point, image, grad_image, P, tiles, grad_points, grad_features, point_heuristic, stream);
-      case 3: return gs::launch_bwd<3>(points, features, tile_ranges, overlap_to_point, image, grad_image, P, tiles, grad_points, grad_features, point_heuristic, stream);
-      default: return gs::launch_bwd<4>(points, features, tile_ranges, overlap_to_point, image, grad_image, P, tiles, grad_points, grad_features, point_heuristic, stream);
+      case 1: return gs::launch_bwd_any<1>(points, features, tile_ranges, overlap_to_point, image, grad_image, P, tiles, grad_points, grad_features, point_heuristic, stream);
+      case 2: return gs::launch_bwd_any<2>(points, features, tile_ranges, overlap_to_point, image, grad_image, P, tiles, grad_points, grad_features, point_heuristic, stream);
+      case 3: return gs::launch_bwd_any<3>(points, features, tile_ranges, overlap_to_point, image, grad_image, P, tiles, grad_points, grad_features, point_heuristic, stream);
+      default: return gs::launch_bwd_any<4>(points, features, tile_ranges, overlap_to_point, image, grad_image, P, tiles, grad_points, grad_features, point_heuristic, stream);
     }
   }
   return gs::raster_bwd_generic<float>(points, features, tile_ranges, overlap_to_point, image, grad_image, width,
