@@ -21,6 +21,13 @@
 
 namespace gs {
 
+#ifndef GS_BWDT_UNROLL
+#define GS_BWDT_UNROLL 8
+#endif
+#ifndef GS_BWDT_MIN_BLOCKS
+#define GS_BWDT_MIN_BLOCKS 3
+#endif
+
 namespace bwdt {
 
 constexpr int kTile = 16;
@@ -54,7 +61,7 @@ struct Smem {
 };
 
 template <int F, bool GP, bool GF, bool HEUR>
-__global__ void __launch_bounds__(kBatch, 3)
+__global__ void __launch_bounds__(kBatch, GS_BWDT_MIN_BLOCKS)
 raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ features,
                     const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
                     const float *__restrict__ image, const float *__restrict__ grad_image, RasterParams<float> P,
@@ -171,7 +178,8 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
 
     for (int h0 = 0; h0 < nhit; h0 += kChunk) {
       // ---- phase 1: lane = pixel; 8 splats in depth order ----
-#pragma unroll 2
+      constexpr int kUnroll1 = GS_BWDT_UNROLL;
+#pragma unroll kUnroll1
       for (int u = 0; u < kChunk; ++u) {
         const int j = sm.list[warp][h0 + u];
         const float4 A = sm.a[j], B = sm.b[j];
