@@ -113,19 +113,23 @@ int gs_project_bwd_f64(const double *position, const double *log_scaling, const 
  * params (M,C,D), D=(degree+1)^2, degree 0..3; out (V,C) = clamp(Y(dir).params + 0.5, 0, 1).
  * Backward accumulates (atomic) into zero-initialised d_params (M,C,D), d_positions (M,3),
  * d_camera_pos (3); any of the three may be NULL.  unique_indexes!=0 promises no index repeats
- * (true for the renderer's visible set) and enables plain vector stores into d_params.        */
+ * (true for the renderer's visible set) and enables plain vector stores into d_params.  `out` (the
+ * forward result, may be NULL) lets the backward take the clamp mask from it instead of re-reading
+ * the coefficient rows.                                                                          */
 int gs_sh_fwd_f32(const float *params, const float *positions, const int64_t *indexes,
                   const float *camera_pos, int64_t v, int32_t channels, int32_t degree, float *out,
                   void *stream);
 int gs_sh_bwd_f32(const float *params, const float *positions, const int64_t *indexes,
-                  const float *camera_pos, const float *d_out, int64_t v, int32_t channels, int32_t degree,
+                  const float *camera_pos, const float *d_out, const float *out /* forward output or NULL */,
+                  int64_t v, int32_t channels, int32_t degree,
                   int32_t unique_indexes, float *d_params, float *d_positions, float *d_camera_pos,
                   void *stream);
 int gs_sh_fwd_f64(const double *params, const double *positions, const int64_t *indexes,
                   const double *camera_pos, int64_t v, int32_t channels, int32_t degree, double *out,
                   void *stream);
 int gs_sh_bwd_f64(const double *params, const double *positions, const int64_t *indexes,
-                  const double *camera_pos, const double *d_out, int64_t v, int32_t channels, int32_t degree,
+                  const double *camera_pos, const double *d_out, const double *out, int64_t v, int32_t channels,
+                  int32_t degree,
                   int32_t unique_indexes, double *d_params, double *d_positions, double *d_camera_pos,
                   void *stream);
 

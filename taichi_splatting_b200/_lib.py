@@ -33,7 +33,7 @@ _PROJECT_CULL = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, D, P, SZ, P, P]
 _PROJECT_WRITE = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, P, P, P, P, P, P]
 _PROJECT_BWD = [P, P, P, P, P, P, P, I64, I32, I32, D, D, P, P, P, P, P, P, P, P, P]
 _SH_FWD = [P, P, P, P, I64, I32, I32, P, P]
-_SH_BWD = [P, P, P, P, P, I64, I32, I32, I32, P, P, P, P]
+_SH_BWD = [P, P, P, P, P, P, I64, I32, I32, I32, P, P, P, P]
 _RASTER_FWD = [P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P]
 _RASTER_BWD = [P, P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P]
 

@@ -125,8 +125,8 @@ template <typename real, int DEG>
 __global__ void __launch_bounds__(256)
 sh_bwd_kernel(const real *__restrict__ params, const real *__restrict__ positions,
               const int64_t *__restrict__ indexes, const real *__restrict__ camera_pos,
-              const real *__restrict__ d_out, int64_t total, int channels, int unique,
-              real *__restrict__ d_params, real *__restrict__ d_positions, real *__restrict__ d_camera_pos) {
+              const real *__restrict__ d_out, const real *__restrict__ out, int64_t total, int channels,
+              int unique, real *__restrict__ d_params, real *__restrict__ d_positions, real *__restrict__ d_camera_pos) {
   constexpr int D = (DEG + 1) * (DEG + 1);
   __shared__ real red[3];
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -141,13 +141,22 @@ sh_bwd_kernel(const real *__restrict__ params, const real *__restrict__ position
     real x = vx * inv, y = vy * inv, z = vz * inv;
     real Y[D];
     rsh<real, DEG>(x, y, z, Y);
+    // clamp mask: from the saved forward output when the caller has it (no need to re-read the D coefficients of
+    // this row: the clamp was active iff the output sits exactly on 0 or 1), else recomputed
+    const bool need_params = (out == nullptr) || ((d_positions || d_camera_pos) && DEG >= 1);
     real p[D];
-    load_row<real, D>(params + (idx * channels + c) * D, p);
-    real pre = 0;
+    real g;
+    if (need_params) load_row<real, D>(params + (idx * channels + c) * D, p);
+    if (out != nullptr) {
+      real o = out[t];
+      g = (o > real(0) && o < real(1)) ? d_out[t] : real(0);
+    } else {
+      real pre = 0;
 #pragma unroll
-    for (int d = 0; d < D; ++d) pre += Y[d] * p[d];
-    pre += real(0.5);
-    real g = (pre >= real(0) && pre <= real(1)) ? d_out[t] : real(0);
+      for (int d = 0; d < D; ++d) pre += Y[d] * p[d];
+      pre += real(0.5);
+      g = (pre >= real(0) && pre <= real(1)) ? d_out[t] : real(0);
+    }
     if (d_params) {
       real *dp = d_params + (idx * channels + c) * D;
       if (unique) {
@@ -211,14 +220,14 @@ int sh_fwd(const real *params, const real *positions, const int64_t *indexes, co
 
 template <typename real>
 int sh_bwd(const real *params, const real *positions, const int64_t *indexes, const real *camera_pos,
-           const real *d_out, int64_t v, int channels, int degree, int unique, real *d_params, real *d_positions,
-           real *d_camera_pos, cudaStream_t stream) {
+           const real *d_out, const real *out, int64_t v, int channels, int degree, int unique, real *d_params,
+           real *d_positions, real *d_camera_pos, cudaStream_t stream) {
   GS_CHECK_ARG(degree >= 0 && degree <= 3, "sh: degree %d not in 0..3", degree);
   int64_t total = v * channels;
   if (total == 0) return GS_OK;
   unsigned grid = (unsigned)ceil_div(total, 256);
 #define GS_SH_BWD(DEG)                                                                                        \
-  sh_bwd_kernel<real, DEG><<<grid, 256, 0, stream>>>(params, positions, indexes, camera_pos, d_out, total,    \
+  sh_bwd_kernel<real, DEG><<<grid, 256, 0, stream>>>(params, positions, indexes, camera_pos, d_out, out, total, \
                                                      channels, unique, d_params, d_positions, d_camera_pos)
   switch (degree) {
     case 0: GS_SH_BWD(0); break;
@@ -241,11 +250,11 @@ int sh_bwd(const real *params, const real *positions, const int64_t *indexes, co
                             (cudaStream_t)stream);                                                              \
   }                                                                                                             \
   extern "C" int gs_sh_bwd_##SUFFIX(const real *params, const real *positions, const int64_t *indexes,          \
-                                    const real *camera_pos, const real *d_out, int64_t v, int32_t channels,     \
-                                    int32_t degree, int32_t unique_indexes, real *d_params, real *d_positions,  \
-                                    real *d_camera_pos, void *stream) {                                         \
-    return gs::sh_bwd<real>(params, positions, indexes, camera_pos, d_out, v, channels, degree, unique_indexes, \
-                            d_params, d_positions, d_camera_pos, (cudaStream_t)stream);                         \
+                                    const real *camera_pos, const real *d_out, const real *out, int64_t v,      \
+                                    int32_t channels, int32_t degree, int32_t unique_indexes, real *d_params,   \
+                                    real *d_positions, real *d_camera_pos, void *stream) {                      \
+    return gs::sh_bwd<real>(params, positions, indexes, camera_pos, d_out, out, v, channels, degree,            \
+                            unique_indexes, d_params, d_positions, d_camera_pos, (cudaStream_t)stream);         \
   }
 
 GS_SH_API(f32, float)

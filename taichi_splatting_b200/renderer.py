@@ -134,10 +134,11 @@ class _RenderFunction(torch.autograd.Function):
     # ---- features ----
     d_feature = None
     if need[4]:
-      d_feature = torch.zeros_like(feature)
+      all_rows_written = use_sh and v == feature.shape[0]
+      d_feature = torch.empty_like(feature) if all_rows_written else torch.zeros_like(feature)
       if v > 0:
         if use_sh:
-          call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), v,
+          call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), ptr(features), v,
                feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, stream)
         else:
           d_feature.index_copy_(0, indexes, grad_f)

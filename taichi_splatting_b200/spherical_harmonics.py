@@ -31,14 +31,14 @@ class _ShFunction(torch.autograd.Function):
     out = torch.empty((v, channels), dtype=params.dtype, device=device)
     _lib.call(f"gs_sh_fwd_{sfx}", _lib.ptr(params), _lib.ptr(points), _lib.ptr(indexes), _lib.ptr(camera_pos),
               v, channels, degree, _lib.ptr(out), _lib.stream_ptr(device))
-    ctx.save_for_backward(params, points, indexes, camera_pos)
+    ctx.save_for_backward(params, points, indexes, camera_pos, out)
     ctx.degree, ctx.unique = degree, bool(unique_indexes)
     ctx.mark_non_differentiable(indexes)
     return out
 
   @staticmethod
   def backward(ctx, doutput):
-    params, points, indexes, camera_pos = ctx.saved_tensors
+    params, points, indexes, camera_pos, out = ctx.saved_tensors
     sfx = _lib.suffix(params.dtype)
     need = ctx.needs_input_grad
     d_params = torch.zeros_like(params) if need[0] else None
@@ -46,7 +46,7 @@ class _ShFunction(torch.autograd.Function):
     d_cam = torch.zeros_like(camera_pos) if need[3] else None
     if (need[0] or need[1] or need[3]) and indexes.shape[0] > 0:
       _lib.call(f"gs_sh_bwd_{sfx}", _lib.ptr(params), _lib.ptr(points), _lib.ptr(indexes), _lib.ptr(camera_pos),
-                _lib.ptr(doutput.contiguous()), indexes.shape[0], params.shape[1], ctx.degree, int(ctx.unique),
+                _lib.ptr(doutput.contiguous()), _lib.ptr(out), indexes.shape[0], params.shape[1], ctx.degree, int(ctx.unique),
                 _lib.ptr(d_params), _lib.ptr(d_points), _lib.ptr(d_cam), _lib.stream_ptr(params.device))
     return d_params, d_points, None, d_cam, None
 
