@@ -242,7 +242,7 @@ def run_ours(args):
   except Exception:
     pass
   roofline = {
-      "bound": "hbm", "kernel": "raster_bwd_kernel<3,GP,GF,HEUR>", "unit": "GB/s",
+      "bound": "hbm", "kernel": "bwdt::raster_bwd_t_kernel<3,GP,GF,HEUR>", "unit": "GB/s",
       "achieved": round(stage_bytes["raster_bwd"] / (bwd_ms * 1e-3) / 1e9, 2) if bwd_ms else None,
       "peak": hbm_peak, "peak_source": peak_kind,
       "frac": round(stage_bytes["raster_bwd"] / (bwd_ms * 1e-3) / 1e9 / hbm_peak, 5) if bwd_ms else None,

@@ -267,7 +267,7 @@ static int raster_fwd_f32_impl(const float *points, const float *features, const
   GS_CHECK_ARG(!cfg->compute_visibility || visibility != nullptr, "raster_fwd: compute_visibility needs a visibility buffer");
   const bool fast = cfg->tile_size == kTile && !cfg->antialias && F >= 1 && F <= 4;
   if (median_image != nullptr) {
-    if (!fast || !cfg->use_alpha_blending || depths == nullptr) {
+    if (!fast || !cfg->use_alpha_blending) {
       set_error("raster_fwd_median: needs tile_size 16, no antialias, 1..4 features, alpha blending and depths");
       return GS_ERR_UNSUPPORTED;
     }
@@ -304,7 +304,7 @@ extern "C" int gs_raster_fwd_median_f32(const float *points, const float *featur
                                         const gs_raster_config *cfg, double median_threshold, float *image,
                                         float *image_alpha, float *visibility, float *median_image, void *stream_) {
   (void)v; (void)k;
-  GS_CHECK_ARG(median_image != nullptr && depths != nullptr, "raster_fwd_median: depths / median_image is NULL");
+  GS_CHECK_ARG(median_image != nullptr && (depths != nullptr || v == 0), "raster_fwd_median: depths / median_image is NULL");
   return gs::raster_fwd_f32_impl(points, features, depths, tile_ranges, overlap_to_point, width, height, F, cfg,
                                  median_threshold, image, image_alpha, visibility, median_image, (cudaStream_t)stream_);
 }

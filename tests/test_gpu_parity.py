@@ -501,3 +501,58 @@ def test_cfg3_full_size_properties(ts):
   assert bool(((w >= 0.75) == hit).float().mean() > 0.9999)
   dmin, dmax = float(out.points.depths.detach().min()), float(out.points.depths.detach().max())
   assert float(med[hit].min()) >= dmin and float(med[hit].max()) <= dmax
+
+
+def test_render_gaussians_fp64_whole_path(ts):
+  """fp64 instantiation of every differentiable stage (the reference's gradcheck dtype): with no fp32 rounding in
+  projection / SH / raster the WHOLE path must match the oracle pipeline tightly (the mapper is fp32 on both sides)."""
+  torch.manual_seed(2)
+  size = (160, 112)
+  cam = random_data.fixed_camera(size, yaw_deg=-4.0)
+  for use_sh in (False, True):
+    g = random_data.random_3d_gaussians(5000, cam, scale_factor=2.0, margin=0.3, sh_degree=3 if use_sh else None)
+    g64 = type(g)(**{k: v.double() for k, v in vars(g).items()})
+    cam64 = random_data.make_camera(cam.T_camera_world.double(), cam.projection.double(), size, cam.near_plane, cam.far_plane)
+    oc = OracleConfig(compute_visibility=True, compute_point_heuristic=True)
+    R = np.random.default_rng(3).uniform(size=(size[1], size[0], 3))
+    ref = pipeline.render_forward_backward(g64, cam64, oc, use_sh=use_sh, grad_image=R, raster_dtype=np.float64)
+    gauss = ts.Gaussians3D(**{k: v.to(DEV).requires_grad_(True) for k, v in vars(g64).items()})
+    camera = ts.perspective.CameraParams(projection=cam64.projection.to(DEV).requires_grad_(True),
+                                         T_camera_world=cam64.T_camera_world.to(DEV).requires_grad_(True),
+                                         near_plane=cam.near_plane, far_plane=cam.far_plane, image_size=size)
+    out = ts.render_gaussians(gauss, camera, to_cfg(ts, oc, forward_saturate_eps=0.0), use_sh=use_sh, render_median_depth=True)
+    assert out.image.dtype == torch.float64 and torch.equal(out.points.idx.cpu(), ref.indexes)
+    assert rel_err(out.image, ref.image) < 1e-10 and rel_err(out.points.visibility, ref.visibility) < 1e-10
+    (out.image * torch.from_numpy(R).to(DEV)).sum().backward()
+    for k in ("position", "log_scaling", "rotation", "alpha_logit", "feature"):
+      assert rel_err(getattr(gauss, k).grad, ref.grads[k]) < 1e-8, (k, rel_err(getattr(gauss, k).grad, ref.grads[k]))
+    assert rel_err(camera.T_camera_world.grad, ref.grads["T_camera_world"]) < 1e-8
+    assert rel_err(camera.projection.grad, ref.grads["projection"]) < 1e-8
+    assert rel_err(out.points.prune_cost, ref.heuristic[:, 0]) < 1e-9
+
+
+def test_render_gaussians_degenerate_inputs(ts):
+  """Nothing visible / empty cloud: zero image, zero gradients, no crash (V = 0 and K = 0 paths)."""
+  size = (64, 48)
+  cam = random_data.fixed_camera(size)
+  camera = ts.perspective.CameraParams(projection=cam.projection.to(DEV), T_camera_world=cam.T_camera_world.to(DEV),
+                                       near_plane=cam.near_plane, far_plane=cam.far_plane, image_size=size)
+  cfg = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True)
+  for n in (0, 7):
+    g = ts.Gaussians3D(position=torch.tensor([[0., 0., -5.]] * n, device=DEV).reshape(n, 3).requires_grad_(True),
+                       log_scaling=torch.zeros((n, 3), device=DEV, requires_grad=True),
+                       rotation=torch.tensor([[0., 0., 0., 1.]] * n, device=DEV).reshape(n, 4).requires_grad_(True),
+                       alpha_logit=torch.zeros((n, 1), device=DEV, requires_grad=True),
+                       feature=torch.rand((n, 3, 16), device=DEV).requires_grad_(True))
+    out = ts.render_gaussians(g, camera, cfg, use_sh=True, render_median_depth=True)
+    assert out.points.idx.numel() == 0 and float(out.image.abs().max()) == 0 and float(out.image_weight.abs().max()) == 0
+    assert out.median_depth_image.shape == (48, 64) and float(out.median_depth_image.abs().max()) == 0
+    out.image.sum().backward()
+    assert g.position.grad.shape == (n, 3) and float(g.feature.grad.abs().sum()) == 0
+  # a splat far larger than the image, and one with alpha below the threshold
+  pts = torch.tensor([[32., 24., 1., 0., 400., 300., 0.9], [10., 10., 0., 1., 2., 2., 0.001]], device=DEV)
+  out = ts.rasterize(pts, torch.tensor([[0.5], [0.1]], device=DEV), torch.tensor([[1., 0., 0.], [0., 1., 0.]], device=DEV), size,
+                     ts.RasterConfig())
+  ref_o2p, ref_ranges = cbind.map_to_tiles(pts.cpu().numpy(), np.array([[0.5], [0.1]], np.float32), size, OracleConfig())
+  img_ref, _, _ = cbind.raster_forward(pts, torch.tensor([[1., 0., 0.], [0., 1., 0.]]), ref_ranges, ref_o2p, size, OracleConfig(), dtype=np.float64)
+  assert rel_err(out.image, img_ref) < TOL_F32 and float(out.image[..., 1].abs().max()) == 0
