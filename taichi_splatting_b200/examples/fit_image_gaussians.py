@@ -1,0 +1,71 @@
+"""2D image fitting with Gaussians: the reference's only end-to-end training entry, reduced to the render path.
+
+Reference: taichi_splatting/examples/fit_image_gaussians.py:89-147,234-358 (BASELINE config 1: 256x256, n=2000).
+The reference drives its own visibility-aware LaProp optimiser and split/prune densification (optim/, out of scope
+here); this version keeps the same forward / loss / backward through `rasterize` and uses
+torch.optim.Adam so that the loop exercises exactly the hot path this package replaces.
+
+  python -m taichi_splatting_b200.examples.fit_image_gaussians [--image path.png] [--n 2000] [--iters 200]
+"""
+import argparse
+import math
+
+import torch
+
+from ..benchmarks.scenes import random_2d_gaussians
+from ..data_types import RasterConfig
+from ..misc.renderer2d import project_gaussians2d
+from ..rasterizer import rasterize
+
+
+def synthetic_image(w, h, device):
+  ys, xs = torch.meshgrid(torch.linspace(0, 1, h, device=device), torch.linspace(0, 1, w, device=device), indexing="ij")
+  return torch.stack([0.5 + 0.5 * torch.sin(6.28 * xs), ys, 0.5 + 0.5 * torch.cos(9.4 * xs * ys)], dim=-1).contiguous()
+
+
+def psnr(a, b):
+  return 10 * math.log10(1 / torch.nn.functional.mse_loss(a, b).item())
+
+
+def main(argv=None):
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--image", type=str, default=None, help="optional image file (needs cv2); default: synthetic")
+  ap.add_argument("--n", type=int, default=2000)
+  ap.add_argument("--size", type=str, default="256,256")
+  ap.add_argument("--iters", type=int, default=200)
+  ap.add_argument("--lr", type=float, default=0.02)
+  ap.add_argument("--tile_size", type=int, default=16)
+  ap.add_argument("--device", type=str, default="cuda:0")
+  args = ap.parse_args(argv)
+  device = torch.device(args.device)
+
+  if args.image is not None:
+    import cv2
+    img = cv2.cvtColor(cv2.imread(args.image), cv2.COLOR_BGR2RGB)
+    ref_image = (torch.from_numpy(img).to(torch.float32) / 255).to(device)
+  else:
+    w, h = map(int, args.size.split(","))
+    ref_image = synthetic_image(w, h, device)
+  h, w = ref_image.shape[:2]
+
+  g = random_2d_gaussians(args.n, (w, h), alpha_range=(0.5, 1.0), scale_factor=0.5, seed=0).to(device)
+  params = [g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature]
+  for p in params:
+    p.requires_grad_(True)
+  opt = torch.optim.Adam([{"params": [g.position], "lr": args.lr * 10}, {"params": params[1:], "lr": args.lr}])
+  config = RasterConfig(tile_size=args.tile_size, compute_visibility=True)
+
+  for it in range(args.iters):
+    opt.zero_grad(set_to_none=True)
+    raster = rasterize(project_gaussians2d(g), torch.clamp(g.depths, 0, 1), g.feature, (w, h), config)
+    loss = torch.nn.functional.mse_loss(raster.image, ref_image)
+    loss.backward()
+    opt.step()
+    if it % 50 == 0 or it == args.iters - 1:
+      visible = int((raster.visibility > 0).sum())
+      print(f"iter {it:5d}  psnr {psnr(raster.image.detach(), ref_image):6.2f} dB  visible {visible}/{args.n}")
+  return psnr(raster.image.detach(), ref_image)
+
+
+if __name__ == "__main__":
+  main()

@@ -556,3 +556,13 @@ def test_render_gaussians_degenerate_inputs(ts):
   ref_o2p, ref_ranges = cbind.map_to_tiles(pts.cpu().numpy(), np.array([[0.5], [0.1]], np.float32), size, OracleConfig())
   img_ref, _, _ = cbind.raster_forward(pts, torch.tensor([[1., 0., 0.], [0., 1., 0.]]), ref_ranges, ref_o2p, size, OracleConfig(), dtype=np.float64)
   assert rel_err(out.image, img_ref) < TOL_F32 and float(out.image[..., 1].abs().max()) == 0
+
+
+def test_fit_image_example_converges(ts):
+  """configs[0] plumbing: the 2D image-fitting loop (examples/fit_image_gaussians.py) improves PSNR through our
+  forward + backward."""
+  from taichi_splatting_b200.examples import fit_image_gaussians
+  torch.manual_seed(0)
+  first = fit_image_gaussians.main(["--n", "2000", "--size", "256,256", "--iters", "1"])
+  final = fit_image_gaussians.main(["--n", "2000", "--size", "256,256", "--iters", "150"])
+  assert final > first + 3.0, (first, final)
