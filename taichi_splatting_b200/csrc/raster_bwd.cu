@@ -376,8 +376,8 @@ extern "C" int gs_raster_bwd_f32(const float *points, const float *features, con
   cudaStream_t stream = (cudaStream_t)stream_;
   GS_CHECK_ARG(cfg != nullptr, "raster_bwd: config is NULL");
   GS_CHECK_ARG(width > 0 && height > 0, "raster_bwd: bad image size %dx%d", width, height);
-  GS_CHECK_ARG(!cfg->compute_point_heuristic || point_heuristic != nullptr, "raster_bwd: compute_point_heuristic needs a buffer");
-  (void)v; (void)k;
+  GS_CHECK_ARG(!cfg->compute_point_heuristic || point_heuristic != nullptr || v == 0, "raster_bwd: compute_point_heuristic needs a buffer");
+  (void)k;
   if (cfg->tile_size == gs::kTileB && !cfg->antialias && F >= 1 && F <= 4) {
     gs::RasterParams<float> P = gs::make_params<float>(cfg, width, height, F);
     int tiles = P.tiles_wide * ((height + gs::kTileB - 1) / gs::kTileB);
@@ -399,8 +399,8 @@ extern "C" int gs_raster_bwd_f64(const double *points, const double *features, c
                                  double *point_heuristic, void *stream_) {
   GS_CHECK_ARG(cfg != nullptr, "raster_bwd: config is NULL");
   GS_CHECK_ARG(width > 0 && height > 0, "raster_bwd: bad image size %dx%d", width, height);
-  GS_CHECK_ARG(!cfg->compute_point_heuristic || point_heuristic != nullptr, "raster_bwd: compute_point_heuristic needs a buffer");
-  (void)v; (void)k;
+  GS_CHECK_ARG(!cfg->compute_point_heuristic || point_heuristic != nullptr || v == 0, "raster_bwd: compute_point_heuristic needs a buffer");
+  (void)k;
   return gs::raster_bwd_generic<double>(points, features, tile_ranges, overlap_to_point, image, grad_image, width,
                                         height, F, cfg, grad_points, grad_features, point_heuristic,
                                         (cudaStream_t)stream_);

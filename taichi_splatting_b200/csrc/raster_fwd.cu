@@ -258,13 +258,13 @@ static int launch_fwd(const float *points, const float *features, const float *d
 }
 
 static int raster_fwd_f32_impl(const float *points, const float *features, const float *depths,
-                               const int32_t *tile_ranges, const int32_t *overlap_to_point, int32_t width,
+                               const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t v, int32_t width,
                                int32_t height, int32_t F, const gs_raster_config *cfg, double median_threshold,
                                float *image, float *image_alpha, float *visibility, float *median_image,
                                cudaStream_t stream) {
   GS_CHECK_ARG(cfg != nullptr, "raster_fwd: config is NULL");
   GS_CHECK_ARG(width > 0 && height > 0, "raster_fwd: bad image size %dx%d", width, height);
-  GS_CHECK_ARG(!cfg->compute_visibility || visibility != nullptr, "raster_fwd: compute_visibility needs a visibility buffer");
+  GS_CHECK_ARG(!cfg->compute_visibility || visibility != nullptr || v == 0, "raster_fwd: compute_visibility needs a visibility buffer");
   const bool fast = cfg->tile_size == kTile && !cfg->antialias && F >= 1 && F <= 4;
   if (median_image != nullptr) {
     if (!fast || !cfg->use_alpha_blending) {
@@ -293,8 +293,8 @@ extern "C" int gs_raster_fwd_f32(const float *points, const float *features, con
                                  const int32_t *overlap_to_point, int64_t v, int64_t k, int32_t width,
                                  int32_t height, int32_t F, const gs_raster_config *cfg, float *image,
                                  float *image_alpha, float *visibility, void *stream_) {
-  (void)v; (void)k;
-  return gs::raster_fwd_f32_impl(points, features, nullptr, tile_ranges, overlap_to_point, width, height, F, cfg, 0.0,
+  (void)k;
+  return gs::raster_fwd_f32_impl(points, features, nullptr, tile_ranges, overlap_to_point, v, width, height, F, cfg, 0.0,
                                  image, image_alpha, visibility, nullptr, (cudaStream_t)stream_);
 }
 
@@ -303,9 +303,9 @@ extern "C" int gs_raster_fwd_median_f32(const float *points, const float *featur
                                         int64_t k, int32_t width, int32_t height, int32_t F,
                                         const gs_raster_config *cfg, double median_threshold, float *image,
                                         float *image_alpha, float *visibility, float *median_image, void *stream_) {
-  (void)v; (void)k;
+  (void)k;
   GS_CHECK_ARG(median_image != nullptr && (depths != nullptr || v == 0), "raster_fwd_median: depths / median_image is NULL");
-  return gs::raster_fwd_f32_impl(points, features, depths, tile_ranges, overlap_to_point, width, height, F, cfg,
+  return gs::raster_fwd_f32_impl(points, features, depths, tile_ranges, overlap_to_point, v, width, height, F, cfg,
                                  median_threshold, image, image_alpha, visibility, median_image, (cudaStream_t)stream_);
 }
 
@@ -315,8 +315,8 @@ extern "C" int gs_raster_fwd_f64(const double *points, const double *features, c
                                  double *image_alpha, double *visibility, void *stream_) {
   GS_CHECK_ARG(cfg != nullptr, "raster_fwd: config is NULL");
   GS_CHECK_ARG(width > 0 && height > 0, "raster_fwd: bad image size %dx%d", width, height);
-  GS_CHECK_ARG(!cfg->compute_visibility || visibility != nullptr, "raster_fwd: compute_visibility needs a visibility buffer");
-  (void)v; (void)k;
+  GS_CHECK_ARG(!cfg->compute_visibility || visibility != nullptr || v == 0, "raster_fwd: compute_visibility needs a visibility buffer");
+  (void)k;
   return gs::raster_fwd_generic<double>(points, features, tile_ranges, overlap_to_point, width, height, F, cfg, image,
                                         image_alpha, visibility, (cudaStream_t)stream_);
 }
