@@ -133,6 +133,14 @@ int gs_sh_bwd_f64(const double *params, const double *positions, const int64_t *
                   int32_t unique_indexes, double *d_params, double *d_positions, double *d_camera_pos,
                   void *stream);
 
+/* View-parallel exchange of the SH gradient (multi-GPU, no reference counterpart).  The per-view SH coefficient
+ * gradient is rank-1, d_params[i,c,:] = Y(dir_view(i)) * g_view[i,c], so W views exchange only their dense
+ * (N, C) colour gradients g_w (all-gathered into g_all, `view_stride` elements apart, zero where culled or
+ * clamped) and camera centres (W,3); this kernel rebuilds sum_w Y_w(i) * g_w[i,c] into d_params (N,C,D).      */
+int gs_sh_bwd_views_f32(const float *positions, const float *cam_positions, const float *g_all, int64_t n,
+                        int32_t views, int32_t channels, int64_t view_stride, int32_t degree, float *d_params,
+                        void *stream);
+
 /* ---- R3-R7: tile mapper -------------------------------------------------------------------------
  * gs_tile_count      replaces tile_overlaps_kernel (mapper/tile_mapper.py:75-86, grid_query.py:46-93)
  * gs_tile_scan       replaces cuda_lib.full_cumsum (cuda_lib/full_cumsum.cu:16-47): cum (V+1) i32,

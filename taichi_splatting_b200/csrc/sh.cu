@@ -200,6 +200,57 @@ sh_bwd_kernel(const real *__restrict__ params, const real *__restrict__ position
   }
 }
 
+// View-parallel gradient exchange.  The SH coefficient gradient of one view is rank-1 per Gaussian and channel:
+// d_params[i, c, :] = Y(dir_view(i)) * g_view[i, c]  (g = dL/dcolour, zero where the clamp was active or the
+// Gaussian was culled).  Summing it over W views therefore needs only the W (N, C) arrays g_w and the W camera
+// centres -- 12 B per Gaussian and view instead of an all-reduce of the 192 B (N, C, 16) gradient.  This kernel
+// rebuilds the sum: one thread per (Gaussian, channel), Y recomputed per view, one coalesced row store.
+template <typename real, int DEG>
+__global__ void __launch_bounds__(256)
+sh_bwd_views_kernel(const real *__restrict__ positions, const real *__restrict__ cam_positions,
+                    const real *__restrict__ g_all, int64_t n, int views, int channels, int64_t view_stride,
+                    real *__restrict__ d_params) {
+  constexpr int D = (DEG + 1) * (DEG + 1);
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n * channels) return;
+  int64_t i = t / channels;
+  real px = positions[3 * i], py = positions[3 * i + 1], pz = positions[3 * i + 2];
+  real acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0;
+  for (int w = 0; w < views; ++w) {
+    real g = g_all[w * view_stride + t];
+    if (g == real(0)) continue;
+    real vx = px - cam_positions[3 * w], vy = py - cam_positions[3 * w + 1], vz = pz - cam_positions[3 * w + 2];
+    real inv = real(1) / math<real>::sqrt(vx * vx + vy * vy + vz * vz);
+    real Y[D];
+    rsh<real, DEG>(vx * inv, vy * inv, vz * inv, Y);
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] += Y[d] * g;
+  }
+  store_row<real, D>(d_params + t * D, acc);
+}
+
+template <typename real>
+int sh_bwd_views(const real *positions, const real *cam_positions, const real *g_all, int64_t n, int views,
+                 int channels, int64_t view_stride, int degree, real *d_params, cudaStream_t stream) {
+  GS_CHECK_ARG(degree >= 0 && degree <= 3, "sh: degree %d not in 0..3", degree);
+  int64_t total = n * channels;
+  if (total == 0) return GS_OK;
+  unsigned grid = (unsigned)ceil_div(total, 256);
+#define GS_SH_VIEWS(DEG) \
+  sh_bwd_views_kernel<real, DEG><<<grid, 256, 0, stream>>>(positions, cam_positions, g_all, n, views, channels, view_stride, d_params)
+  switch (degree) {
+    case 0: GS_SH_VIEWS(0); break;
+    case 1: GS_SH_VIEWS(1); break;
+    case 2: GS_SH_VIEWS(2); break;
+    default: GS_SH_VIEWS(3); break;
+  }
+#undef GS_SH_VIEWS
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
 template <typename real>
 int sh_fwd(const real *params, const real *positions, const int64_t *indexes, const real *camera_pos, int64_t v,
            int channels, int degree, real *out, cudaStream_t stream) {
@@ -256,6 +307,13 @@ int sh_bwd(const real *params, const real *positions, const int64_t *indexes, co
     return gs::sh_bwd<real>(params, positions, indexes, camera_pos, d_out, out, v, channels, degree,            \
                             unique_indexes, d_params, d_positions, d_camera_pos, (cudaStream_t)stream);         \
   }
+
+extern "C" int gs_sh_bwd_views_f32(const float *positions, const float *cam_positions, const float *g_all, int64_t n,
+                                   int32_t views, int32_t channels, int64_t view_stride, int32_t degree,
+                                   float *d_params, void *stream) {
+  return gs::sh_bwd_views<float>(positions, cam_positions, g_all, n, views, channels, view_stride, degree, d_params,
+                                 (cudaStream_t)stream);
+}
 
 GS_SH_API(f32, float)
 GS_SH_API(f64, double)

@@ -4,8 +4,10 @@ One process per GPU (`torch.distributed`, NCCL over NVLink/NVSwitch; gloo on CPU
 The path shards two natural ways, both with exactly ONE collective, in the backward pass:
 
   view-parallel   the cloud is replicated, rank r renders its own camera(s); no communication in the
-                  forward; the backward ends with an all-reduce(sum) of the per-Gaussian parameter gradients
-                  (`allreduce_gradients`).
+                  forward; the backward sums the per-Gaussian parameter gradients over ranks: either one
+                  all-reduce of everything (`allreduce_gradients`), or -- `render_view_parallel` -- an
+                  all-reduce of the geometry gradients (44 B / Gaussian) plus an all-gather of the rank-1
+                  factors of the SH gradient (12 B / Gaussian / view instead of 192 B; `ShGradientExchange`).
   tile-sharded    one view, the tile grid is cut into `world` contiguous tile-id ranges holding equal
                   numbers of (tile, Gaussian) overlaps (`partition_tiles`); every rank projects / bins / sorts
                   the whole (cheap, O(N)) front end, rasterises only its own tiles, and the gradients of the
@@ -57,6 +59,60 @@ def allreduce_gradients(tensors: Sequence[torch.Tensor], group=None, bucket: boo
     n = g.numel()
     g.copy_(flat[offset:offset + n].view_as(g))
     offset += n
+
+
+class ShGradientExchange:
+  """View-parallel exchange of the spherical-harmonics gradient, exploiting its structure.
+
+  For one view the SH coefficient gradient is rank-1 per Gaussian and channel,
+      d_params[i, c, :] = Y(normalize(p_i - camera)) * g[i, c],     g = dL/dcolour (0 where clamped / culled),
+  so instead of all-reducing the (N, C, 16) tensor (192 B per Gaussian at degree 3, 81 % of all gradient bytes)
+  every rank all-gathers its dense (N, C) factor g and its camera centre (12 B per Gaussian and view) and rebuilds
+  sum_w Y_w * g_w locally with one kernel (gs_sh_bwd_views_f32).  The result equals the all-reduced gradient up to
+  fp32 summation order.  Used through `render_view_parallel`; the renderer's backward calls `sum_sh_gradient`."""
+
+  def __init__(self, group=None):
+    self.group = group
+    self.rank, self.world = world_info(group)
+
+  def sum_sh_gradient(self, sh_params, positions, indexes, colours, d_colours, camera_pos, degree):
+    from . import _lib
+    n, channels = sh_params.shape[0], sh_params.shape[1]
+    device = sh_params.device
+    stride = n * channels + 3
+    local = torch.zeros((stride,), dtype=torch.float32, device=device)
+    masked = torch.where((colours > 0) & (colours < 1), d_colours, torch.zeros_like(d_colours))
+    local[:n * channels].view(n, channels).index_copy_(0, indexes, masked)
+    local[n * channels:] = camera_pos
+    gathered = torch.empty((self.world, stride), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(gathered, local, group=self.group)
+    cams = gathered[:, n * channels:].contiguous()
+    d_params = torch.empty_like(sh_params)
+    _lib.call("gs_sh_bwd_views_f32", _lib.ptr(positions), _lib.ptr(cams), _lib.ptr(gathered), n, self.world, channels,
+              stride, degree, _lib.ptr(d_params), _lib.stream_ptr(device))
+    return d_params
+
+
+def render_view_parallel(gaussians, camera_params, config, use_sh: bool = False, use_depth16: bool = False,
+                         render_median_depth: bool = False, group=None):
+  """render_gaussians for this rank's view of a replicated cloud.  After `loss.backward()` call
+  `finish_view_parallel_backward(gaussians, use_sh, group)`: with SH the feature gradient has already been
+  summed over ranks inside the backward (ShGradientExchange); everything else is all-reduced there."""
+  from .renderer import _RenderFunction, _wrap_rendering
+  exchange = ShGradientExchange(group) if use_sh else None
+  outs = _RenderFunction.apply(*gaussians.shape_tensors(), gaussians.feature, camera_params.T_camera_world,
+                               camera_params.projection, camera_params, config, use_sh, use_depth16,
+                               render_median_depth, exchange)
+  return _wrap_rendering(outs, camera_params, config, render_median_depth)
+
+
+def finish_view_parallel_backward(gaussians, use_sh: bool, group=None) -> None:
+  """The single NCCL all-reduce of the view-parallel path: geometry gradients (44 B per Gaussian), plus the plain
+  feature gradient when SH is not used."""
+  tensors = [gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit]
+  if not use_sh or gaussians.feature.dtype != torch.float32:
+    tensors.append(gaussians.feature)
+  allreduce_gradients(tensors, group=group, bucket=False)
 
 
 # ------------------------------------------------------------------------------------------ tile-sharded

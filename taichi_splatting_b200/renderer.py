@@ -24,7 +24,7 @@ class _RenderFunction(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, position, log_scaling, rotation, alpha_logit, feature, T_camera_world, projection, camera, config,
-              use_sh, use_depth16, render_median_depth):
+              use_sh, use_depth16, render_median_depth, sh_exchange=None):
     _lib.require_cuda(position=position, log_scaling=log_scaling, rotation=rotation, alpha_logit=alpha_logit,
                       feature=feature, T_camera_world=T_camera_world, projection=projection)
     dtype, device = position.dtype, position.device
@@ -105,6 +105,7 @@ class _RenderFunction(torch.autograd.Function):
     ctx.save_for_backward(*tensors, feature_c, indexes, g2d, features, image, overlap_to_point, ranges,
                           cam_pos if cam_pos is not None else torch.empty(0, device=device))
     ctx.meta = (config, (w, h), blur, margin, bool(use_sh), heuristic)
+    ctx.sh_exchange = sh_exchange
     ctx.set_materialize_grads(False)
     ctx.mark_non_differentiable(alpha, indexes, visibility, heuristic, median, overlap_to_point, tile_ranges)
     return image, alpha, g2d, depths, indexes, features, visibility, heuristic, median, overlap_to_point, tile_ranges
@@ -135,8 +136,16 @@ class _RenderFunction(torch.autograd.Function):
     d_feature = None
     if need[4]:
       all_rows_written = use_sh and v == feature.shape[0]
-      d_feature = torch.empty_like(feature) if all_rows_written else torch.zeros_like(feature)
-      if v > 0:
+      exchange = ctx.sh_exchange if (use_sh and dtype == torch.float32) else None
+      if exchange is not None and exchange.world > 1:
+        # view-parallel: exchange the rank-1 factors of the SH gradient instead of all-reducing it (parallel.py)
+        d_feature = exchange.sum_sh_gradient(feature, position, indexes, features, grad_f, cam_pos,
+                                             check_sh_degree(feature))
+      else:
+        d_feature = torch.empty_like(feature) if all_rows_written else torch.zeros_like(feature)
+      if exchange is not None and exchange.world > 1:
+        pass
+      elif v > 0:
         if use_sh:
           call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), ptr(features), v,
                feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, stream)
@@ -150,7 +159,7 @@ class _RenderFunction(torch.autograd.Function):
       dd = d_depths.contiguous() if d_depths is not None else torch.zeros((v, 1), dtype=dtype, device=device)
       call(f"gs_project_bwd_{sfx}", ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(T_camera_world),
            ptr(projection), ptr(indexes), v, w, h, blur, margin, ptr(grad_g), ptr(dd), *[ptr(g) for g in grads], stream)
-    return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None)
+    return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)
 
 
 @beartype
@@ -160,9 +169,14 @@ def render_gaussians(gaussians: Gaussians3D, camera_params: CameraParams, config
   """Complete renderer for 3D Gaussians; same parameters and result type as the reference (renderer.py:22-59).
   `render_depth` is accepted and unused, as in the reference.  Runs as one fused autograd node
   (`_RenderFunction`); `render_projected` below is the operator-by-operator composition of the same stages."""
-  (image, alpha, g2d, depths, indexes, features, visibility, heuristic, median, _, _) = _RenderFunction.apply(
-      *gaussians.shape_tensors(), gaussians.feature, camera_params.T_camera_world, camera_params.projection,
-      camera_params, config, use_sh, use_depth16, render_median_depth)
+  outs = _RenderFunction.apply(*gaussians.shape_tensors(), gaussians.feature, camera_params.T_camera_world,
+                               camera_params.projection, camera_params, config, use_sh, use_depth16,
+                               render_median_depth)
+  return _wrap_rendering(outs, camera_params, config, render_median_depth)
+
+
+def _wrap_rendering(outs, camera_params, config, render_median_depth) -> Rendering:
+  (image, alpha, g2d, depths, indexes, features, visibility, heuristic, median, _, _) = outs
   points = RenderedPoints(
       idx=indexes, depths=depths, gaussians2d=g2d,
       _visibility=visibility if config.compute_visibility else None,

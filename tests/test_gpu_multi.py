@@ -76,6 +76,14 @@ def _worker(rank, world, port, results):
     for k in names:
       want = sum(pv[k] for pv in per_view)
       assert _rel(getattr(c, k).grad, want) < 2e-5, (k, _rel(getattr(c, k).grad, want))
+    # same sums through the structured exchange (SH gradient via its rank-1 factors, geometry via all-reduce)
+    c, cm, _ = _scene(ts, dev, yaw=2.0 * rank)
+    o = parallel.render_view_parallel(c, cm, cfg, use_sh=True)
+    (o.image * R).sum().backward()
+    parallel.finish_view_parallel_backward(c, use_sh=True)
+    for k in names:
+      want = sum(pv[k] for pv in per_view)
+      assert _rel(getattr(c, k).grad, want) < 2e-5, ("structured", k, _rel(getattr(c, k).grad, want))
     results[rank] = "ok"
   finally:
     dist.destroy_process_group()
