@@ -78,15 +78,19 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
   const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
   const float clamp_max = P.clamp_max, thr = P.thr, sat = P.sat;
 
-  float remaining[F], gpix[F];
+  // The reference tracks remaining[c] = image[c] - sum_{j<=i} f_j[c] w_j per channel (backward.py:116-176), but it is
+  // only ever used through its dot product with this pixel's dL/dimage, so one scalar carries the whole state:
+  //   rem_dot = remaining . gpix ;  dL/dalpha = T (f . gpix) - rem_dot / (1 - alpha)
+  float gpix[F];
 #pragma unroll
-  for (int c = 0; c < F; ++c) { remaining[c] = 0.f; gpix[c] = 0.f; }
+  for (int c = 0; c < F; ++c) gpix[c] = 0.f;
+  float rem_dot = 0.f;
   float total_weight = 1.0f;
   if (in_bounds) {
     const float *img = image + ((int64_t)py * P.width + px) * F;
     const float *gi = grad_image + ((int64_t)py * P.width + px) * F;
 #pragma unroll
-    for (int c = 0; c < F; ++c) { remaining[c] = img[c]; gpix[c] = gi[c]; }
+    for (int c = 0; c < F; ++c) { gpix[c] = gi[c]; rem_dot = fmaf(img[c], gpix[c], rem_dot); }
     total_weight = 0.f;
   }
   {
@@ -195,13 +199,11 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         float weight = has_grad ? alpha * T_i : 0.f;
         total_weight += weight;
         float inv_1ma = rcp_approx(1.0f - alpha);
-        float alpha_grad = 0.f;
+        float fg = feat[0] * gpix[0];
 #pragma unroll
-        for (int c = 0; c < F; ++c) {
-          remaining[c] = fmaf(-feat[c], weight, remaining[c]);
-          float diff = fmaf(-remaining[c], inv_1ma, feat[c] * T_i);
-          alpha_grad = fmaf(diff, gpix[c], alpha_grad);
-        }
+        for (int c = 1; c < F; ++c) fg = fmaf(feat[c], gpix[c], fg);
+        rem_dot = fmaf(-weight, fg, rem_dot);
+        float alpha_grad = fmaf(-rem_dot, inv_1ma, fg * T_i);
         float G = has_grad ? B.z * alpha_grad : 0.f;
         float Gp = G * ga;
         float h1 = 0.f;
