@@ -47,20 +47,50 @@ def peaks():
 
 
 class ClockSampler:
-  """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+  """Samples SM clocks / throttle reasons while the timed region runs: NVML every 5 ms when pynvml is importable
+  (the region is ~0.1 s, too short for more than one `nvidia-smi` fork), else `nvidia-smi` every 100 ms."""
   Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+  NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
   def __init__(self, index):
     self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+    self.nvml = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      # map the torch device index through CUDA_VISIBLE_DEVICES
+      vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+      phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+      self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+      self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+      self.nvml = pynvml
+    except Exception:
+      self.nvml = None
+
+  def _sample_nvml(self):
+    n = self.nvml
+    sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+    power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+    try:
+      reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+    except Exception:
+      reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+    flags = [bool(reasons & 0x8), bool(reasons & 0x40), bool(reasons & 0x20), bool(reasons & 0x4)]  # hw, hw_thermal, sw_thermal, sw_power
+    return [sm, self.max_sm, power] + flags
 
   def _run(self):
     while not self.stop_flag.is_set():
       try:
+        if self.nvml is not None:
+          self.samples.append(self._sample_nvml())
+          self.stop_flag.wait(0.005)
+          continue
         out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                              capture_output=True, text=True, timeout=5).stdout.strip()
         if out:
-          self.samples.append([x.strip() for x in out.split(",")])
+          f = [x.strip() for x in out.split(",")]
+          self.samples.append([float(f[0]), float(f[1]), float(f[2])] + [x.lower().startswith("active") for x in f[3:7]])
       except Exception:
         pass
       self.stop_flag.wait(0.1)
@@ -77,11 +107,10 @@ class ClockSampler:
   def summary(self):
     if not self.samples:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-    sm = sorted(float(s[0]) for s in self.samples)
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-            "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+    sm = sorted(s[0] for s in self.samples)
+    reasons = [n for i, n in enumerate(self.NAMES) if any(s[3 + i] for s in self.samples)]
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons, "samples": len(sm),
+            "power_w_max": round(max(s[2] for s in self.samples), 1), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def algorithmic_bytes(N, V, K, P, T, F, D):
@@ -287,7 +316,7 @@ def run_ours(args):
       "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "stages_ms": stages_ms,
   }
   if rank == 0 and world == 1:
-    line["cpu_baseline"] = cpu_baseline(steps=1)
+    line["cpu_baseline"] = cpu_baseline(steps=2, warmup=1)   # warm: the first CPU step pays thread-pool start-up
   if rank == 0:
     print(json.dumps(line), flush=True)
   if world > 1:
@@ -359,7 +388,7 @@ def run_reference(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--steps", type=int, default=50)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   args = ap.parse_args()
