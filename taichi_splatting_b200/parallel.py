@@ -75,8 +75,8 @@ class ShGradientExchange:
     self.group = group
     self.rank, self.world = world_info(group)
 
-  def sum_sh_gradient(self, sh_params, positions, indexes, colours, d_colours, camera_pos, degree):
-    from . import _lib
+  def start(self, sh_params, indexes, colours, d_colours, camera_pos):
+    """Launch the all-gather of this rank's factors (asynchronously: the caller overlaps the projection backward)."""
     n, channels = sh_params.shape[0], sh_params.shape[1]
     device = sh_params.device
     stride = n * channels + 3
@@ -85,12 +85,23 @@ class ShGradientExchange:
     local[:n * channels].view(n, channels).index_copy_(0, indexes, masked)
     local[n * channels:] = camera_pos
     gathered = torch.empty((self.world, stride), dtype=torch.float32, device=device)
-    dist.all_gather_into_tensor(gathered, local, group=self.group)
+    work = dist.all_gather_into_tensor(gathered, local, group=self.group, async_op=True)
+    return (work, gathered, local, stride)
+
+  def finish(self, pending, sh_params, positions, degree):
+    """Wait for the gathered factors and rebuild sum_w Y_w * g_w -> d_params (N, C, D)."""
+    from . import _lib
+    work, gathered, _local, stride = pending
+    work.wait()
+    n, channels = sh_params.shape[0], sh_params.shape[1]
     cams = gathered[:, n * channels:].contiguous()
     d_params = torch.empty_like(sh_params)
     _lib.call("gs_sh_bwd_views_f32", _lib.ptr(positions), _lib.ptr(cams), _lib.ptr(gathered), n, self.world, channels,
-              stride, degree, _lib.ptr(d_params), _lib.stream_ptr(device))
+              stride, degree, _lib.ptr(d_params), _lib.stream_ptr(sh_params.device))
     return d_params
+
+  def sum_sh_gradient(self, sh_params, positions, indexes, colours, d_colours, camera_pos, degree):
+    return self.finish(self.start(sh_params, indexes, colours, d_colours, camera_pos), sh_params, positions, degree)
 
 
 def render_view_parallel(gaussians, camera_params, config, use_sh: bool = False, use_depth16: bool = False,
@@ -112,7 +123,7 @@ def finish_view_parallel_backward(gaussians, use_sh: bool, group=None) -> None:
   tensors = [gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit]
   if not use_sh or gaussians.feature.dtype != torch.float32:
     tensors.append(gaussians.feature)
-  allreduce_gradients(tensors, group=group, bucket=False)
+  allreduce_gradients(tensors, group=group, bucket=True)   # one 44 B/Gaussian message instead of four
 
 
 # ------------------------------------------------------------------------------------------ tile-sharded

@@ -132,25 +132,13 @@ class _RenderFunction(torch.autograd.Function):
            ptr(grad_g) if need_geom else None, ptr(grad_f) if need[4] else None,
            ptr(heuristic) if config.compute_point_heuristic else None, stream)
 
-    # ---- features ----
+    # ---- features (part 1): view-parallel runs launch the exchange of the SH-gradient factors now, so that the
+    # all-gather overlaps the projection backward ----
     d_feature = None
-    if need[4]:
-      all_rows_written = use_sh and v == feature.shape[0]
-      exchange = ctx.sh_exchange if (use_sh and dtype == torch.float32) else None
-      if exchange is not None and exchange.world > 1:
-        # view-parallel: exchange the rank-1 factors of the SH gradient instead of all-reducing it (parallel.py)
-        d_feature = exchange.sum_sh_gradient(feature, position, indexes, features, grad_f, cam_pos,
-                                             check_sh_degree(feature))
-      else:
-        d_feature = torch.empty_like(feature) if all_rows_written else torch.zeros_like(feature)
-      if exchange is not None and exchange.world > 1:
-        pass
-      elif v > 0:
-        if use_sh:
-          call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), ptr(features), v,
-               feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, stream)
-        else:
-          d_feature.index_copy_(0, indexes, grad_f)
+    exchange = ctx.sh_exchange if (need[4] and use_sh and dtype == torch.float32) else None
+    if exchange is not None and exchange.world <= 1:
+      exchange = None
+    pending = exchange.start(feature, indexes, features, grad_f, cam_pos) if exchange is not None else None
 
     # ---- projection backward ----
     grads = [torch.zeros_like(t) if need[i] else None
@@ -159,6 +147,19 @@ class _RenderFunction(torch.autograd.Function):
       dd = d_depths.contiguous() if d_depths is not None else torch.zeros((v, 1), dtype=dtype, device=device)
       call(f"gs_project_bwd_{sfx}", ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(T_camera_world),
            ptr(projection), ptr(indexes), v, w, h, blur, margin, ptr(grad_g), ptr(dd), *[ptr(g) for g in grads], stream)
+
+    # ---- features (part 2) ----
+    if exchange is not None:
+      d_feature = exchange.finish(pending, feature, position, check_sh_degree(feature))
+    elif need[4]:
+      all_rows_written = use_sh and v == feature.shape[0]
+      d_feature = torch.empty_like(feature) if all_rows_written else torch.zeros_like(feature)
+      if v > 0:
+        if use_sh:
+          call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), ptr(features), v,
+               feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, stream)
+        else:
+          d_feature.index_copy_(0, indexes, grad_f)
     return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)
 
 
