@@ -1,0 +1,37 @@
+// packed_f32.cuh -- sm_100a packed fp32 arithmetic (PTX add/mul/fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2).
+//
+// One issue slot does two IEEE fp32 operations on an aligned 64-bit register pair; a scalar operand is
+// broadcast by the instruction itself (`R.F32`), so pk(x, x) costs nothing.  The raster kernels are limited by
+// issue slots, not by the FMA pipe, which is what makes this worth using.  Rounding is identical to the scalar
+// instructions (round-to-nearest, no flush-to-zero), so results do not depend on which form is used.
+#pragma once
+
+namespace gs {
+
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+}  // namespace gs

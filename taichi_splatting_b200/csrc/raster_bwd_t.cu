@@ -17,6 +17,7 @@
 //
 // Per splat this is ~1 STS.128 + 2 LDS.128 + ~1 SHFL on the LSU pipe and ~20 issue slots for the reduction,
 // against 15 SHFL and ~50 issue slots before.
+#include "packed_f32.cuh"
 #include "raster_common.cuh"
 
 namespace gs {
@@ -30,10 +31,15 @@ namespace gs {
 
 namespace bwdt {
 
+#ifdef GS_COUNT   // debug build only: work counters read by profiles/count_work.py
+__device__ unsigned long long g_count[4];   // warp iterations (padded), hit-list entries, live (pixel, splat) lanes, batches
+#endif
+
 constexpr int kTile = 16;
 constexpr int kBatch = 256;
 constexpr int kChunk = 8;          // splats per phase-1 / phase-2 round
 constexpr int kRow = 33;           // panel row stride in float4 (32 pixels + 1 pad: conflict-free transposed reads)
+constexpr int kRowG = 9;           // gpix row stride in float4 (8 pixels + 1 pad)
 constexpr int kAcc = 13;           // accumulator stride: 6 moments, 4 features, 2 heuristics, 1 pad (odd)
 constexpr float kExpScale = 0.84932180028801904f;
 
@@ -53,7 +59,7 @@ struct Smem {
   float4 b[kBatch + 1];            // (perp/sy)*k, alpha, unused
   float4 f[kBatch + 1];
   float acc[kBatch * kAcc];
-  float4 gpix[8][32];              // dL/dimage of each warp's 32 pixels
+  float4 gpix[8][4 * kRowG];       // dL/dimage of each warp's 32 pixels, rows padded (conflict-free phase-2 reads)
   float4 panel[8][kChunk * kRow];  // per-warp [splat][pixel] scratch
   unsigned short list[8][kBatch + kChunk];
   unsigned char mask[kBatch];
@@ -75,8 +81,11 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
   const int tile_x0 = (tile % P.tiles_wide) * kTile, tile_y0 = (tile / P.tiles_wide) * kTile;
   const int px = tile_x0 + (warp & 1) * 8 + (lane & 7), py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
   const bool in_bounds = px < P.width && py < P.height;
-  const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
-  const float clamp_max = P.clamp_max, thr = P.thr, sat = P.sat;
+  // pixel centre relative to the tile centre: (tx, ty) = lx (ux, wx) + ly (uy, wy) + (tx0, ty0), two FFMA2
+  const float lx = (float)((warp & 1) * 8 + (lane & 7)) - 7.5f, ly_pix = (float)((warp >> 1) * 4 + (lane >> 3)) - 7.5f;
+  const f32x2 lx2 = pk(lx, lx), ly2 = pk(ly_pix, ly_pix);
+  const float clamp_max = P.clamp_max, thr = P.thr;
+  const float t_min = 1.0f - P.sat;   // a pixel is saturated (backward.py:131) once its transmittance is <= 1 - sat
 
   // The reference tracks remaining[c] = image[c] - sum_{j<=i} f_j[c] w_j per channel (backward.py:116-176), but it is
   // only ever used through its dot product with this pixel's dL/dimage, so one scalar carries the whole state:
@@ -85,18 +94,18 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
 #pragma unroll
   for (int c = 0; c < F; ++c) gpix[c] = 0.f;
   float rem_dot = 0.f;
-  float total_weight = 1.0f;
+  float trans = 0.f;                  // transmittance 1 - sum of weights; 0 outside the image: nothing contributes
   if (in_bounds) {
     const float *img = image + ((int64_t)py * P.width + px) * F;
     const float *gi = grad_image + ((int64_t)py * P.width + px) * F;
 #pragma unroll
     for (int c = 0; c < F; ++c) { gpix[c] = gi[c]; rem_dot = fmaf(img[c], gpix[c], rem_dot); }
-    total_weight = 0.f;
+    trans = 1.0f;
   }
   {
     float4 gq = make_float4(gpix[0], F > 1 ? gpix[F > 1 ? 1 : 0] : 0.f, F > 2 ? gpix[F > 2 ? 2 : 0] : 0.f,
                             F > 3 ? gpix[F > 3 ? 3 : 0] : 0.f);
-    sm.gpix[warp][lane] = gq;
+    sm.gpix[warp][(lane >> 3) * kRowG + (lane & 7)] = gq;
   }
 
   // phase-2 role of this lane: splat s of the chunk, pixel row q of the warp rectangle
@@ -134,8 +143,11 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
       s_mx = mx; s_my = my; s_ax = ax; s_ay = ay; s_isx = isx; s_isy = isy; s_alpha = alpha;
       float ux = ax * isx * kExpScale, uy = ay * isx * kExpScale;
       float wx = -ay * isy * kExpScale, wy = ax * isy * kExpScale;
-      sm.a[tid] = make_float4(mx, my, ux, uy);
-      sm.b[tid] = make_float4(wx, wy, alpha, 0.f);
+      {
+        const float ddx = mx - ((float)tile_x0 + 8.0f), ddy = my - ((float)tile_y0 + 8.0f);
+        sm.a[tid] = make_float4(-fmaf(ux, ddx, uy * ddy), -fmaf(wx, ddx, wy * ddy), ux, wx);
+        sm.b[tid] = make_float4(uy, wy, alpha, 0.f);
+      }
       unsigned mask = 0;
       if (alpha > thr) {
         float rc = sqrtf(2.0f * __logf(alpha / thr)) * 1.001f + 0.01f;
@@ -168,7 +180,7 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
 
     // ---- per-warp ordered hit list, padded to a multiple of the chunk with the null record ----
     int nhit = 0;
-    if (!__all_sync(full, total_weight >= sat)) {
+    if (!__all_sync(full, trans <= t_min)) {
       for (int c = 0; c < nb; c += 32) {
         int j = c + lane;
         bool hit = j < nb && ((sm.mask[j] >> warp) & 1);
@@ -179,6 +191,9 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
       if (lane < kChunk) sm.list[warp][nhit + lane] = (unsigned short)kBatch;
       __syncwarp();
     }
+#ifdef GS_COUNT
+    if (lane == 0) { atomicAdd(&g_count[1], (unsigned long long)nhit); if (warp == 0) atomicAdd(&g_count[3], 1ull); }
+#endif
 
     for (int h0 = 0; h0 < nhit; h0 += kChunk) {
       // ---- phase 1: lane = pixel; 8 splats in depth order ----
@@ -189,15 +204,16 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         const float4 A = sm.a[j], B = sm.b[j];
         const float4 fv = sm.f[j];
         const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
-        float dx = fx - A.x, dy = fy - A.y;
-        float tx = dx * A.z + dy * A.w, ty = dx * B.x + dy * B.y;
+        const f32x2 t2 = fma2(lx2, pk(A.z, A.w), fma2(ly2, pk(B.x, B.y), pk(A.x, A.y)));
+        float tx, ty;
+        upk(t2, tx, ty);
         float ga = ex2_approx(-(tx * tx + ty * ty));
         float alpha = B.z * ga;
-        const bool has_grad = alpha > thr && total_weight < sat;
+        const bool has_grad = alpha > thr && trans > t_min;
         alpha = fminf(alpha, clamp_max);
-        float T_i = 1.0f - total_weight;
+        const float T_i = trans;
         float weight = has_grad ? alpha * T_i : 0.f;
-        total_weight += weight;
+        trans -= weight;
         float inv_1ma = rcp_approx(1.0f - alpha);
         float fg = feat[0] * gpix[0];
 #pragma unroll
@@ -208,18 +224,28 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         float Gp = G * ga;
         float h1 = 0.f;
         if (HEUR) {
+          // |G dpdf/dmean|_1 = |Gp| (|tx ux + ty wx| + |tx uy + ty wy|) / k^2  (t and u, w carry one factor k each)
           const float inv_k2 = 1.0f / (kExpScale * kExpScale);
-          float a1 = Gp * tx, a2 = Gp * ty;   // each carries one exp-scale factor k, as do A.zw / B.xy
-          h1 = (fabsf(a1 * A.z + a2 * B.x) + fabsf(a1 * A.w + a2 * B.y)) * inv_k2;
+          float p0, p1, q0, q1;
+          upk(mul2(t2, pk(A.z, A.w)), p0, p1);
+          upk(mul2(t2, pk(B.x, B.y)), q0, q1);
+          h1 = (fabsf(p0 + p1) + fabsf(q0 + q1)) * fabsf(Gp * inv_k2);
         }
         panel[u * kRow + lane] = make_float4(Gp, weight, G * G, h1);
+#ifdef GS_COUNT
+        {
+          unsigned live = __ballot_sync(full, has_grad);
+          if (lane == 0) { atomicAdd(&g_count[0], 1ull); atomicAdd(&g_count[2], (unsigned long long)__popc(live)); }
+        }
+#endif
       }
       __syncwarp();
 
       // ---- phase 2: lane = (splat s, pixel row q): walk the row's 8 pixels for one splat ----
       float m0 = 0.f, s1 = 0.f, s2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, hh0 = 0.f, hh1 = 0.f;
+      f32x2 f01 = pk(0.f, 0.f), f23 = pk(0.f, 0.f), hh = pk(0.f, 0.f);
       const float4 *row = panel + s * kRow + q * 8;
-      const float4 *grow = sm.gpix[warp] + q * 8;
+      const float4 *grow = sm.gpix[warp] + q * kRowG;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 v = row[i];
@@ -228,13 +254,16 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         s2 = fmaf(v.x, (float)(i * i), s2);
         if (GF) {
           const float4 g = grow[i];
-          f0 = fmaf(v.y, g.x, f0);
-          if (F > 1) f1 = fmaf(v.y, g.y, f1);
-          if (F > 2) f2 = fmaf(v.y, g.z, f2);
-          if (F > 3) f3 = fmaf(v.y, g.w, f3);
+          if (F == 1) f0 = fmaf(v.y, g.x, f0);
+          if (F >= 2) f01 = fma2(pk(g.x, g.y), pk(v.y, v.y), f01);
+          if (F == 3) f2 = fmaf(v.y, g.z, f2);
+          if (F == 4) f23 = fma2(pk(g.z, g.w), pk(v.y, v.y), f23);
         }
-        if (HEUR) { hh0 += v.z; hh1 += v.w; }
+        if (HEUR) hh = add2(hh, pk(v.z, v.w));
       }
+      if (F >= 2) upk(f01, f0, f1);
+      if (F == 4) upk(f23, f2, f3);
+      if (HEUR) upk(hh, hh0, hh1);
       // row-local -> tile-centred moments (x = bx + i, y = ly)
       const float Lx = fmaf(bx, m0, s1);
       const float Lxx = fmaf(bx, fmaf(bx, m0, 2.0f * s1), s2);
@@ -265,9 +294,9 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
           if (v[i] != 0.f) atomicAdd(dst + i, v[i]);
       }
       __syncwarp();
-      if (__all_sync(full, total_weight >= sat)) break;
+      if (__all_sync(full, trans <= t_min)) break;
     }
-    if (__all_sync(full, total_weight >= sat) && lane == 0) sm.warp_done[warp] = 1;
+    if (__all_sync(full, trans <= t_min) && lane == 0) sm.warp_done[warp] = 1;
 
     // ---- flush: one thread per staged splat ----
     __syncthreads();
@@ -354,3 +383,11 @@ template int launch_bwd_transpose<4>(const float *, const float *, const int32_t
                                      const float *, const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
 
 }  // namespace gs
+
+#ifdef GS_COUNT
+extern "C" int gs_debug_counters(unsigned long long *out4, int reset) {
+  cudaMemcpyFromSymbol(out4, gs::bwdt::g_count, sizeof(unsigned long long) * 4);
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(gs::bwdt::g_count, z, sizeof z); }
+  return 0;
+}
+#endif

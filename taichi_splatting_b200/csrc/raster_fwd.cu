@@ -17,7 +17,12 @@
 //   * the inner loop is branch-free and unrolled by 16; per-splat visibility (sum of blend weights over
 //     pixels) is reduced 16 splats at a time with one transposed butterfly (16 shuffles per 16 splats
 //     instead of 5 per splat) and one shared-memory atomic instruction per 16 splats.
+#include "packed_f32.cuh"
 #include "raster_common.cuh"
+
+#ifndef GS_PACKED
+#define GS_PACKED 1   // tile-centred affine form of (tx, ty) evaluated with FFMA2 (2 issue slots instead of 6)
+#endif
 
 namespace gs {
 
@@ -58,8 +63,17 @@ __device__ __forceinline__ unsigned stage_splat(const float *__restrict__ g, flo
   float isx = 1.0f / sx, isy = 1.0f / sy;
   float ux = ax * isx * kExpScale, uy = ay * isx * kExpScale;
   float wx = -ay * isy * kExpScale, wy = ax * isy * kExpScale;
+#if GS_PACKED
+  {
+    // (tx, ty) = X (ux, wx) + Y (uy, wy) + (tx0, ty0) with (X, Y) the pixel centre relative to the tile centre
+    const float ddx = mx - (tile_x0 + 8.0f), ddy = my - (tile_y0 + 8.0f);
+    A = make_float4(-fmaf(ux, ddx, uy * ddy), -fmaf(wx, ddx, wy * ddy), ux, wx);
+    B = make_float4(uy, wy, alpha, 0.f);
+  }
+#else
   A = make_float4(mx, my, ux, uy);
   B = make_float4(wx, wy, alpha, 0.f);
+#endif
   if (!(alpha > thr)) return 0u;
   // conservative support radius in sigma units (margin covers fp32 / ex2.approx evaluation error)
   float rc = sqrtf(2.0f * __logf(alpha / thr)) * 1.001f + 0.01f;
@@ -112,7 +126,12 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
   const int tile_x0 = (tile % P.tiles_wide) * kTile, tile_y0 = (tile / P.tiles_wide) * kTile;
   const int px = tile_x0 + (warp & 1) * 8 + (lane & 7), py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
   const bool in_bounds = px < P.width && py < P.height;
+#if GS_PACKED
+  const float lx = (float)((warp & 1) * 8 + (lane & 7)) - 7.5f, ly = (float)((warp >> 1) * 4 + (lane >> 3)) - 7.5f;
+  const f32x2 lx2 = pk(lx, lx), ly2 = pk(ly, ly);
+#else
   const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+#endif
   const float clamp_max = P.clamp_max, thr = P.thr, eps = P.fwd_eps;
 
   float accum[F];
@@ -121,7 +140,6 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
   float total_weight = in_bounds ? 0.f : 1.f;
   bool done = !in_bounds;
   float median = 0.f;
-  bool median_done = false;
   const float sat_lim = 1.0f - P.sat;
 
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
@@ -180,19 +198,37 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
         const int j = sm.list[warp][h0 + u];
         const float4 A = sm.a[j], B = sm.b[j];
         const float4 fv = sm.f[j];
+#if GS_PACKED
+        float tx, ty;
+        upk(fma2(lx2, pk(A.z, A.w), fma2(ly2, pk(B.x, B.y), pk(A.x, A.y))), tx, ty);
+#else
         float dx = fx - A.x, dy = fy - A.y;
         float tx = dx * A.z + dy * A.w, ty = dx * B.x + dy * B.y;
+#endif
         float ga = ex2_approx(-(tx * tx + ty * ty));
         float alpha = fminf(B.z * ga, clamp_max);
         const bool hit = alpha > thr && !done;
         float weight = alpha * (1.0f - total_weight);
         weight = hit ? weight : 0.f;
+        if (MEDIAN) median = (hit && total_weight < median_lim) ? B.w : median;   // last splat entered below the limit
         total_weight += weight;
         if (BLEND) {
+#if GS_PACKED
+          if (F == 1) accum[0] = fmaf(fv.x, weight, accum[0]);
+          if (F >= 2) {
+            const f32x2 w2 = pk(weight, weight);
+            upk(fma2(pk(fv.x, fv.y), w2, pk(accum[0], accum[F > 1 ? 1 : 0])), accum[0], accum[F > 1 ? 1 : 0]);
+            if (F == 3) accum[F > 2 ? 2 : 0] = fmaf(fv.z, weight, accum[F > 2 ? 2 : 0]);
+            if (F == 4)
+              upk(fma2(pk(fv.z, fv.w), w2, pk(accum[F > 2 ? 2 : 0], accum[F > 3 ? 3 : 0])), accum[F > 2 ? 2 : 0],
+                  accum[F > 3 ? 3 : 0]);
+          }
+#else
           accum[0] = fmaf(fv.x, weight, accum[0]);
           if (F > 1) accum[1] = fmaf(fv.y, weight, accum[1]);
           if (F > 2) accum[2] = fmaf(fv.z, weight, accum[2]);
           if (F > 3) accum[3] = fmaf(fv.w, weight, accum[3]);
+#endif
           done = done || (1.0f - total_weight <= eps);   // eps == 0: never (total_weight < 1 in bounds)
         } else {
           const bool trig = hit && total_weight >= sat_lim;
@@ -201,11 +237,6 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
           if (F > 2) accum[2] = trig ? fv.z : accum[2];
           if (F > 3) accum[3] = trig ? fv.w : accum[3];
           done = done || trig;
-        }
-        if (MEDIAN) {
-          const bool trig = hit && !median_done && total_weight >= median_lim;
-          median = trig ? B.w : median;
-          median_done = median_done || trig;
         }
         wv[u] = weight;
       }
@@ -232,7 +263,8 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
 #pragma unroll
     for (int c = 0; c < F; ++c) out[c] = accum[c];
     image_alpha[(int64_t)py * P.width + px] = BLEND ? total_weight : (total_weight > 0.f ? 1.f : 0.f);
-    if (MEDIAN) median_image[(int64_t)py * P.width + px] = median;
+    // the splat that crossed the limit is the last one entered below it -- if the limit was crossed at all
+    if (MEDIAN) median_image[(int64_t)py * P.width + px] = total_weight >= median_lim ? median : 0.f;
   }
 }
 
