@@ -34,4 +34,10 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   return d;
 }
 
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 }  // namespace gs

@@ -26,7 +26,7 @@ namespace gs {
 #define GS_BWDT_UNROLL 8
 #endif
 #ifndef GS_BWDT_MIN_BLOCKS
-#define GS_BWDT_MIN_BLOCKS 3
+#define GS_BWDT_MIN_BLOCKS 4
 #endif
 
 namespace bwdt {
@@ -36,9 +36,11 @@ __device__ unsigned long long g_count[4];   // warp iterations (padded), hit-lis
 #endif
 
 constexpr int kTile = 16;
-constexpr int kBatch = 256;
+constexpr int kWarps = 4;          // one warp per 8x8 pixel block; every lane owns two pixels (rows r and r + 4)
+constexpr int kThreads = kWarps * 32;
+constexpr int kBatch = kThreads;   // splats staged per round: thread j stages and finally flushes splat j
 constexpr int kChunk = 8;          // splats per phase-1 / phase-2 round
-constexpr int kRow = 33;           // panel row stride in float4 (32 pixels + 1 pad: conflict-free transposed reads)
+constexpr int kRow = 65;           // panel row stride in float4 (64 pixels + 1 pad: conflict-free transposed reads)
 constexpr int kRowG = 9;           // gpix row stride in float4 (8 pixels + 1 pad)
 constexpr int kAcc = 13;           // accumulator stride: 6 moments, 4 features, 2 heuristics, 1 pad (odd)
 constexpr float kExpScale = 0.84932180028801904f;
@@ -55,19 +57,19 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 struct Smem {
-  float4 a[kBatch + 1];            // mean.x, mean.y, (axis/sx)*k      (+1: null record that pads the hit lists)
-  float4 b[kBatch + 1];            // (perp/sy)*k, alpha, unused
+  float4 a[kBatch + 1];            // tx0, ty0, ux, wx                 (+1: null record that pads the hit lists)
+  float4 b[kBatch + 1];            // uy, wy, alpha, unused
   float4 f[kBatch + 1];
   float acc[kBatch * kAcc];
-  float4 gpix[8][4 * kRowG];       // dL/dimage of each warp's 32 pixels, rows padded (conflict-free phase-2 reads)
-  float4 panel[8][kChunk * kRow];  // per-warp [splat][pixel] scratch
-  unsigned short list[8][kBatch + kChunk];
+  float4 gpix[kWarps][8 * kRowG];  // dL/dimage of each warp's 64 pixels, rows padded (conflict-free phase-2 reads)
+  float4 panel[kWarps][kChunk * kRow];  // per-warp [splat][pixel] scratch
+  unsigned short list[kWarps][kBatch + kChunk];
   unsigned char mask[kBatch];
-  int warp_done[8];
+  int warp_done[kWarps];
 };
 
 template <int F, bool GP, bool GF, bool HEUR>
-__global__ void __launch_bounds__(kBatch, GS_BWDT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, GS_BWDT_MIN_BLOCKS)
 raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ features,
                     const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
                     const float *__restrict__ image, const float *__restrict__ grad_image, RasterParams<float> P,
@@ -79,39 +81,44 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
   const int tile_x0 = (tile % P.tiles_wide) * kTile, tile_y0 = (tile / P.tiles_wide) * kTile;
-  const int px = tile_x0 + (warp & 1) * 8 + (lane & 7), py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
-  const bool in_bounds = px < P.width && py < P.height;
-  // pixel centre relative to the tile centre: (tx, ty) = lx (ux, wx) + ly (uy, wy) + (tx0, ty0), two FFMA2
-  const float lx = (float)((warp & 1) * 8 + (lane & 7)) - 7.5f, ly_pix = (float)((warp >> 1) * 4 + (lane >> 3)) - 7.5f;
-  const f32x2 lx2 = pk(lx, lx), ly2 = pk(ly_pix, ly_pix);
+  const int bx = (warp & 1) * 8 + (lane & 7), by = (warp >> 1) * 8 + (lane >> 3);
+  const int px = tile_x0 + bx, py[2] = {tile_y0 + by, tile_y0 + by + 4};
+  const bool in_bounds[2] = {px < P.width && py[0] < P.height, px < P.width && py[1] < P.height};
+  // pixel centre relative to the tile centre: (tx, ty) = lx (ux, wx) + ly (uy, wy) + (tx0, ty0)
+  const float lx = (float)bx - 7.5f, ly0 = (float)by - 7.5f;
+  const f32x2 lx2 = pk(lx, lx), ly2[2] = {pk(ly0, ly0), pk(ly0 + 4.0f, ly0 + 4.0f)};
   const float clamp_max = P.clamp_max, thr = P.thr;
   const float t_min = 1.0f - P.sat;   // a pixel is saturated (backward.py:131) once its transmittance is <= 1 - sat
 
-  // The reference tracks remaining[c] = image[c] - sum_{j<=i} f_j[c] w_j per channel (backward.py:116-176), but it is
-  // only ever used through its dot product with this pixel's dL/dimage, so one scalar carries the whole state:
-  //   rem_dot = remaining . gpix ;  dL/dalpha = T (f . gpix) - rem_dot / (1 - alpha)
-  float gpix[F];
-#pragma unroll
-  for (int c = 0; c < F; ++c) gpix[c] = 0.f;
-  float rem_dot = 0.f;
-  float trans = 0.f;                  // transmittance 1 - sum of weights; 0 outside the image: nothing contributes
-  if (in_bounds) {
-    const float *img = image + ((int64_t)py * P.width + px) * F;
-    const float *gi = grad_image + ((int64_t)py * P.width + px) * F;
-#pragma unroll
-    for (int c = 0; c < F; ++c) { gpix[c] = gi[c]; rem_dot = fmaf(img[c], gpix[c], rem_dot); }
-    trans = 1.0f;
-  }
+  // Per-pixel state, packed over the lane's two pixels.  The reference tracks remaining[c] = image[c] -
+  // sum_{j<=i} f_j[c] w_j per channel (backward.py:116-176), but it is only ever used through its dot product with
+  // this pixel's dL/dimage, so one scalar carries it:  rneg = -(remaining . gpix);
+  //   dL/dalpha = T (f . gpix) + rneg / (1 - alpha)
+  f32x2 gpix2[F];                     // (dL/dimage[c] of pixel 0, of pixel 1)
+  float rneg[2] = {0.f, 0.f};
+  float trans[2] = {0.f, 0.f};        // transmittance 1 - sum of weights; 0 outside the image: nothing contributes
   {
-    float4 gq = make_float4(gpix[0], F > 1 ? gpix[F > 1 ? 1 : 0] : 0.f, F > 2 ? gpix[F > 2 ? 2 : 0] : 0.f,
-                            F > 3 ? gpix[F > 3 ? 3 : 0] : 0.f);
-    sm.gpix[warp][(lane >> 3) * kRowG + (lane & 7)] = gq;
+    float g[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (in_bounds[p]) {
+        const float *img = image + ((int64_t)py[p] * P.width + px) * F;
+        const float *gi = grad_image + ((int64_t)py[p] * P.width + px) * F;
+#pragma unroll
+        for (int c = 0; c < F; ++c) { g[p][c] = gi[c]; rneg[p] = fmaf(-img[c], g[p][c], rneg[p]); }
+        trans[p] = 1.0f;
+      }
+      sm.gpix[warp][((lane >> 3) + 4 * p) * kRowG + (lane & 7)] = make_float4(g[p][0], g[p][1], g[p][2], g[p][3]);
+    }
+#pragma unroll
+    for (int c = 0; c < F; ++c) gpix2[c] = pk(g[0][c], g[1][c]);
   }
 
-  // phase-2 role of this lane: splat s of the chunk, pixel row q of the warp rectangle
+  // phase-2 role of this lane: splat s of the chunk, pixel rows q and q + 4 of the warp's block
   const int s = lane & 7, q = lane >> 3;
-  const float bx = (float)((warp & 1) * 8) - 7.5f;            // tile-centred x of the row's first pixel
-  const float ly = (float)((warp >> 1) * 4 + q) - 7.5f;       // tile-centred y of the row
+  const float bx0 = (float)((warp & 1) * 8) - 7.5f;           // tile-centred x of a row's first pixel
+  const float lya = (float)((warp >> 1) * 8 + q) - 7.5f;      // tile-centred y of the two rows
+  const float lyb = lya + 4.0f;
   const int slot_base = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0);
   float4 *panel = sm.panel[warp];
 
@@ -129,7 +136,7 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
     {
       int all_done = 1;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) all_done &= sm.warp_done[w];
+      for (int w = 0; w < kWarps; ++w) all_done &= sm.warp_done[w];
       if (all_done) break;
     }
     // ---- stage (thread j owns splat j of the batch, and flushes it at the end) ----
@@ -143,25 +150,23 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
       s_mx = mx; s_my = my; s_ax = ax; s_ay = ay; s_isx = isx; s_isy = isy; s_alpha = alpha;
       float ux = ax * isx * kExpScale, uy = ay * isx * kExpScale;
       float wx = -ay * isy * kExpScale, wy = ax * isy * kExpScale;
-      {
-        const float ddx = mx - ((float)tile_x0 + 8.0f), ddy = my - ((float)tile_y0 + 8.0f);
-        sm.a[tid] = make_float4(-fmaf(ux, ddx, uy * ddy), -fmaf(wx, ddx, wy * ddy), ux, wx);
-        sm.b[tid] = make_float4(uy, wy, alpha, 0.f);
-      }
+      const float ddx = mx - ((float)tile_x0 + 8.0f), ddy = my - ((float)tile_y0 + 8.0f);
+      const float tx0 = -fmaf(ux, ddx, uy * ddy), ty0 = -fmaf(wx, ddx, wy * ddy);
+      sm.a[tid] = make_float4(tx0, ty0, ux, wx);
+      sm.b[tid] = make_float4(uy, wy, alpha, 0.f);
       unsigned mask = 0;
       if (alpha > thr) {
         float rc = sqrtf(2.0f * __logf(alpha / thr)) * 1.001f + 0.01f;
         float rcs = rc * kExpScale;
         float e1x = ax * sx, e1y = ay * sx, e2x = ay * sy, e2y = ax * sy;
         float ex = rc * sqrtf(e1x * e1x + e2x * e2x), ey = rc * sqrtf(e1y * e1y + e2y * e2y);
-        float hu = fabsf(ux) * 3.5f + fabsf(uy) * 1.5f + rcs;
-        float hw = fabsf(wx) * 3.5f + fabsf(wy) * 1.5f + rcs;
+        float hu = (fabsf(ux) + fabsf(uy)) * 3.5f + rcs;
+        float hw = (fabsf(wx) + fabsf(wy)) * 3.5f + rcs;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          float dcx = (float)(tile_x0 + (w & 1) * 8) + 4.0f - mx;
-          float dcy = (float)(tile_y0 + (w >> 1) * 4) + 2.0f - my;
-          bool hit = (fabsf(dcx) - 3.5f <= ex) && (fabsf(dcy) - 1.5f <= ey) &&
-                     (fabsf(ux * dcx + uy * dcy) <= hu) && (fabsf(wx * dcx + wy * dcy) <= hw);
+        for (int w = 0; w < kWarps; ++w) {
+          const float ox = (w & 1) ? 4.0f : -4.0f, oy = (w >> 1) ? 4.0f : -4.0f;   // block centre - tile centre
+          bool hit = (fabsf(ox - ddx) - 3.5f <= ex) && (fabsf(oy - ddy) - 3.5f <= ey) &&
+                     (fabsf(fmaf(ux, ox, fmaf(uy, oy, tx0))) <= hu) && (fabsf(fmaf(wx, ox, fmaf(wy, oy, ty0))) <= hw);
           mask |= hit ? (1u << w) : 0u;
         }
       }
@@ -180,7 +185,7 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
 
     // ---- per-warp ordered hit list, padded to a multiple of the chunk with the null record ----
     int nhit = 0;
-    if (!__all_sync(full, trans <= t_min)) {
+    if (!__all_sync(full, trans[0] <= t_min && trans[1] <= t_min)) {
       for (int c = 0; c < nb; c += 32) {
         int j = c + lane;
         bool hit = j < nb && ((sm.mask[j] >> warp) & 1);
@@ -196,7 +201,7 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
 #endif
 
     for (int h0 = 0; h0 < nhit; h0 += kChunk) {
-      // ---- phase 1: lane = pixel; 8 splats in depth order ----
+      // ---- phase 1: lane = two pixels; 8 splats in depth order ----
       constexpr int kUnroll1 = GS_BWDT_UNROLL;
 #pragma unroll kUnroll1
       for (int u = 0; u < kChunk; ++u) {
@@ -204,71 +209,101 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         const float4 A = sm.a[j], B = sm.b[j];
         const float4 fv = sm.f[j];
         const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
-        const f32x2 t2 = fma2(lx2, pk(A.z, A.w), fma2(ly2, pk(B.x, B.y), pk(A.x, A.y)));
-        float tx, ty;
-        upk(t2, tx, ty);
-        float ga = ex2_approx(-(tx * tx + ty * ty));
-        float alpha = B.z * ga;
-        const bool has_grad = alpha > thr && trans > t_min;
-        alpha = fminf(alpha, clamp_max);
-        const float T_i = trans;
-        float weight = has_grad ? alpha * T_i : 0.f;
-        trans -= weight;
-        float inv_1ma = rcp_approx(1.0f - alpha);
-        float fg = feat[0] * gpix[0];
+        const f32x2 uw_x = pk(A.z, A.w), uw_y = pk(B.x, B.y);
+        const f32x2 tbase = fma2(lx2, uw_x, pk(A.x, A.y));
+        const f32x2 t2[2] = {fma2(ly2[0], uw_y, tbase), fma2(ly2[1], uw_y, tbase)};
+        float t0x, t0y, t1x, t1y;
+        upk(t2[0], t0x, t0y);
+        upk(t2[1], t1x, t1y);
+        const float g0 = ex2_approx(-fmaf(t0x, t0x, t0y * t0y)), g1 = ex2_approx(-fmaf(t1x, t1x, t1y * t1y));
+        const f32x2 ga2 = pk(g0, g1), alpha_pt2 = pk(B.z, B.z);
+        float a0, a1;
+        upk(mul2(ga2, alpha_pt2), a0, a1);
+        const bool hg0 = a0 > thr && trans[0] > t_min, hg1 = a1 > thr && trans[1] > t_min;
+        a0 = fminf(a0, clamp_max);
+        a1 = fminf(a1, clamp_max);
+        const f32x2 a2 = pk(a0, a1), T2 = pk(trans[0], trans[1]);
+        float w0, w1;
+        upk(mul2(a2, T2), w0, w1);
+        w0 = hg0 ? w0 : 0.f;
+        w1 = hg1 ? w1 : 0.f;
+        const f32x2 w2 = pk(w0, w1);
+        upk(sub2(T2, w2), trans[0], trans[1]);
+        float om0, om1;
+        upk(sub2(pk(1.0f, 1.0f), a2), om0, om1);
+        const f32x2 inv2 = pk(rcp_approx(om0), rcp_approx(om1));
+        f32x2 fg2 = mul2(pk(feat[0], feat[0]), gpix2[0]);
 #pragma unroll
-        for (int c = 1; c < F; ++c) fg = fmaf(feat[c], gpix[c], fg);
-        rem_dot = fmaf(-weight, fg, rem_dot);
-        float alpha_grad = fmaf(-rem_dot, inv_1ma, fg * T_i);
-        float G = has_grad ? B.z * alpha_grad : 0.f;
-        float Gp = G * ga;
-        float h1 = 0.f;
+        for (int c = 1; c < F; ++c) fg2 = fma2(pk(feat[c], feat[c]), gpix2[c], fg2);
+        const f32x2 rn2 = fma2(w2, fg2, pk(rneg[0], rneg[1]));
+        upk(rn2, rneg[0], rneg[1]);
+        float G0, G1;
+        upk(mul2(alpha_pt2, fma2(rn2, inv2, mul2(fg2, T2))), G0, G1);
+        G0 = hg0 ? G0 : 0.f;
+        G1 = hg1 ? G1 : 0.f;
+        const f32x2 G2 = pk(G0, G1);
+        const f32x2 Gp2 = mul2(G2, ga2), GG2 = mul2(G2, G2);
+        float Gp0, Gp1, GG0, GG1, h0v = 0.f, h1v = 0.f;
+        upk(Gp2, Gp0, Gp1);
+        upk(GG2, GG0, GG1);
         if (HEUR) {
-          // |G dpdf/dmean|_1 = |Gp| (|tx ux + ty wx| + |tx uy + ty wy|) / k^2  (t and u, w carry one factor k each)
+          // |G dpdf/dmean|_1 = |Gp| (|tx ux + ty wx| + |tx uy + ty wy|) / k^2  (t and u, w carry one factor k each);
+          // stored signed (the bracket is >= 0), phase 2 adds the absolute value
           const float inv_k2 = 1.0f / (kExpScale * kExpScale);
-          float p0, p1, q0, q1;
-          upk(mul2(t2, pk(A.z, A.w)), p0, p1);
-          upk(mul2(t2, pk(B.x, B.y)), q0, q1);
-          h1 = (fabsf(p0 + p1) + fabsf(q0 + q1)) * fabsf(Gp * inv_k2);
+          float p0, p1, q0, q1, r0, r1, v0, v1;
+          upk(mul2(t2[0], uw_x), p0, p1);
+          upk(mul2(t2[0], uw_y), q0, q1);
+          upk(mul2(t2[1], uw_x), r0, r1);
+          upk(mul2(t2[1], uw_y), v0, v1);
+          const f32x2 br2 = pk(fabsf(p0 + p1) + fabsf(q0 + q1), fabsf(r0 + r1) + fabsf(v0 + v1));
+          upk(mul2(br2, mul2(Gp2, pk(inv_k2, inv_k2))), h0v, h1v);
         }
-        panel[u * kRow + lane] = make_float4(Gp, weight, G * G, h1);
+        panel[u * kRow + lane] = make_float4(Gp0, w0, GG0, h0v);
+        panel[u * kRow + 32 + lane] = make_float4(Gp1, w1, GG1, h1v);
 #ifdef GS_COUNT
         {
-          unsigned live = __ballot_sync(full, has_grad);
-          if (lane == 0) { atomicAdd(&g_count[0], 1ull); atomicAdd(&g_count[2], (unsigned long long)__popc(live)); }
+          unsigned live = __ballot_sync(full, hg0), live1 = __ballot_sync(full, hg1);
+          if (lane == 0) { atomicAdd(&g_count[0], 1ull); atomicAdd(&g_count[2], (unsigned long long)(__popc(live) + __popc(live1))); }
         }
 #endif
       }
       __syncwarp();
 
-      // ---- phase 2: lane = (splat s, pixel row q): walk the row's 8 pixels for one splat ----
-      float m0 = 0.f, s1 = 0.f, s2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, hh0 = 0.f, hh1 = 0.f;
-      f32x2 f01 = pk(0.f, 0.f), f23 = pk(0.f, 0.f), hh = pk(0.f, 0.f);
-      const float4 *row = panel + s * kRow + q * 8;
-      const float4 *grow = sm.gpix[warp] + q * kRowG;
+      // ---- phase 2: lane = (splat s, rows q and q + 4): walk the 16 pixels of the two rows for one splat ----
+      float m0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, hh0 = 0.f, hh1 = 0.f;
+      f32x2 f01 = pk(0.f, 0.f), f23 = pk(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 v = row[i];
-        m0 += v.x;
-        s1 = fmaf(v.x, (float)i, s1);
-        s2 = fmaf(v.x, (float)(i * i), s2);
-        if (GF) {
-          const float4 g = grow[i];
-          if (F == 1) f0 = fmaf(v.y, g.x, f0);
-          if (F >= 2) f01 = fma2(pk(g.x, g.y), pk(v.y, v.y), f01);
-          if (F == 3) f2 = fmaf(v.y, g.z, f2);
-          if (F == 4) f23 = fma2(pk(g.z, g.w), pk(v.y, v.y), f23);
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const float4 *row = panel + s * kRow + hrow * 32 + q * 8;
+        const float4 *grow = sm.gpix[warp] + (q + 4 * hrow) * kRowG;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = row[i];
+          m0[hrow] += v.x;
+          s1[hrow] = fmaf(v.x, (float)i, s1[hrow]);
+          s2[hrow] = fmaf(v.x, (float)(i * i), s2[hrow]);
+          if (GF) {
+            const float4 g = grow[i];
+            if (F == 1) f0 = fmaf(v.y, g.x, f0);
+            if (F >= 2) f01 = fma2(pk(g.x, g.y), pk(v.y, v.y), f01);
+            if (F == 3) f2 = fmaf(v.y, g.z, f2);
+            if (F == 4) f23 = fma2(pk(g.z, g.w), pk(v.y, v.y), f23);
+          }
+          if (HEUR) { hh0 += v.z; hh1 += fabsf(v.w); }
         }
-        if (HEUR) hh = add2(hh, pk(v.z, v.w));
       }
       if (F >= 2) upk(f01, f0, f1);
       if (F == 4) upk(f23, f2, f3);
-      if (HEUR) upk(hh, hh0, hh1);
-      // row-local -> tile-centred moments (x = bx + i, y = ly)
-      const float Lx = fmaf(bx, m0, s1);
-      const float Lxx = fmaf(bx, fmaf(bx, m0, 2.0f * s1), s2);
-      float v[12] = {m0, Lx, ly * m0, Lxx, ly * Lx, ly * ly * m0, f0, f1, f2, f3, hh0, hh1};
-      // sum over the 4 rows with a 2-stage transposed butterfly: 6 + 3 shuffles, 3 finished sums per lane
+      // row-local -> tile-centred moments (x = bx0 + i, y = lya | lyb)
+      const float Lxa = fmaf(bx0, m0[0], s1[0]), Lxb = fmaf(bx0, m0[1], s1[1]);
+      const float M0 = m0[0] + m0[1], S1 = s1[0] + s1[1], S2 = s2[0] + s2[1];
+      const float Lxx = fmaf(bx0, fmaf(bx0, M0, 2.0f * S1), S2);
+      const float Ly = fmaf(lya, m0[0], lyb * m0[1]);
+      const float Lxy = fmaf(lya, Lxa, lyb * Lxb);
+      const float Lyy = fmaf(lya * lya, m0[0], lyb * lyb * m0[1]);
+      float v[12] = {M0, Lxa + Lxb, Ly, Lxx, Lxy, Lyy, f0, f1, f2, f3, hh0, hh1};
+      // sum over the 4 row pairs with a 2-stage transposed butterfly: 6 + 3 shuffles, 3 finished sums per lane
       {
         const bool up = (lane & 16) != 0;
 #pragma unroll
@@ -294,9 +329,9 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
           if (v[i] != 0.f) atomicAdd(dst + i, v[i]);
       }
       __syncwarp();
-      if (__all_sync(full, trans <= t_min)) break;
+      if (__all_sync(full, trans[0] <= t_min && trans[1] <= t_min)) break;
     }
-    if (__all_sync(full, trans <= t_min) && lane == 0) sm.warp_done[warp] = 1;
+    if (__all_sync(full, trans[0] <= t_min && trans[1] <= t_min) && lane == 0) sm.warp_done[warp] = 1;
 
     // ---- flush: one thread per staged splat ----
     __syncthreads();
@@ -357,7 +392,7 @@ int launch_bwd_transpose(const float *points, const float *features, const int32
       GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
       configured = true;                                                                                        \
     }                                                                                                           \
-    kern<<<tiles, bwdt::kBatch, smem, stream>>>(points, features, ranges, o2p, image, grad_image, P,            \
+    kern<<<tiles, bwdt::kThreads, smem, stream>>>(points, features, ranges, o2p, image, grad_image, P,            \
                                                 grad_points, grad_features, heuristic);                         \
   } while (0)
   if (gp && gf && he) GS_BWDT(true, true, true);

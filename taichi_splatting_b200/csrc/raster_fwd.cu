@@ -17,12 +17,11 @@
 //   * the inner loop is branch-free and unrolled by 16; per-splat visibility (sum of blend weights over
 //     pixels) is reduced 16 splats at a time with one transposed butterfly (16 shuffles per 16 splats
 //     instead of 5 per splat) and one shared-memory atomic instruction per 16 splats.
+#include <type_traits>
+
 #include "packed_f32.cuh"
 #include "raster_common.cuh"
 
-#ifndef GS_PACKED
-#define GS_PACKED 1   // tile-centred affine form of (tx, ty) evaluated with FFMA2 (2 issue slots instead of 6)
-#endif
 
 namespace gs {
 
@@ -33,6 +32,8 @@ int raster_fwd_generic(const real *points, const real *features, const int32_t *
 
 constexpr int kTile = 16;
 constexpr int kBatch = 256;
+constexpr int kWarps = 4;             // one warp per 8x8 pixel block of the tile
+constexpr int kThreads = kWarps * 32;
 #ifndef GS_FWD_UNROLL
 #define GS_FWD_UNROLL 16
 #endif
@@ -46,49 +47,42 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 struct FwdSmem {
-  float4 a[kBatch + 1];    // mean.x, mean.y, (axis/sx)*k          (+1: null record for list padding)
-  float4 b[kBatch + 1];    // (perp/sy)*k, alpha, depth
+  float4 a[kBatch + 1];    // tx0, ty0, ux, wx   (t = (tx, ty) at the tile centre; u = axis/sx*k, w = perp/sy*k)
+  float4 b[kBatch + 1];    // uy, wy, alpha, depth                     (+1: null record for list padding)
   float4 f[kBatch + 1];    // features (F <= 4)
   int id[kBatch];
   float vis[kBatch + 1];
   unsigned char mask[kBatch];
-  unsigned short list[8][kBatch + kUnroll];
-  int warp_done[8];
+  unsigned short list[kWarps][kBatch + kUnroll];
+  int warp_done[kWarps];
 };
 
-// Stage one splat: returns the 8-bit mask of warp rectangles it can touch.
+// Stage one splat: digested records and the 4-bit mask of 8x8 pixel blocks it can touch.
+// (tx, ty) = X (ux, wx) + Y (uy, wy) + (tx0, ty0) with (X, Y) the pixel centre relative to the tile centre.
 __device__ __forceinline__ unsigned stage_splat(const float *__restrict__ g, float thr, float tile_x0,
                                                 float tile_y0, float4 &A, float4 &B) {
   float mx = g[0], my = g[1], ax = g[2], ay = g[3], sx = g[4], sy = g[5], alpha = g[6];
   float isx = 1.0f / sx, isy = 1.0f / sy;
   float ux = ax * isx * kExpScale, uy = ay * isx * kExpScale;
   float wx = -ay * isy * kExpScale, wy = ax * isy * kExpScale;
-#if GS_PACKED
-  {
-    // (tx, ty) = X (ux, wx) + Y (uy, wy) + (tx0, ty0) with (X, Y) the pixel centre relative to the tile centre
-    const float ddx = mx - (tile_x0 + 8.0f), ddy = my - (tile_y0 + 8.0f);
-    A = make_float4(-fmaf(ux, ddx, uy * ddy), -fmaf(wx, ddx, wy * ddy), ux, wx);
-    B = make_float4(uy, wy, alpha, 0.f);
-  }
-#else
-  A = make_float4(mx, my, ux, uy);
-  B = make_float4(wx, wy, alpha, 0.f);
-#endif
+  const float ddx = mx - (tile_x0 + 8.0f), ddy = my - (tile_y0 + 8.0f);
+  const float tx0 = -fmaf(ux, ddx, uy * ddy), ty0 = -fmaf(wx, ddx, wy * ddy);
+  A = make_float4(tx0, ty0, ux, wx);
+  B = make_float4(uy, wy, alpha, 0.f);
   if (!(alpha > thr)) return 0u;
   // conservative support radius in sigma units (margin covers fp32 / ex2.approx evaluation error)
   float rc = sqrtf(2.0f * __logf(alpha / thr)) * 1.001f + 0.01f;
   float rcs = rc * kExpScale;
   float e1x = ax * sx, e1y = ay * sx, e2x = ay * sy, e2y = ax * sy;
   float ex = rc * sqrtf(e1x * e1x + e2x * e2x), ey = rc * sqrtf(e1y * e1y + e2y * e2y);
-  float hu = fabsf(ux) * 3.5f + fabsf(uy) * 1.5f + rcs;
-  float hw = fabsf(wx) * 3.5f + fabsf(wy) * 1.5f + rcs;
+  float hu = (fabsf(ux) + fabsf(uy)) * 3.5f + rcs;     // pixel centres of a block span +-3.5 around its centre
+  float hw = (fabsf(wx) + fabsf(wy)) * 3.5f + rcs;
   unsigned mask = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    float dcx = tile_x0 + (float)((w & 1) * 8) + 4.0f - mx;
-    float dcy = tile_y0 + (float)((w >> 1) * 4) + 2.0f - my;
-    bool hit = (fabsf(dcx) - 3.5f <= ex) && (fabsf(dcy) - 1.5f <= ey) &&
-               (fabsf(ux * dcx + uy * dcy) <= hu) && (fabsf(wx * dcx + wy * dcy) <= hw);
+  for (int w = 0; w < kWarps; ++w) {
+    const float ox = (w & 1) ? 4.0f : -4.0f, oy = (w >> 1) ? 4.0f : -4.0f;   // block centre - tile centre
+    bool hit = (fabsf(ox - ddx) - 3.5f <= ex) && (fabsf(oy - ddy) - 3.5f <= ey) &&
+               (fabsf(fmaf(ux, ox, fmaf(uy, oy, tx0))) <= hu) && (fabsf(fmaf(wx, ox, fmaf(wy, oy, ty0))) <= hw);
     mask |= hit ? (1u << w) : 0u;
   }
   return mask;
@@ -111,36 +105,39 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
 }
 
 #ifndef GS_FWD_MIN_BLOCKS
-#define GS_FWD_MIN_BLOCKS 3
+#define GS_FWD_MIN_BLOCKS 6
 #endif
+// Every lane owns TWO pixels of its warp's 8x8 block -- column (lane & 7), rows (lane >> 3) and (lane >> 3) + 4 --
+// so one broadcast LDS.128 of a splat record feeds 64 pixel evaluations (the kernel is bound by the shared-memory
+// data pipe, ~2.7 cycles per broadcast LDS.128), and the two pixels share packed FFMA2 / FMUL2 / FADD2 issue slots.
 template <int F, bool VIS, bool BLEND, bool MEDIAN>
-__global__ void __launch_bounds__(kBatch, GS_FWD_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, GS_FWD_MIN_BLOCKS)
 raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ features,
                   const float *__restrict__ depths, const int32_t *__restrict__ ranges,
                   const int32_t *__restrict__ overlap_to_point, RasterParams<float> P, float median_lim,
                   float *__restrict__ image, float *__restrict__ image_alpha, float *__restrict__ visibility,
                   float *__restrict__ median_image) {
   __shared__ FwdSmem sm;
+  const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
   const int tile_x0 = (tile % P.tiles_wide) * kTile, tile_y0 = (tile / P.tiles_wide) * kTile;
-  const int px = tile_x0 + (warp & 1) * 8 + (lane & 7), py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
-  const bool in_bounds = px < P.width && py < P.height;
-#if GS_PACKED
-  const float lx = (float)((warp & 1) * 8 + (lane & 7)) - 7.5f, ly = (float)((warp >> 1) * 4 + (lane >> 3)) - 7.5f;
-  const f32x2 lx2 = pk(lx, lx), ly2 = pk(ly, ly);
-#else
-  const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
-#endif
+  const int bx = (warp & 1) * 8 + (lane & 7), by = (warp >> 1) * 8 + (lane >> 3);
+  const int px = tile_x0 + bx, py[2] = {tile_y0 + by, tile_y0 + by + 4};
+  const bool in_bounds[2] = {px < P.width && py[0] < P.height, px < P.width && py[1] < P.height};
+  const float lx = (float)bx - 7.5f, ly0 = (float)by - 7.5f;
+  const f32x2 lx2 = pk(lx, lx), ly2[2] = {pk(ly0, ly0), pk(ly0 + 4.0f, ly0 + 4.0f)};
   const float clamp_max = P.clamp_max, thr = P.thr, eps = P.fwd_eps;
+  const float median_trans = 1.0f - median_lim;   // sum of weights < lim  <=>  transmittance > 1 - lim
+  const float sat_trans = P.sat;                  // non-blend mode: sum of weights >= 1 - sat <=> transmittance <= sat
 
-  float accum[F];
+  float accum[2][F];
 #pragma unroll
-  for (int c = 0; c < F; ++c) accum[c] = 0.f;
-  float total_weight = in_bounds ? 0.f : 1.f;
-  bool done = !in_bounds;
-  float median = 0.f;
-  const float sat_lim = 1.0f - P.sat;
+  for (int c = 0; c < F; ++c) accum[0][c] = accum[1][c] = 0.f;
+  // transmittance 1 - sum of weights; 0 outside the image, where nothing can contribute (forward.py:49-52)
+  float trans[2] = {in_bounds[0] ? 1.f : 0.f, in_bounds[1] ? 1.f : 0.f};
+  bool done[2] = {!in_bounds[0], !in_bounds[1]};   // non-blend mode only: pixel frozen after its trigger
+  float median[2] = {0.f, 0.f};
 
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
   if (lane == 0) sm.warp_done[warp] = 0;
@@ -156,34 +153,37 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
     {
       int all_done = 1;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) all_done &= sm.warp_done[w];
+      for (int w = 0; w < kWarps; ++w) all_done &= sm.warp_done[w];
       if (all_done) break;
     }
-    if (tid < nb) {
-      int id = overlap_to_point[base + tid];
+    for (int j = tid; j < nb; j += kThreads) {
+      int id = overlap_to_point[base + j];
       float4 A, B;
       unsigned m = stage_splat(points + 7 * (int64_t)id, thr, (float)tile_x0, (float)tile_y0, A, B);
       if (MEDIAN) B.w = depths[id];
-      sm.a[tid] = A; sm.b[tid] = B;
+      sm.a[j] = A; sm.b[j] = B;
       float4 fv = make_float4(0.f, 0.f, 0.f, 0.f);
       const float *fp = features + (int64_t)F * id;
       fv.x = fp[0];
       if (F > 1) fv.y = fp[1];
       if (F > 2) fv.z = fp[2];
       if (F > 3) fv.w = fp[3];
-      sm.f[tid] = fv;
-      sm.mask[tid] = (unsigned char)m;
-      if (VIS) { sm.id[tid] = id; sm.vis[tid] = 0.f; }
+      sm.f[j] = fv;
+      sm.mask[j] = (unsigned char)m;
+      if (VIS) { sm.id[j] = id; sm.vis[j] = 0.f; }
     }
     __syncthreads();
 
-    // per-warp ordered compaction of the splats that can touch this warp's 8x4 pixels
+    // a warp is finished when neither of its pixels can change any more
+    const bool lane_done = BLEND ? (trans[0] <= eps && trans[1] <= eps) : (done[0] && done[1]);
+
+    // per-warp ordered compaction of the splats that can touch this warp's 8x8 pixels
     int nhit = 0;
-    if (!__all_sync(0xffffffffu, done)) {
+    if (!__all_sync(full, lane_done)) {
       for (int c = 0; c < nb; c += 32) {
         int j = c + lane;
         bool hit = j < nb && ((sm.mask[j] >> warp) & 1);
-        unsigned bal = __ballot_sync(0xffffffffu, hit);
+        unsigned bal = __ballot_sync(full, hit);
         if (hit) sm.list[warp][nhit + __popc(bal & ((1u << lane) - 1))] = (unsigned short)j;
         nhit += __popc(bal);
       }
@@ -193,78 +193,92 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
 
     for (int h0 = 0; h0 < nhit; h0 += kUnroll) {
       float wv[kUnroll];
+      // one unrolled chunk of the sweep; the median bookkeeping is compiled out once every pixel of the warp has
+      // crossed the median limit (it happens within the first few splats of a pixel)
+      auto sweep = [&](auto median_tag) {
+      constexpr bool kMedian = decltype(median_tag)::value;
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int j = sm.list[warp][h0 + u];
         const float4 A = sm.a[j], B = sm.b[j];
         const float4 fv = sm.f[j];
-#if GS_PACKED
-        float tx, ty;
-        upk(fma2(lx2, pk(A.z, A.w), fma2(ly2, pk(B.x, B.y), pk(A.x, A.y))), tx, ty);
-#else
-        float dx = fx - A.x, dy = fy - A.y;
-        float tx = dx * A.z + dy * A.w, ty = dx * B.x + dy * B.y;
-#endif
-        float ga = ex2_approx(-(tx * tx + ty * ty));
-        float alpha = fminf(B.z * ga, clamp_max);
-        const bool hit = alpha > thr && !done;
-        float weight = alpha * (1.0f - total_weight);
-        weight = hit ? weight : 0.f;
-        if (MEDIAN) median = (hit && total_weight < median_lim) ? B.w : median;   // last splat entered below the limit
-        total_weight += weight;
+        const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
+        const f32x2 tbase = fma2(lx2, pk(A.z, A.w), pk(A.x, A.y)), uw_y = pk(B.x, B.y);
+        float t0x, t0y, t1x, t1y;
+        upk(fma2(ly2[0], uw_y, tbase), t0x, t0y);
+        upk(fma2(ly2[1], uw_y, tbase), t1x, t1y);
+        const float g0 = ex2_approx(-fmaf(t0x, t0x, t0y * t0y)), g1 = ex2_approx(-fmaf(t1x, t1x, t1y * t1y));
+        float alpha[2], weight[2];
+        upk(mul2(pk(g0, g1), pk(B.z, B.z)), alpha[0], alpha[1]);
+        alpha[0] = fminf(alpha[0], clamp_max);
+        alpha[1] = fminf(alpha[1], clamp_max);
         if (BLEND) {
-#if GS_PACKED
-          if (F == 1) accum[0] = fmaf(fv.x, weight, accum[0]);
-          if (F >= 2) {
-            const f32x2 w2 = pk(weight, weight);
-            upk(fma2(pk(fv.x, fv.y), w2, pk(accum[0], accum[F > 1 ? 1 : 0])), accum[0], accum[F > 1 ? 1 : 0]);
-            if (F == 3) accum[F > 2 ? 2 : 0] = fmaf(fv.z, weight, accum[F > 2 ? 2 : 0]);
-            if (F == 4)
-              upk(fma2(pk(fv.z, fv.w), w2, pk(accum[F > 2 ? 2 : 0], accum[F > 3 ? 3 : 0])), accum[F > 2 ? 2 : 0],
-                  accum[F > 3 ? 3 : 0]);
+          // no per-splat early-out test: a pixel below eps keeps compositing (as the reference does, D2) until
+          // the whole warp is below eps; pixels outside the image have trans == 0 and so weight == 0.
+          const bool hit[2] = {alpha[0] > thr, alpha[1] > thr};
+          upk(mul2(pk(alpha[0], alpha[1]), pk(trans[0], trans[1])), weight[0], weight[1]);
+          weight[0] = hit[0] ? weight[0] : 0.f;
+          weight[1] = hit[1] ? weight[1] : 0.f;
+          if (kMedian) {   // the splat that crosses the limit is the last one entered below it
+            median[0] = (hit[0] && trans[0] > median_trans) ? B.w : median[0];
+            median[1] = (hit[1] && trans[1] > median_trans) ? B.w : median[1];
           }
-#else
-          accum[0] = fmaf(fv.x, weight, accum[0]);
-          if (F > 1) accum[1] = fmaf(fv.y, weight, accum[1]);
-          if (F > 2) accum[2] = fmaf(fv.z, weight, accum[2]);
-          if (F > 3) accum[3] = fmaf(fv.w, weight, accum[3]);
-#endif
-          done = done || (1.0f - total_weight <= eps);   // eps == 0: never (total_weight < 1 in bounds)
+          upk(sub2(pk(trans[0], trans[1]), pk(weight[0], weight[1])), trans[0], trans[1]);
+          const f32x2 w2 = pk(weight[0], weight[1]);
+#pragma unroll
+          for (int c = 0; c < F; ++c)
+            upk(fma2(pk(feat[c], feat[c]), w2, pk(accum[0][c], accum[1][c])), accum[0][c], accum[1][c]);
         } else {
-          const bool trig = hit && total_weight >= sat_lim;
-          accum[0] = trig ? fv.x : accum[0];
-          if (F > 1) accum[1] = trig ? fv.y : accum[1];
-          if (F > 2) accum[2] = trig ? fv.z : accum[2];
-          if (F > 3) accum[3] = trig ? fv.w : accum[3];
-          done = done || trig;
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const bool hit = alpha[p] > thr && !done[p];
+            weight[p] = hit ? alpha[p] * trans[p] : 0.f;
+            trans[p] -= weight[p];
+            const bool trig = hit && trans[p] <= sat_trans;
+#pragma unroll
+            for (int c = 0; c < F; ++c) accum[p][c] = trig ? feat[c] : accum[p][c];
+            done[p] = done[p] || trig;
+          }
         }
-        wv[u] = weight;
+        wv[u] = weight[0] + weight[1];
       }
+      };
+      if (MEDIAN && !__all_sync(full, trans[0] <= median_trans && trans[1] <= median_trans))
+        sweep(std::true_type{});
+      else
+        sweep(std::false_type{});
       if (VIS) {
         warp_transpose_reduce16(wv, lane);
         const int h = h0 + (lane >> 1);
         if ((lane & 1) == 0 && h < nhit && wv[0] != 0.f) atomicAdd(&sm.vis[sm.list[warp][h]], wv[0]);
       }
-      if (__all_sync(0xffffffffu, done)) break;
+      const bool now_done = BLEND ? (trans[0] <= eps && trans[1] <= eps) : (done[0] && done[1]);
+      if (__all_sync(full, now_done)) break;
     }
-    if (__all_sync(0xffffffffu, done) && lane == 0) sm.warp_done[warp] = 1;
+    {
+      const bool now_done = BLEND ? (trans[0] <= eps && trans[1] <= eps) : (done[0] && done[1]);
+      if (__all_sync(full, now_done) && lane == 0) sm.warp_done[warp] = 1;
+    }
 
     if (VIS) {
       __syncthreads();
-      if (tid < nb) {
-        float vsum = sm.vis[tid];
-        if (vsum != 0.f) atomicAdd(visibility + sm.id[tid], vsum);
+      for (int j = tid; j < nb; j += kThreads) {
+        float vsum = sm.vis[j];
+        if (vsum != 0.f) atomicAdd(visibility + sm.id[j], vsum);
       }
     }
   }
 
-  if (in_bounds) {
-    float *out = image + ((int64_t)py * P.width + px) * F;
 #pragma unroll
-    for (int c = 0; c < F; ++c) out[c] = accum[c];
-    image_alpha[(int64_t)py * P.width + px] = BLEND ? total_weight : (total_weight > 0.f ? 1.f : 0.f);
-    // the splat that crossed the limit is the last one entered below it -- if the limit was crossed at all
-    if (MEDIAN) median_image[(int64_t)py * P.width + px] = total_weight >= median_lim ? median : 0.f;
+  for (int p = 0; p < 2; ++p) {
+    if (!in_bounds[p]) continue;
+    const int64_t pix = (int64_t)py[p] * P.width + px;
+    float *out = image + pix * F;
+#pragma unroll
+    for (int c = 0; c < F; ++c) out[c] = accum[p][c];
+    const float total_weight = 1.0f - trans[p];
+    image_alpha[pix] = BLEND ? total_weight : (total_weight > 0.f ? 1.f : 0.f);
+    if (MEDIAN) median_image[pix] = trans[p] <= median_trans ? median[p] : 0.f;
   }
 }
 
@@ -275,7 +289,7 @@ static int launch_fwd(const float *points, const float *features, const float *d
   const bool vis = P.vis && visibility != nullptr;
   const bool med = median_image != nullptr;
 #define GS_FWD(VIS, BLEND, MED)                                                                              \
-  raster_fwd_kernel<F, VIS, BLEND, MED><<<tiles, kBatch, 0, stream>>>(points, features, depths, ranges, o2p, \
+  raster_fwd_kernel<F, VIS, BLEND, MED><<<tiles, kThreads, 0, stream>>>(points, features, depths, ranges, o2p, \
                                                                       P, median_lim, image, image_alpha,    \
                                                                       visibility, median_image)
   if (P.blend) {
