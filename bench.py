@@ -195,7 +195,7 @@ def run_ours(args):
   # ---- device-resident arm ----
   for _ in range(max(args.warmup, 3)):
     out, _ = step(gaussians, camera)
-  prof = _lib.Profiler(only={"gs_raster_bwd_f32", "gs_raster_fwd_f32"})
+  prof = _lib.Profiler(only={"gs_raster_bwd_digest_f32", "gs_raster_fwd_digest_f32"})
   _lib.profiler = prof
   with ClockSampler(local_rank) as clocks:
     total_ms = timed(lambda: step(gaussians, camera), args.steps)
@@ -280,7 +280,7 @@ def run_ours(args):
   P = w * h
   stage_bytes, total_bytes = algorithmic_bytes(n, V, K, P, T, 3, (deg + 1)**2)
   hbm_peak, peak_kind = peaks()
-  bwd_ms = stage_hot.get("gs_raster_bwd_f32")
+  bwd_ms = stage_hot.get("gs_raster_bwd_digest_f32")
   traffic = None
   try:
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:

@@ -223,6 +223,28 @@ int gs_raster_bwd_f64(const double *points, const double *features, const int32_
                       const gs_raster_config *config, double *grad_points, double *grad_features,
                       double *point_heuristic, void *stream);
 
+/* ---- Raster digest: per-Gaussian records shared by the tuned forward and backward kernels ----------------------
+ * The reference's rasteriser reads the packed (V,7) Gaussians and (V,F) features once per (tile, splat) overlap
+ * (rasterizer/forward.py:82-97 load_point / backward.py:95-112).  The tuned fp32 kernels (tile_size 16, no
+ * antialias, 1..4 features) instead gather a 64-byte, 64-byte-aligned record per visible Gaussian holding the
+ * exp-scaled inverse-sigma basis, alpha, depth, features, support radius and 1/sigma -- written once per frame by
+ * gs_raster_digest_f32 and passed to gs_raster_fwd_digest_f32 / gs_raster_bwd_digest_f32 (same arguments as
+ * gs_raster_fwd_median_f32 / gs_raster_bwd_f32 with the three input tensors replaced by the digest; median_image
+ * may be NULL).  gs_raster_fwd_f32 / gs_raster_fwd_median_f32 / gs_raster_bwd_f32 keep the reference-shaped
+ * argument lists and build the digest into library-owned scratch (one grow-only buffer per device and stream).
+ * `depths` may be NULL when no median depth is wanted.  Returns GS_ERR_UNSUPPORTED for other configurations.   */
+int gs_raster_digest_bytes(int64_t v, size_t *bytes);
+int gs_raster_digest_f32(const float *points, const float *features, const float *depths, int64_t v,
+                         int32_t num_features, const gs_raster_config *config, void *digest, void *stream);
+int gs_raster_fwd_digest_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point,
+                             int64_t v, int64_t k, int32_t width, int32_t height, int32_t num_features,
+                             const gs_raster_config *config, double median_threshold, float *image,
+                             float *image_alpha, float *visibility, float *median_image, void *stream);
+int gs_raster_bwd_digest_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point,
+                             const float *image, const float *grad_image, int64_t v, int64_t k, int32_t width,
+                             int32_t height, int32_t num_features, const gs_raster_config *config,
+                             float *grad_points, float *grad_features, float *point_heuristic, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,10 @@ SIGNATURES = {
     "gs_raster_fwd_f32": (_RASTER_FWD, c_int32), "gs_raster_fwd_f64": (_RASTER_FWD, c_int32),
     "gs_raster_fwd_median_f32": ([P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_f32": (_RASTER_BWD, c_int32), "gs_raster_bwd_f64": (_RASTER_BWD, c_int32),
+    "gs_raster_digest_bytes": ([I64, POINTER(SZ)], c_int32),
+    "gs_raster_digest_f32": ([P, P, P, I64, I32, POINTER(RasterConfigC), P, P], c_int32),
+    "gs_raster_fwd_digest_f32": ([P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
+    "gs_raster_bwd_digest_f32": ([P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
 }
 
 _lib = None
@@ -101,8 +105,8 @@ OWN_KERNELS = {
     "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_camera_position_f32": 1, "gs_camera_position_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
     "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_sh_bwd_views_f32": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
     "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1,
-    "gs_tile_ranges_from_tiles": 1, "gs_raster_fwd_f32": 1, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 1, "gs_raster_bwd_f32": 1,
-    "gs_raster_bwd_f64": 1,
+    "gs_tile_ranges_from_tiles": 1, "gs_raster_fwd_f32": 2, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 2, "gs_raster_bwd_f32": 2,
+    "gs_raster_bwd_f64": 1, "gs_raster_digest_f32": 1, "gs_raster_fwd_digest_f32": 1, "gs_raster_bwd_digest_f32": 1,
 }
 
 

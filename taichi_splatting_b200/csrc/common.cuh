@@ -9,6 +9,7 @@
 namespace gs {
 
 void set_error(const char *fmt, ...);
+void *stream_workspace(cudaStream_t stream, size_t bytes);   // api.cu: library-owned scratch per (device, stream)
 
 #define GS_CHECK_ARG(cond, ...)                 \
   do {                                          \

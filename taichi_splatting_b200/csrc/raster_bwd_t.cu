@@ -40,7 +40,7 @@ constexpr int kWarps = 4;          // one warp per 8x8 pixel block; every lane o
 constexpr int kThreads = kWarps * 32;
 constexpr int kBatch = kThreads;   // splats staged per round: thread j stages and finally flushes splat j
 constexpr int kChunk = 8;          // splats per phase-1 / phase-2 round
-constexpr int kRow = 65;           // panel row stride in float4 (64 pixels + 1 pad: conflict-free transposed reads)
+constexpr int kRow = 33;           // panel row stride in float4 (32 lanes + 1 pad: conflict-free transposed reads)
 constexpr int kRowG = 9;           // gpix row stride in float4 (8 pixels + 1 pad)
 constexpr int kAcc = 13;           // accumulator stride: 6 moments, 4 features, 2 heuristics, 1 pad (odd)
 constexpr float kExpScale = 0.84932180028801904f;
@@ -60,18 +60,21 @@ struct Smem {
   float4 a[kBatch + 1];            // tx0, ty0, ux, wx                 (+1: null record that pads the hit lists)
   float4 b[kBatch + 1];            // uy, wy, alpha, unused
   float4 f[kBatch + 1];
+  float4 c[kBatch];                // mean - tile centre, 1/sigma.x, 1/sigma.y  (read by the flush only)
   float acc[kBatch * kAcc];
   float4 gpix[kWarps][8 * kRowG];  // dL/dimage of each warp's 64 pixels, rows padded (conflict-free phase-2 reads)
-  float4 panel[kWarps][kChunk * kRow];  // per-warp [splat][pixel] scratch
-  unsigned short list[kWarps][kBatch + kChunk];
+  float4 panel0[kWarps][kChunk * kRow];  // per-warp [splat][lane] scratch: {S, D, sum G^2, sum |G dpdf/dmean|}
+  float4 panel1[kWarps][kChunk * kRow];  //                                 {sum weight dL/dimage[c]}
+  // byte offsets (16 j) of the staged records a warp must visit; entry k lives at index k + 3, so that the eight
+  // "next" entries of a chunk (k = h0 + 1 .. h0 + 8) are two aligned 16-byte loads
+  alignas(16) unsigned list[kWarps][kBatch + kChunk + 4];
   unsigned char mask[kBatch];
   int warp_done[kWarps];
 };
 
 template <int F, bool GP, bool GF, bool HEUR>
 __global__ void __launch_bounds__(kThreads, GS_BWDT_MIN_BLOCKS)
-raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ features,
-                    const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
+raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
                     const float *__restrict__ image, const float *__restrict__ grad_image, RasterParams<float> P,
                     float *__restrict__ grad_points, float *__restrict__ grad_features,
                     float *__restrict__ heuristic) {
@@ -117,10 +120,17 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
   // phase-2 role of this lane: splat s of the chunk, pixel rows q and q + 4 of the warp's block
   const int s = lane & 7, q = lane >> 3;
   const float bx0 = (float)((warp & 1) * 8) - 7.5f;           // tile-centred x of a row's first pixel
-  const float lya = (float)((warp >> 1) * 8 + q) - 7.5f;      // tile-centred y of the two rows
-  const float lyb = lya + 4.0f;
+  const float lya = (float)((warp >> 1) * 8 + q) - 7.5f;      // tile-centred y of the upper row (the other: + 4)
   const int slot_base = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0);
-  float4 *panel = sm.panel[warp];
+  float4 *panel0 = sm.panel0[warp], *panel1 = sm.panel1[warp];
+  const unsigned char *rec_a = reinterpret_cast<const unsigned char *>(sm.a);
+  const unsigned char *rec_b = reinterpret_cast<const unsigned char *>(sm.b);
+  const unsigned char *rec_f = reinterpret_cast<const unsigned char *>(sm.f);
+  float g_scalar[2][4];               // dL/dimage of the two pixels as scalars (same registers as gpix2)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { g_scalar[0][c] = 0.f; g_scalar[1][c] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < F; ++c) upk(gpix2[c], g_scalar[0][c], g_scalar[1][c]);
 
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
   if (lane == 0) sm.warp_done[warp] = 0;
@@ -141,27 +151,23 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
     }
     // ---- stage (thread j owns splat j of the batch, and flushes it at the end) ----
     int my_id = -1;
-    float s_mx = 0.f, s_my = 0.f, s_ax = 0.f, s_ay = 0.f, s_isx = 0.f, s_isy = 0.f, s_alpha = 1.f;
     if (tid < nb) {
       my_id = overlap_to_point[base + tid];
-      const float *g = points + 7 * (int64_t)my_id;
-      float mx = g[0], my = g[1], ax = g[2], ay = g[3], sx = g[4], sy = g[5], alpha = g[6];
-      float isx = 1.0f / sx, isy = 1.0f / sy;
-      s_mx = mx; s_my = my; s_ax = ax; s_ay = ay; s_isx = isx; s_isy = isy; s_alpha = alpha;
-      float ux = ax * isx * kExpScale, uy = ay * isx * kExpScale;
-      float wx = -ay * isy * kExpScale, wy = ax * isy * kExpScale;
-      const float ddx = mx - ((float)tile_x0 + 8.0f), ddy = my - ((float)tile_y0 + 8.0f);
+      const float4 *rec = digest + 4 * (int64_t)my_id;
+      const float4 R0 = __ldg(rec), R1 = __ldg(rec + 1), R2 = __ldg(rec + 2), R3 = __ldg(rec + 3);
+      const float ux = R0.z, wx = R0.w, uy = R1.x, wy = R1.y, rcs = R3.x;
+      const float ddx = R0.x - ((float)tile_x0 + 8.0f), ddy = R0.y - ((float)tile_y0 + 8.0f);
       const float tx0 = -fmaf(ux, ddx, uy * ddy), ty0 = -fmaf(wx, ddx, wy * ddy);
       sm.a[tid] = make_float4(tx0, ty0, ux, wx);
-      sm.b[tid] = make_float4(uy, wy, alpha, 0.f);
+      sm.b[tid] = R1;
+      sm.f[tid] = R2;
+      sm.c[tid] = make_float4(ddx, ddy, R3.y, R3.z);
       unsigned mask = 0;
-      if (alpha > thr) {
-        float rc = sqrtf(2.0f * __logf(alpha / thr)) * 1.001f + 0.01f;
-        float rcs = rc * kExpScale;
-        float e1x = ax * sx, e1y = ay * sx, e2x = ay * sy, e2y = ax * sy;
-        float ex = rc * sqrtf(e1x * e1x + e2x * e2x), ey = rc * sqrtf(e1y * e1y + e2y * e2y);
-        float hu = (fabsf(ux) + fabsf(uy)) * 3.5f + rcs;
-        float hw = (fabsf(wx) + fabsf(wy)) * 3.5f + rcs;
+      if (rcs > 0.f) {   // same block test as the forward kernel (raster_fwd.cu: stage_splat)
+        const float sc = rcs * rcp_approx(fabsf(ux * wy - uy * wx)) * 1.0001f;
+        const float ex = sc * sqrtf(fmaf(uy, uy, wy * wy)), ey = sc * sqrtf(fmaf(ux, ux, wx * wx));
+        const float hu = (fabsf(ux) + fabsf(uy)) * 3.5f + rcs;
+        const float hw = (fabsf(wx) + fabsf(wy)) * 3.5f + rcs;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
           const float ox = (w & 1) ? 4.0f : -4.0f, oy = (w >> 1) ? 4.0f : -4.0f;   // block centre - tile centre
@@ -171,13 +177,6 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         }
       }
       sm.mask[tid] = (unsigned char)mask;
-      float4 fv = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float *fp = features + (int64_t)F * my_id;
-      fv.x = fp[0];
-      if (F > 1) fv.y = fp[1];
-      if (F > 2) fv.z = fp[2];
-      if (F > 3) fv.w = fp[3];
-      sm.f[tid] = fv;
 #pragma unroll
       for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
     }
@@ -190,24 +189,38 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         int j = c + lane;
         bool hit = j < nb && ((sm.mask[j] >> warp) & 1);
         unsigned bal = __ballot_sync(full, hit);
-        if (hit) sm.list[warp][nhit + __popc(bal & ((1u << lane) - 1))] = (unsigned short)j;
+        if (hit) sm.list[warp][3 + nhit + __popc(bal & ((1u << lane) - 1))] = 16u * (unsigned)j;
         nhit += __popc(bal);
       }
-      if (lane < kChunk) sm.list[warp][nhit + lane] = (unsigned short)kBatch;
-      __syncwarp();
     }
+    // pad with the null record (also when the list is empty: the sweep prefetches entry 0 unconditionally)
+    if (lane <= kChunk) sm.list[warp][3 + nhit + lane] = 16u * (unsigned)kBatch;
+    __syncwarp();
 #ifdef GS_COUNT
     if (lane == 0) { atomicAdd(&g_count[1], (unsigned long long)nhit); if (warp == 0) atomicAdd(&g_count[3], 1ull); }
 #endif
 
+    // records of the first hit: every iteration loads the NEXT splat's records before it computes (the loads
+    // then sit ahead of the panel stores in program order, so their latency hides behind the arithmetic)
+    float4 A, B, fv;
+    {
+      const unsigned off = sm.list[warp][3];
+      A = *reinterpret_cast<const float4 *>(rec_a + off);
+      B = *reinterpret_cast<const float4 *>(rec_b + off);
+      fv = *reinterpret_cast<const float4 *>(rec_f + off);
+    }
     for (int h0 = 0; h0 < nhit; h0 += kChunk) {
       // ---- phase 1: lane = two pixels; 8 splats in depth order ----
+      const uint4 nx0 = *reinterpret_cast<const uint4 *>(&sm.list[warp][h0 + 4]);
+      const uint4 nx1 = *reinterpret_cast<const uint4 *>(&sm.list[warp][h0 + 8]);
+      const unsigned next_off[kChunk] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
       constexpr int kUnroll1 = GS_BWDT_UNROLL;
 #pragma unroll kUnroll1
       for (int u = 0; u < kChunk; ++u) {
-        const int j = sm.list[warp][h0 + u];
-        const float4 A = sm.a[j], B = sm.b[j];
-        const float4 fv = sm.f[j];
+        const unsigned off_next = next_off[u];
+        const float4 An = *reinterpret_cast<const float4 *>(rec_a + off_next);
+        const float4 Bn = *reinterpret_cast<const float4 *>(rec_b + off_next);
+        const float4 fn = *reinterpret_cast<const float4 *>(rec_f + off_next);
         const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
         const f32x2 uw_x = pk(A.z, A.w), uw_y = pk(B.x, B.y);
         const f32x2 tbase = fma2(lx2, uw_x, pk(A.x, A.y));
@@ -241,68 +254,77 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         upk(mul2(alpha_pt2, fma2(rn2, inv2, mul2(fg2, T2))), G0, G1);
         G0 = hg0 ? G0 : 0.f;
         G1 = hg1 ? G1 : 0.f;
-        const f32x2 G2 = pk(G0, G1);
-        const f32x2 Gp2 = mul2(G2, ga2), GG2 = mul2(G2, G2);
-        float Gp0, Gp1, GG0, GG1, h0v = 0.f, h1v = 0.f;
+        float Gp0, Gp1;
+        const f32x2 Gp2 = mul2(pk(G0, G1), ga2);
         upk(Gp2, Gp0, Gp1);
-        upk(GG2, GG0, GG1);
+        // the pixel pair shares its column, so the pair enters the panel pre-summed: S = Gp0 + Gp1 carries the
+        // 1, x, x^2 moments and D = Gp1 (the pixel 4 rows down) completes the y moments
+        float4 e0 = make_float4(Gp0 + Gp1, Gp1, 0.f, 0.f);
         if (HEUR) {
-          // |G dpdf/dmean|_1 = |Gp| (|tx ux + ty wx| + |tx uy + ty wy|) / k^2  (t and u, w carry one factor k each);
-          // stored signed (the bracket is >= 0), phase 2 adds the absolute value
-          const float inv_k2 = 1.0f / (kExpScale * kExpScale);
-          float p0, p1, q0, q1, r0, r1, v0, v1;
+          // |G dpdf/dmean|_1 = |Gp| (|tx ux + ty wx| + |tx uy + ty wy|) / k^2  (t and u, w carry one factor k each;
+          // the 1 / k^2 is applied once per splat in phase 2)
+          float p0, p1, q0, q1, r0, r1, v0, v1, hk0, hk1;
           upk(mul2(t2[0], uw_x), p0, p1);
           upk(mul2(t2[0], uw_y), q0, q1);
           upk(mul2(t2[1], uw_x), r0, r1);
           upk(mul2(t2[1], uw_y), v0, v1);
-          const f32x2 br2 = pk(fabsf(p0 + p1) + fabsf(q0 + q1), fabsf(r0 + r1) + fabsf(v0 + v1));
-          upk(mul2(br2, mul2(Gp2, pk(inv_k2, inv_k2))), h0v, h1v);
+          upk(mul2(pk(fabsf(p0 + p1) + fabsf(q0 + q1), fabsf(r0 + r1) + fabsf(v0 + v1)), Gp2), hk0, hk1);
+          e0.z = fmaf(G0, G0, G1 * G1);
+          e0.w = fabsf(hk0) + fabsf(hk1);
         }
-        panel[u * kRow + lane] = make_float4(Gp0, w0, GG0, h0v);
-        panel[u * kRow + 32 + lane] = make_float4(Gp1, w1, GG1, h1v);
+        panel0[u * kRow + lane] = e0;
+        if (GF) {
+          float4 e1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          e1.x = fmaf(w0, g_scalar[0][0], w1 * g_scalar[1][0]);
+          if (F > 1) e1.y = fmaf(w0, g_scalar[0][1], w1 * g_scalar[1][1]);
+          if (F > 2) e1.z = fmaf(w0, g_scalar[0][2], w1 * g_scalar[1][2]);
+          if (F > 3) e1.w = fmaf(w0, g_scalar[0][3], w1 * g_scalar[1][3]);
+          panel1[u * kRow + lane] = e1;
+        }
 #ifdef GS_COUNT
         {
           unsigned live = __ballot_sync(full, hg0), live1 = __ballot_sync(full, hg1);
           if (lane == 0) { atomicAdd(&g_count[0], 1ull); atomicAdd(&g_count[2], (unsigned long long)(__popc(live) + __popc(live1))); }
         }
 #endif
+        A = An; B = Bn; fv = fn;
       }
       __syncwarp();
 
-      // ---- phase 2: lane = (splat s, rows q and q + 4): walk the 16 pixels of the two rows for one splat ----
-      float m0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
-      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, hh0 = 0.f, hh1 = 0.f;
-      f32x2 f01 = pk(0.f, 0.f), f23 = pk(0.f, 0.f);
-#pragma unroll
-      for (int hrow = 0; hrow < 2; ++hrow) {
-        const float4 *row = panel + s * kRow + hrow * 32 + q * 8;
-        const float4 *grow = sm.gpix[warp] + (q + 4 * hrow) * kRowG;
+      // ---- phase 2: lane = (splat s, row pair q): walk the 8 lane entries of rows q and q + 4 for one splat ----
+      f32x2 md = pk(0.f, 0.f), sd1 = pk(0.f, 0.f), hh = pk(0.f, 0.f), f01 = pk(0.f, 0.f), f23 = pk(0.f, 0.f);
+      float s2 = 0.f;
+      {
+        const float4 *row0 = panel0 + s * kRow + q * 8, *row1 = panel1 + s * kRow + q * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 v = row[i];
-          m0[hrow] += v.x;
-          s1[hrow] = fmaf(v.x, (float)i, s1[hrow]);
-          s2[hrow] = fmaf(v.x, (float)(i * i), s2[hrow]);
+          const float4 e0 = row0[i];
+          const f32x2 sd = pk(e0.x, e0.y);
+          md = add2(md, sd);                                         // (sum S, sum D)
+          sd1 = fma2(sd, pk((float)i, (float)i), sd1);               // (sum i S, sum i D)
+          s2 = fmaf(e0.x, (float)(i * i), s2);
+          if (HEUR) hh = add2(hh, pk(e0.z, e0.w));
           if (GF) {
-            const float4 g = grow[i];
-            if (F == 1) f0 = fmaf(v.y, g.x, f0);
-            if (F >= 2) f01 = fma2(pk(g.x, g.y), pk(v.y, v.y), f01);
-            if (F == 3) f2 = fmaf(v.y, g.z, f2);
-            if (F == 4) f23 = fma2(pk(g.z, g.w), pk(v.y, v.y), f23);
+            const float4 e1 = row1[i];
+            f01 = add2(f01, pk(e1.x, e1.y));
+            if (F > 2) f23 = add2(f23, pk(e1.z, e1.w));
           }
-          if (HEUR) { hh0 += v.z; hh1 += fabsf(v.w); }
         }
       }
-      if (F >= 2) upk(f01, f0, f1);
-      if (F == 4) upk(f23, f2, f3);
-      // row-local -> tile-centred moments (x = bx0 + i, y = lya | lyb)
-      const float Lxa = fmaf(bx0, m0[0], s1[0]), Lxb = fmaf(bx0, m0[1], s1[1]);
-      const float M0 = m0[0] + m0[1], S1 = s1[0] + s1[1], S2 = s2[0] + s2[1];
-      const float Lxx = fmaf(bx0, fmaf(bx0, M0, 2.0f * S1), S2);
-      const float Ly = fmaf(lya, m0[0], lyb * m0[1]);
-      const float Lxy = fmaf(lya, Lxa, lyb * Lxb);
-      const float Lyy = fmaf(lya * lya, m0[0], lyb * lyb * m0[1]);
-      float v[12] = {M0, Lxa + Lxb, Ly, Lxx, Lxy, Lyy, f0, f1, f2, f3, hh0, hh1};
+      float m0, d0, s1, d1, f0, f1, f2, f3, hh0, hh1;
+      upk(md, m0, d0);
+      upk(sd1, s1, d1);
+      upk(f01, f0, f1);
+      upk(f23, f2, f3);
+      upk(hh, hh0, hh1);
+      hh1 *= 1.0f / (kExpScale * kExpScale);
+      // lane-entry sums -> tile-centred moments (x = bx0 + i; y = lya for S - D, lya + 4 for D)
+      const float Lx = fmaf(bx0, m0, s1);
+      const float Lxx = fmaf(bx0, fmaf(bx0, m0, 2.0f * s1), s2);
+      const float Ly = fmaf(lya, m0, 4.0f * d0);
+      const float Lxy = fmaf(lya, Lx, 4.0f * fmaf(bx0, d0, d1));
+      const float Lyy = fmaf(lya * lya, m0, fmaf(8.0f, lya, 16.0f) * d0);
+      float v[12] = {m0, Lx, Ly, Lxx, Lxy, Lyy, f0, f1, f2, f3, hh0, hh1};
       // sum over the 4 row pairs with a 2-stage transposed butterfly: 6 + 3 shuffles, 3 finished sums per lane
       {
         const bool up = (lane & 16) != 0;
@@ -323,7 +345,7 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
         }
       }
       if (h0 + s < nhit) {
-        float *dst = sm.acc + sm.list[warp][h0 + s] * kAcc + slot_base;
+        float *dst = sm.acc + (sm.list[warp][3 + h0 + s] >> 4) * kAcc + slot_base;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
           if (v[i] != 0.f) atomicAdd(dst + i, v[i]);
@@ -343,13 +365,15 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
       if (any) {
         if (GP) {
           // shift the tile-centred moments to the splat mean: d = l + c
-          const float cx = (float)tile_x0 + 8.0f - s_mx, cy = (float)tile_y0 + 8.0f - s_my;
+          const float4 RA = sm.a[tid], RB = sm.b[tid], RC = sm.c[tid];
+          const float inv_k = 1.0f / kExpScale;
+          const float cx = -RC.x, cy = -RC.y, s_isx = RC.z, s_isy = RC.w, s_alpha = RB.z;
           const float M0 = S[0], Lx = S[1], Ly = S[2], Lxx = S[3], Lxy = S[4], Lyy = S[5];
           const float Mx = fmaf(cx, M0, Lx), My = fmaf(cy, M0, Ly);
           const float Mxx = Lxx + cx * (2.0f * Lx + cx * M0);
           const float Myy = Lyy + cy * (2.0f * Ly + cy * M0);
           const float Mxy = Lxy + cx * Ly + cy * Lx + cx * cy * M0;
-          const float ux = s_ax * s_isx, uy = s_ay * s_isx, wx = -s_ay * s_isy, wy = s_ax * s_isy;
+          const float ux = RA.z * inv_k, uy = RB.x * inv_k, wx = RA.w * inv_k, wy = RB.y * inv_k;   // axis / sigma
           const float S1 = ux * Mx + uy * My, S2 = wx * Mx + wy * My;
           const float S3 = ux * Mxx + uy * Mxy, S4 = ux * Mxy + uy * Myy;
           const float S5 = wx * Mxx + wy * Mxy, S6 = wx * Mxy + wy * Myy;
@@ -379,7 +403,7 @@ raster_bwd_t_kernel(const float *__restrict__ points, const float *__restrict__ 
 }  // namespace bwdt
 
 template <int F>
-int launch_bwd_transpose(const float *points, const float *features, const int32_t *ranges, const int32_t *o2p,
+int launch_bwd_transpose(const float4 *digest, const int32_t *ranges, const int32_t *o2p,
                          const float *image, const float *grad_image, const RasterParams<float> &P, int tiles,
                          float *grad_points, float *grad_features, float *heuristic, cudaStream_t stream) {
   const bool gp = grad_points != nullptr, gf = grad_features != nullptr, he = P.heur && heuristic != nullptr;
@@ -392,7 +416,7 @@ int launch_bwd_transpose(const float *points, const float *features, const int32
       GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
       configured = true;                                                                                        \
     }                                                                                                           \
-    kern<<<tiles, bwdt::kThreads, smem, stream>>>(points, features, ranges, o2p, image, grad_image, P,            \
+    kern<<<tiles, bwdt::kThreads, smem, stream>>>(digest, ranges, o2p, image, grad_image, P,                    \
                                                 grad_points, grad_features, heuristic);                         \
   } while (0)
   if (gp && gf && he) GS_BWDT(true, true, true);
@@ -408,14 +432,14 @@ int launch_bwd_transpose(const float *points, const float *features, const int32
   return GS_OK;
 }
 
-template int launch_bwd_transpose<1>(const float *, const float *, const int32_t *, const int32_t *, const float *,
-                                     const float *, const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
-template int launch_bwd_transpose<2>(const float *, const float *, const int32_t *, const int32_t *, const float *,
-                                     const float *, const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
-template int launch_bwd_transpose<3>(const float *, const float *, const int32_t *, const int32_t *, const float *,
-                                     const float *, const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
-template int launch_bwd_transpose<4>(const float *, const float *, const int32_t *, const int32_t *, const float *,
-                                     const float *, const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
+template int launch_bwd_transpose<1>(const float4 *, const int32_t *, const int32_t *, const float *, const float *,
+                                     const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
+template int launch_bwd_transpose<2>(const float4 *, const int32_t *, const int32_t *, const float *, const float *,
+                                     const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
+template int launch_bwd_transpose<3>(const float4 *, const int32_t *, const int32_t *, const float *, const float *,
+                                     const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
+template int launch_bwd_transpose<4>(const float4 *, const int32_t *, const int32_t *, const float *, const float *,
+                                     const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
 
 }  // namespace gs
 

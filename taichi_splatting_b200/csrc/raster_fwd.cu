@@ -38,7 +38,6 @@ constexpr int kThreads = kWarps * 32;
 #define GS_FWD_UNROLL 16
 #endif
 constexpr int kUnroll = GS_FWD_UNROLL;
-constexpr float kExpScale = 0.84932180028801904f;  // sqrt(0.5 * log2(e)):  exp(-0.5 r^2) = 2^-(k r)^2
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -53,30 +52,35 @@ struct FwdSmem {
   int id[kBatch];
   float vis[kBatch + 1];
   unsigned char mask[kBatch];
-  unsigned short list[kWarps][kBatch + kUnroll];
+  alignas(16) unsigned list[kWarps][kBatch + kUnroll];   // byte offsets (16 j) of the records a warp must visit
   int warp_done[kWarps];
 };
 
-// Stage one splat: digested records and the 4-bit mask of 8x8 pixel blocks it can touch.
-// (tx, ty) = X (ux, wx) + Y (uy, wy) + (tx0, ty0) with (X, Y) the pixel centre relative to the tile centre.
-__device__ __forceinline__ unsigned stage_splat(const float *__restrict__ g, float thr, float tile_x0,
-                                                float tile_y0, float4 &A, float4 &B) {
-  float mx = g[0], my = g[1], ax = g[2], ay = g[3], sx = g[4], sy = g[5], alpha = g[6];
-  float isx = 1.0f / sx, isy = 1.0f / sy;
-  float ux = ax * isx * kExpScale, uy = ay * isx * kExpScale;
-  float wx = -ay * isy * kExpScale, wy = ax * isy * kExpScale;
-  const float ddx = mx - (tile_x0 + 8.0f), ddy = my - (tile_y0 + 8.0f);
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Stage one splat from its digest (raster_digest.cu): tile-centred records and the 4-bit mask of 8x8 pixel blocks
+// it can touch.  (tx, ty) = X (ux, wx) + Y (uy, wy) + (tx0, ty0) with (X, Y) the pixel centre relative to the
+// tile centre.  The block test is the separating-axis test of the block against the oriented box of the support
+// ellipse (conservative: tile axes via the ellipse's bounding box, then the two ellipse axes).
+__device__ __forceinline__ unsigned stage_splat(const float4 *__restrict__ rec, float tile_cx, float tile_cy,
+                                                float4 &A, float4 &B, float4 &fv) {
+  const float4 R0 = __ldg(rec), R1 = __ldg(rec + 1), R2 = __ldg(rec + 2), R3 = __ldg(rec + 3);
+  const float ux = R0.z, wx = R0.w, uy = R1.x, wy = R1.y, rcs = R3.x;
+  const float ddx = R0.x - tile_cx, ddy = R0.y - tile_cy;
   const float tx0 = -fmaf(ux, ddx, uy * ddy), ty0 = -fmaf(wx, ddx, wy * ddy);
   A = make_float4(tx0, ty0, ux, wx);
-  B = make_float4(uy, wy, alpha, 0.f);
-  if (!(alpha > thr)) return 0u;
-  // conservative support radius in sigma units (margin covers fp32 / ex2.approx evaluation error)
-  float rc = sqrtf(2.0f * __logf(alpha / thr)) * 1.001f + 0.01f;
-  float rcs = rc * kExpScale;
-  float e1x = ax * sx, e1y = ay * sx, e2x = ay * sy, e2y = ax * sy;
-  float ex = rc * sqrtf(e1x * e1x + e2x * e2x), ey = rc * sqrtf(e1y * e1y + e2y * e2y);
-  float hu = (fabsf(ux) + fabsf(uy)) * 3.5f + rcs;     // pixel centres of a block span +-3.5 around its centre
-  float hw = (fabsf(wx) + fabsf(wy)) * 3.5f + rcs;
+  B = R1;
+  fv = R2;
+  if (!(rcs > 0.f)) return 0u;
+  // half extents of the support ellipse { |U d| <= rcs }, U = [u; w]:  rcs sqrt(uy^2 + wy^2) / |det U| in x
+  const float s = rcs * rcp_approx(fabsf(ux * wy - uy * wx)) * 1.0001f;
+  const float ex = s * sqrtf(fmaf(uy, uy, wy * wy)), ey = s * sqrtf(fmaf(ux, ux, wx * wx));
+  const float hu = (fabsf(ux) + fabsf(uy)) * 3.5f + rcs;     // pixel centres of a block span +-3.5 around its centre
+  const float hw = (fabsf(wx) + fabsf(wy)) * 3.5f + rcs;
   unsigned mask = 0;
 #pragma unroll
   for (int w = 0; w < kWarps; ++w) {
@@ -112,8 +116,7 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
 // data pipe, ~2.7 cycles per broadcast LDS.128), and the two pixels share packed FFMA2 / FMUL2 / FADD2 issue slots.
 template <int F, bool VIS, bool BLEND, bool MEDIAN>
 __global__ void __launch_bounds__(kThreads, GS_FWD_MIN_BLOCKS)
-raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ features,
-                  const float *__restrict__ depths, const int32_t *__restrict__ ranges,
+raster_fwd_kernel(const float4 *__restrict__ digest, const int32_t *__restrict__ ranges,
                   const int32_t *__restrict__ overlap_to_point, RasterParams<float> P, float median_lim,
                   float *__restrict__ image, float *__restrict__ image_alpha, float *__restrict__ visibility,
                   float *__restrict__ median_image) {
@@ -139,6 +142,9 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
   bool done[2] = {!in_bounds[0], !in_bounds[1]};   // non-blend mode only: pixel frozen after its trigger
   float median[2] = {0.f, 0.f};
 
+  const unsigned char *rec_a = reinterpret_cast<const unsigned char *>(sm.a);
+  const unsigned char *rec_b = reinterpret_cast<const unsigned char *>(sm.b);
+  const unsigned char *rec_f = reinterpret_cast<const unsigned char *>(sm.f);
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
   if (lane == 0) sm.warp_done[warp] = 0;
   if (tid == 0) {  // null record: alpha = 0 never passes the threshold
@@ -158,16 +164,9 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
     }
     for (int j = tid; j < nb; j += kThreads) {
       int id = overlap_to_point[base + j];
-      float4 A, B;
-      unsigned m = stage_splat(points + 7 * (int64_t)id, thr, (float)tile_x0, (float)tile_y0, A, B);
-      if (MEDIAN) B.w = depths[id];
+      float4 A, B, fv;
+      unsigned m = stage_splat(digest + 4 * (int64_t)id, (float)tile_x0 + 8.0f, (float)tile_y0 + 8.0f, A, B, fv);
       sm.a[j] = A; sm.b[j] = B;
-      float4 fv = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float *fp = features + (int64_t)F * id;
-      fv.x = fp[0];
-      if (F > 1) fv.y = fp[1];
-      if (F > 2) fv.z = fp[2];
-      if (F > 3) fv.w = fp[3];
       sm.f[j] = fv;
       sm.mask[j] = (unsigned char)m;
       if (VIS) { sm.id[j] = id; sm.vis[j] = 0.f; }
@@ -184,24 +183,31 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
         int j = c + lane;
         bool hit = j < nb && ((sm.mask[j] >> warp) & 1);
         unsigned bal = __ballot_sync(full, hit);
-        if (hit) sm.list[warp][nhit + __popc(bal & ((1u << lane) - 1))] = (unsigned short)j;
+        if (hit) sm.list[warp][nhit + __popc(bal & ((1u << lane) - 1))] = 16u * (unsigned)j;
         nhit += __popc(bal);
       }
-      if (lane < kUnroll) sm.list[warp][nhit + lane] = (unsigned short)kBatch;  // pad with the null record
+      if (lane < kUnroll) sm.list[warp][nhit + lane] = 16u * (unsigned)kBatch;  // pad with the null record
       __syncwarp();
     }
 
     for (int h0 = 0; h0 < nhit; h0 += kUnroll) {
       float wv[kUnroll];
+      unsigned offs[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; u += 4) {
+        const uint4 o = *reinterpret_cast<const uint4 *>(&sm.list[warp][h0 + u]);
+        offs[u] = o.x; offs[u + 1] = o.y; offs[u + 2] = o.z; offs[u + 3] = o.w;
+      }
       // one unrolled chunk of the sweep; the median bookkeeping is compiled out once every pixel of the warp has
       // crossed the median limit (it happens within the first few splats of a pixel)
       auto sweep = [&](auto median_tag) {
       constexpr bool kMedian = decltype(median_tag)::value;
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const int j = sm.list[warp][h0 + u];
-        const float4 A = sm.a[j], B = sm.b[j];
-        const float4 fv = sm.f[j];
+        const unsigned off = offs[u];
+        const float4 A = *reinterpret_cast<const float4 *>(rec_a + off);
+        const float4 B = *reinterpret_cast<const float4 *>(rec_b + off);
+        const float4 fv = *reinterpret_cast<const float4 *>(rec_f + off);
         const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
         const f32x2 tbase = fma2(lx2, pk(A.z, A.w), pk(A.x, A.y)), uw_y = pk(B.x, B.y);
         float t0x, t0y, t1x, t1y;
@@ -250,7 +256,7 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
       if (VIS) {
         warp_transpose_reduce16(wv, lane);
         const int h = h0 + (lane >> 1);
-        if ((lane & 1) == 0 && h < nhit && wv[0] != 0.f) atomicAdd(&sm.vis[sm.list[warp][h]], wv[0]);
+        if ((lane & 1) == 0 && h < nhit && wv[0] != 0.f) atomicAdd(&sm.vis[sm.list[warp][h] >> 4], wv[0]);
       }
       const bool now_done = BLEND ? (trans[0] <= eps && trans[1] <= eps) : (done[0] && done[1]);
       if (__all_sync(full, now_done)) break;
@@ -283,15 +289,14 @@ raster_fwd_kernel(const float *__restrict__ points, const float *__restrict__ fe
 }
 
 template <int F>
-static int launch_fwd(const float *points, const float *features, const float *depths, const int32_t *ranges,
-                      const int32_t *o2p, const RasterParams<float> &P, float median_lim, int tiles, float *image,
-                      float *image_alpha, float *visibility, float *median_image, cudaStream_t stream) {
+static int launch_fwd(const float4 *digest, const int32_t *ranges, const int32_t *o2p, const RasterParams<float> &P,
+                      float median_lim, int tiles, float *image, float *image_alpha, float *visibility,
+                      float *median_image, cudaStream_t stream) {
   const bool vis = P.vis && visibility != nullptr;
   const bool med = median_image != nullptr;
-#define GS_FWD(VIS, BLEND, MED)                                                                              \
-  raster_fwd_kernel<F, VIS, BLEND, MED><<<tiles, kThreads, 0, stream>>>(points, features, depths, ranges, o2p, \
-                                                                      P, median_lim, image, image_alpha,    \
-                                                                      visibility, median_image)
+#define GS_FWD(VIS, BLEND, MED)                                                                                  \
+  raster_fwd_kernel<F, VIS, BLEND, MED><<<tiles, kThreads, 0, stream>>>(digest, ranges, o2p, P, median_lim, image, \
+                                                                        image_alpha, visibility, median_image)
   if (P.blend) {
     if (med) { if (vis) GS_FWD(true, true, true); else GS_FWD(false, true, true); }
     else     { if (vis) GS_FWD(true, true, false); else GS_FWD(false, true, false); }
@@ -303,6 +308,41 @@ static int launch_fwd(const float *points, const float *features, const float *d
   return GS_OK;
 }
 
+int raster_digest_f32(const float *points, const float *features, const float *depths, int64_t v, int F,
+                      double alpha_threshold, void *digest, cudaStream_t stream);   // raster_digest.cu
+
+static bool fwd_tuned(const gs_raster_config *cfg, int F) {
+  return cfg->tile_size == kTile && !cfg->antialias && F >= 1 && F <= 4;
+}
+
+// Tuned kernel on a ready digest.
+static int raster_fwd_digest_impl(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point,
+                                  int64_t v, int32_t width, int32_t height, int32_t F, const gs_raster_config *cfg,
+                                  double median_threshold, float *image, float *image_alpha, float *visibility,
+                                  float *median_image, cudaStream_t stream) {
+  GS_CHECK_ARG(cfg != nullptr, "raster_fwd: config is NULL");
+  GS_CHECK_ARG(width > 0 && height > 0, "raster_fwd: bad image size %dx%d", width, height);
+  GS_CHECK_ARG(!cfg->compute_visibility || visibility != nullptr || v == 0, "raster_fwd: compute_visibility needs a visibility buffer");
+  GS_CHECK_ARG(digest != nullptr || v == 0, "raster_fwd: digest is NULL");
+  if (!fwd_tuned(cfg, F) || (median_image != nullptr && !cfg->use_alpha_blending)) {
+    set_error("raster_fwd (digest): needs tile_size 16, no antialias, 1..4 features%s",
+              median_image != nullptr ? ", alpha blending for the fused median" : "");
+    return GS_ERR_UNSUPPORTED;
+  }
+  RasterParams<float> P = make_params<float>(cfg, width, height, F);
+  const int tiles = P.tiles_wide * ((height + kTile - 1) / kTile);
+  const float median_lim = (float)(1.0 - median_threshold);
+  const float4 *d = reinterpret_cast<const float4 *>(digest);
+  switch (F) {
+    case 1: return launch_fwd<1>(d, tile_ranges, overlap_to_point, P, median_lim, tiles, image, image_alpha, visibility, median_image, stream);
+    case 2: return launch_fwd<2>(d, tile_ranges, overlap_to_point, P, median_lim, tiles, image, image_alpha, visibility, median_image, stream);
+    case 3: return launch_fwd<3>(d, tile_ranges, overlap_to_point, P, median_lim, tiles, image, image_alpha, visibility, median_image, stream);
+    default: return launch_fwd<4>(d, tile_ranges, overlap_to_point, P, median_lim, tiles, image, image_alpha, visibility, median_image, stream);
+  }
+}
+
+// Reference-shaped entry (raw (V,7) points + features): digest into library scratch, then the tuned kernel;
+// other configurations go to the generic kernel.
 static int raster_fwd_f32_impl(const float *points, const float *features, const float *depths,
                                const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t v, int32_t width,
                                int32_t height, int32_t F, const gs_raster_config *cfg, double median_threshold,
@@ -311,23 +351,21 @@ static int raster_fwd_f32_impl(const float *points, const float *features, const
   GS_CHECK_ARG(cfg != nullptr, "raster_fwd: config is NULL");
   GS_CHECK_ARG(width > 0 && height > 0, "raster_fwd: bad image size %dx%d", width, height);
   GS_CHECK_ARG(!cfg->compute_visibility || visibility != nullptr || v == 0, "raster_fwd: compute_visibility needs a visibility buffer");
-  const bool fast = cfg->tile_size == kTile && !cfg->antialias && F >= 1 && F <= 4;
-  if (median_image != nullptr) {
-    if (!fast || !cfg->use_alpha_blending) {
-      set_error("raster_fwd_median: needs tile_size 16, no antialias, 1..4 features, alpha blending and depths");
-      return GS_ERR_UNSUPPORTED;
-    }
+  const bool fast = fwd_tuned(cfg, F);
+  if (median_image != nullptr && (!fast || !cfg->use_alpha_blending)) {
+    set_error("raster_fwd_median: needs tile_size 16, no antialias, 1..4 features, alpha blending and depths");
+    return GS_ERR_UNSUPPORTED;
   }
   if (fast) {
-    RasterParams<float> P = make_params<float>(cfg, width, height, F);
-    int tiles = P.tiles_wide * ((height + kTile - 1) / kTile);
-    float median_lim = (float)(1.0 - median_threshold);
-    switch (F) {
-      case 1: return launch_fwd<1>(points, features, depths, tile_ranges, overlap_to_point, P, median_lim, tiles, image, image_alpha, visibility, median_image, stream);
-      case 2: return launch_fwd<2>(points, features, depths, tile_ranges, overlap_to_point, P, median_lim, tiles, image, image_alpha, visibility, median_image, stream);
-      case 3: return launch_fwd<3>(points, features, depths, tile_ranges, overlap_to_point, P, median_lim, tiles, image, image_alpha, visibility, median_image, stream);
-      default: return launch_fwd<4>(points, features, depths, tile_ranges, overlap_to_point, P, median_lim, tiles, image, image_alpha, visibility, median_image, stream);
+    void *digest = nullptr;
+    if (v > 0) {
+      digest = stream_workspace(stream, (size_t)v * 64);
+      if (digest == nullptr) return GS_ERR_CUDA;
+      int rc = raster_digest_f32(points, features, depths, v, F, cfg->alpha_threshold, digest, stream);
+      if (rc != GS_OK) return rc;
     }
+    return raster_fwd_digest_impl(digest, tile_ranges, overlap_to_point, v, width, height, F, cfg, median_threshold,
+                                  image, image_alpha, visibility, median_image, stream);
   }
   return raster_fwd_generic<float>(points, features, tile_ranges, overlap_to_point, width, height, F, cfg, image,
                                    image_alpha, visibility, stream);
@@ -353,6 +391,16 @@ extern "C" int gs_raster_fwd_median_f32(const float *points, const float *featur
   GS_CHECK_ARG(median_image != nullptr && (depths != nullptr || v == 0), "raster_fwd_median: depths / median_image is NULL");
   return gs::raster_fwd_f32_impl(points, features, depths, tile_ranges, overlap_to_point, v, width, height, F, cfg,
                                  median_threshold, image, image_alpha, visibility, median_image, (cudaStream_t)stream_);
+}
+
+extern "C" int gs_raster_fwd_digest_f32(const void *digest, const int32_t *tile_ranges,
+                                        const int32_t *overlap_to_point, int64_t v, int64_t k, int32_t width,
+                                        int32_t height, int32_t F, const gs_raster_config *cfg,
+                                        double median_threshold, float *image, float *image_alpha, float *visibility,
+                                        float *median_image, void *stream_) {
+  (void)k;
+  return gs::raster_fwd_digest_impl(digest, tile_ranges, overlap_to_point, v, width, height, F, cfg, median_threshold,
+                                    image, image_alpha, visibility, median_image, (cudaStream_t)stream_);
 }
 
 extern "C" int gs_raster_fwd_f64(const double *points, const double *features, const int32_t *tile_ranges,

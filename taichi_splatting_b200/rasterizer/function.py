@@ -20,10 +20,26 @@ RasterOut = NamedTuple('RasterOut', [
 ])
 
 
+def tuned_supported(config: RasterConfig, num_features: int, dtype) -> bool:
+  """Configurations of the tuned kernels (raster_fwd.cu / raster_bwd_t.cu), which read the raster digest."""
+  return dtype == torch.float32 and config.tile_size == 16 and not config.antialias and 1 <= num_features <= 4
+
+
 def fused_median_supported(config: RasterConfig, num_features: int, dtype) -> bool:
-  """gs_raster_fwd_median_f32 covers the tuned kernel's configurations only."""
-  return (dtype == torch.float32 and config.tile_size == 16 and not config.antialias and 1 <= num_features <= 4
-          and config.use_alpha_blending)
+  """The fused median-depth output exists in the tuned, alpha-blending kernel only."""
+  return tuned_supported(config, num_features, dtype) and config.use_alpha_blending
+
+
+def make_digest(gaussians2d: torch.Tensor, features: torch.Tensor, depths: Optional[torch.Tensor],
+                config: RasterConfig) -> torch.Tensor:
+  """(V,16) fp32 raster records (gs_raster_digest_f32): written once, gathered by forward and backward."""
+  v = gaussians2d.shape[0]
+  digest = torch.empty((v, 16), dtype=torch.float32, device=gaussians2d.device)
+  if v > 0:
+    _lib.call("gs_raster_digest_f32", _lib.ptr(gaussians2d), _lib.ptr(features),
+              _lib.ptr(depths) if depths is not None else None, v, features.shape[1], _lib.raster_config_c(config),
+              _lib.ptr(digest), _lib.stream_ptr(gaussians2d.device))
+  return digest
 
 
 def rasterize_with_tiles_and_median(gaussians2d, features, depths, overlap_to_point, tile_overlap_ranges, image_size,
@@ -72,20 +88,23 @@ class _RasterFunction(torch.autograd.Function):
     cfg = _lib.raster_config_c(config)
     vis_ptr = _lib.ptr(visibility) if config.compute_visibility else None
     median = None
+    digest = torch.empty((0, 16), dtype=torch.float32, device=device)
     if median_depths is not None:
       assert fused_median_supported(config, F, dtype), "fused median depth: unsupported configuration"
       median = torch.empty((h, w), dtype=dtype, device=device)
-      d = median_depths.detach().contiguous().view(-1)
-      _lib.call("gs_raster_fwd_median_f32", _lib.ptr(g), _lib.ptr(f), _lib.ptr(d), _lib.ptr(ranges), _lib.ptr(o2p), v,
-                o2p.shape[0], w, h, F, cfg, float(config.median_threshold), _lib.ptr(image), _lib.ptr(alpha), vis_ptr,
-                _lib.ptr(median), _lib.stream_ptr(device))
+    if tuned_supported(config, F, dtype):
+      d = median_depths.detach().contiguous().view(-1) if median_depths is not None else None
+      digest = make_digest(g, f, d, config)
+      _lib.call("gs_raster_fwd_digest_f32", _lib.ptr(digest), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0], w, h,
+                F, cfg, float(config.median_threshold), _lib.ptr(image), _lib.ptr(alpha), vis_ptr,
+                _lib.ptr(median) if median is not None else None, _lib.stream_ptr(device))
     else:
       _lib.call(f"gs_raster_fwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0],
                 w, h, F, cfg, _lib.ptr(image), _lib.ptr(alpha), vis_ptr, _lib.stream_ptr(device))
 
     ctx.config, ctx.image_size = config, (w, h)
     ctx.heuristic = heuristic
-    ctx.save_for_backward(g, f, image, o2p, ranges)
+    ctx.save_for_backward(g, f, image, o2p, ranges, digest)
     ctx.mark_non_differentiable(alpha, heuristic, visibility)
     if median is not None:
       ctx.mark_non_differentiable(median)
@@ -94,7 +113,7 @@ class _RasterFunction(torch.autograd.Function):
 
   @staticmethod
   def backward(ctx, grad_image, grad_alpha, grad_heuristic, grad_visibility, *grad_median):
-    g, f, image, o2p, ranges = ctx.saved_tensors
+    g, f, image, o2p, ranges, digest = ctx.saved_tensors
     config, (w, h) = ctx.config, ctx.image_size
     sfx = _lib.suffix(g.dtype)
     need_g, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
@@ -102,10 +121,15 @@ class _RasterFunction(torch.autograd.Function):
     grad_f = torch.zeros_like(f) if need_f else None
     if need_g or need_f or config.compute_point_heuristic:
       cfg = _lib.raster_config_c(config)
-      _lib.call(f"gs_raster_bwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), _lib.ptr(image),
-                _lib.ptr(grad_image.contiguous()), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
-                _lib.ptr(grad_g), _lib.ptr(grad_f),
-                _lib.ptr(ctx.heuristic) if config.compute_point_heuristic else None, _lib.stream_ptr(g.device))
+      heur_ptr = _lib.ptr(ctx.heuristic) if config.compute_point_heuristic else None
+      if tuned_supported(config, f.shape[1], g.dtype):
+        _lib.call("gs_raster_bwd_digest_f32", _lib.ptr(digest), _lib.ptr(ranges), _lib.ptr(o2p), _lib.ptr(image),
+                  _lib.ptr(grad_image.contiguous()), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
+                  _lib.ptr(grad_g), _lib.ptr(grad_f), heur_ptr, _lib.stream_ptr(g.device))
+      else:
+        _lib.call(f"gs_raster_bwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), _lib.ptr(image),
+                  _lib.ptr(grad_image.contiguous()), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
+                  _lib.ptr(grad_g), _lib.ptr(grad_f), heur_ptr, _lib.stream_ptr(g.device))
     return grad_g, grad_f, None, None, None, None, None
 
 

@@ -10,7 +10,8 @@ from .data_types import Gaussians3D, RasterConfig
 from .mapper.tile_mapper import bin_and_sort, map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import apply_with_ndc, camera_position
-from .rasterizer.function import fused_median_supported, rasterize_with_tiles, rasterize_with_tiles_and_median
+from .rasterizer.function import (fused_median_supported, make_digest, rasterize_with_tiles,
+                                  rasterize_with_tiles_and_median, tuned_supported)
 from .rendering import RenderedPoints, Rendering, ndc_depth
 from .spherical_harmonics import check_sh_degree, evaluate_sh_at
 
@@ -87,10 +88,16 @@ class _RenderFunction(torch.autograd.Function):
     vis_ptr = ptr(visibility) if config.compute_visibility else None
     cfg = _lib.raster_config_c(config)
     median = torch.empty((0,), dtype=dtype, device=device)
-    if render_median_depth and fused_median_supported(config, F, dtype):
-      median = torch.empty((h, w), dtype=dtype, device=device)
-      call("gs_raster_fwd_median_f32", ptr(g2d), ptr(features), ptr(depths), ptr(ranges), ptr(overlap_to_point), v, k,
-           w, h, F, cfg, float(config.median_threshold), ptr(image), ptr(alpha), vis_ptr, ptr(median), stream)
+    digest = torch.empty((0, 16), dtype=torch.float32, device=device)
+    fused_median = render_median_depth and fused_median_supported(config, F, dtype)
+    if tuned_supported(config, F, dtype) and (fused_median or not render_median_depth):
+      # raster records, written once and gathered by the forward and the backward kernel
+      digest = make_digest(g2d, features, depths.view(-1) if fused_median else None, config)
+      if fused_median:
+        median = torch.empty((h, w), dtype=dtype, device=device)
+      call("gs_raster_fwd_digest_f32", ptr(digest), ptr(ranges), ptr(overlap_to_point), v, k, w, h, F, cfg,
+           float(config.median_threshold), ptr(image), ptr(alpha), vis_ptr, ptr(median) if fused_median else None,
+           stream)
     else:
       call(f"gs_raster_fwd_{sfx}", ptr(g2d), ptr(features), ptr(ranges), ptr(overlap_to_point), v, k, w, h, F, cfg,
            ptr(image), ptr(alpha), vis_ptr, stream)
@@ -103,7 +110,7 @@ class _RenderFunction(torch.autograd.Function):
         median = median3.squeeze(-1)
 
     ctx.save_for_backward(*tensors, feature_c, indexes, g2d, features, image, overlap_to_point, ranges,
-                          cam_pos if cam_pos is not None else torch.empty(0, device=device))
+                          cam_pos if cam_pos is not None else torch.empty(0, device=device), digest)
     ctx.meta = (config, (w, h), blur, margin, bool(use_sh), heuristic)
     ctx.sh_exchange = sh_exchange
     ctx.set_materialize_grads(False)
@@ -113,7 +120,7 @@ class _RenderFunction(torch.autograd.Function):
   @staticmethod
   def backward(ctx, d_image, d_alpha, d_g2d, d_depths, d_indexes, d_features, *unused):
     (position, log_scaling, rotation, alpha_logit, T_camera_world, projection, feature, indexes, g2d, features, image,
-     overlap_to_point, ranges, cam_pos) = ctx.saved_tensors
+     overlap_to_point, ranges, cam_pos, digest) = ctx.saved_tensors
     config, (w, h), blur, margin, use_sh, heuristic = ctx.meta
     dtype, device = position.dtype, position.device
     sfx = _lib.suffix(dtype)
@@ -127,10 +134,16 @@ class _RenderFunction(torch.autograd.Function):
     grad_g = d_g2d.clone() if d_g2d is not None else torch.zeros_like(g2d)
     grad_f = d_features.clone() if d_features is not None else torch.zeros_like(features)
     if d_image is not None and v > 0:
-      call(f"gs_raster_bwd_{sfx}", ptr(g2d), ptr(features), ptr(ranges), ptr(overlap_to_point), ptr(image),
-           ptr(d_image.contiguous()), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
-           ptr(grad_g) if need_geom else None, ptr(grad_f) if need[4] else None,
-           ptr(heuristic) if config.compute_point_heuristic else None, stream)
+      out_ptrs = (ptr(grad_g) if need_geom else None, ptr(grad_f) if need[4] else None,
+                  ptr(heuristic) if config.compute_point_heuristic else None)
+      if digest.shape[0] == v:
+        call("gs_raster_bwd_digest_f32", ptr(digest), ptr(ranges), ptr(overlap_to_point), ptr(image),
+             ptr(d_image.contiguous()), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
+             *out_ptrs, stream)
+      else:
+        call(f"gs_raster_bwd_{sfx}", ptr(g2d), ptr(features), ptr(ranges), ptr(overlap_to_point), ptr(image),
+             ptr(d_image.contiguous()), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
+             *out_ptrs, stream)
 
     # ---- features (part 1): view-parallel runs launch the exchange of the SH-gradient factors now, so that the
     # all-gather overlaps the projection backward ----
