@@ -245,6 +245,87 @@ int gs_raster_bwd_digest_f32(const void *digest, const int32_t *tile_ranges, con
                              int32_t height, int32_t num_features, const gs_raster_config *config,
                              float *grad_points, float *grad_features, float *point_heuristic, void *stream);
 
+/* ---- Whole-frame host drivers (renderer.py:22-108 in one call per phase) --------------------------------------
+ * The per-stage entry points above mirror the reference's operators one to one, and a Python caller that chains
+ * them spends 20-30 us of interpreter time per launch: at the bench workload the front end (13 short kernels,
+ * two host reads) is then bound by the HOST, the GPU idling between launches.  These three drivers enqueue the
+ * same kernels, in the same order, with the same arguments, from C -- nothing else changes, and the results are
+ * bit-identical.  fp32, tuned raster configuration (tile_size 16, no antialias, 1..4 features, alpha blending).
+ *
+ * Buffers are still caller-owned.  Because V (visible Gaussians) is only known inside stage A, every per-visible
+ * buffer is passed with CAPACITY n rows and the caller narrows it to V rows afterwards; the K-sized buffers are
+ * allocated by the caller between stage A (which returns K) and stage B.
+ *
+ *   stage A : project+cull -> [host read V] -> compacted write (+ndc) -> depth order -> tile counts -> scan ->
+ *             [host read K];  on the library's auxiliary stream, beside the mapper chain: SH evaluation (or the
+ *             feature gather), zero fills of visibility / heuristic, the raster digest.
+ *   stage B : ordered key emit -> stable tile sort -> tile ranges -> join the auxiliary stream -> raster forward.
+ *   backward: zero fills (auxiliary stream, beside the raster backward) -> raster backward -> projection backward
+ *             on the caller's stream beside the SH backward (or feature scatter) on the auxiliary stream -> join.
+ * The auxiliary stream is owned by the library (one per device) and fenced against `stream` with events.
+ * ev_* : optional cudaEvent_t handles recorded around the raster launch on `stream` (NULL: not recorded).      */
+typedef struct gs_render_args {
+  const float *position, *log_scaling, *rotation, *alpha_logit;   /* (n,3) (n,3) (n,4) (n,1) */
+  const float *feature;            /* use_sh: SH coefficients (n,channels,(degree+1)^2); else features (n,channels) */
+  const float *T_camera_world, *projection;
+  int64_t n;
+  int32_t width, height;
+  double near_plane, far_plane, blur_cov, clamp_margin, median_threshold;
+  int32_t use_sh, sh_degree, channels, use_depth16, want_median, reserved;
+  gs_raster_config config;
+  /* outputs with capacity n rows (V rows are written) */
+  float *points;                   /* (n,7) */
+  float *depths, *ndc;             /* (n,1) */
+  int64_t *indexes;                /* (n) */
+  float *features;                 /* (n,channels) */
+  void *digest;                    /* 64 n bytes, 64-byte aligned */
+  float *visibility;               /* (n) or NULL */
+  float *heuristic;                /* (n,2) or NULL */
+  float *camera_pos;               /* (3) */
+  int32_t *order, *counts, *cum;   /* (n) (n) (n+1) */
+  /* workspaces (gs_project_workspace_bytes / gs_depth_order_workspace_bytes / gs_tile_scan_workspace_bytes of n) */
+  void *ws_project; size_t ws_project_bytes;
+  void *ws_order; size_t ws_order_bytes;
+  void *ws_scan; size_t ws_scan_bytes;
+  /* image-sized outputs */
+  float *image, *image_alpha, *median_image /* NULL unless want_median */;
+  int32_t *tile_ranges;            /* (tiles,2) */
+  void *ev_raster_start, *ev_raster_end;
+} gs_render_args;
+
+int gs_render_stage_a_f32(const gs_render_args *args, int64_t *v_out, int64_t *k_out, void *stream);
+int gs_render_stage_b_f32(const gs_render_args *args, int64_t v, int64_t k, uint32_t *tiles /* (2,k) */,
+                          int32_t *overlap_to_point /* (2,k): sorted result in row 1 */, void *ws_sort,
+                          size_t ws_sort_bytes, void *stream);
+
+typedef struct gs_render_bwd_args {
+  const float *position, *log_scaling, *rotation, *alpha_logit, *feature, *T_camera_world, *projection;
+  int64_t n, v, k;
+  int32_t width, height;
+  double blur_cov, clamp_margin;
+  int32_t use_sh, sh_degree, channels, reserved;
+  gs_raster_config config;
+  /* saved by the forward */
+  const int64_t *indexes;
+  const float *features, *image, *camera_pos;
+  const void *digest;
+  const int32_t *overlap_to_point, *tile_ranges;
+  /* incoming gradients */
+  const float *d_image;            /* (H,W,channels) contiguous */
+  const float *d_depths;           /* (v,1) or NULL (zero) */
+  /* scratch / accumulated: grad_points (v,7) and grad_features (v,channels) are zero-filled here unless
+   * grad_*_preset != 0 (the caller already stored incoming gradients in them) */
+  float *grad_points, *grad_features;
+  int32_t grad_points_preset, grad_features_preset;
+  float *heuristic;                /* (v,2) accumulated in place, or NULL */
+  /* outputs (zero-filled here; any may be NULL) */
+  float *d_position, *d_log_scaling, *d_rotation, *d_alpha_logit, *d_T_camera_world, *d_projection;
+  float *d_feature;                /* same shape as feature */
+  void *ev_raster_start, *ev_raster_end;
+} gs_render_bwd_args;
+
+int gs_render_backward_f32(const gs_render_bwd_args *args, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ LIB_PATH = _PKG / f"libgsplat_b200{os.environ.get('GS_BUILD_VARIANT', '')}.so"
 P, I32, I64, D, SZ = c_void_p, c_int32, c_int64, c_double, c_size_t
 
 
+
 class RasterConfigC(ctypes.Structure):
   """struct gs_raster_config"""
   _fields_ = [
@@ -26,6 +27,45 @@ class RasterConfigC(ctypes.Structure):
       ("compute_point_heuristic", c_int32), ("reserved", c_int32),
       ("clamp_max_alpha", c_double), ("alpha_threshold", c_double), ("saturate_threshold", c_double),
       ("forward_saturate_eps", c_double),
+  ]
+
+
+class RenderArgsC(ctypes.Structure):
+  """struct gs_render_args"""
+  _fields_ = [
+      ("position", P), ("log_scaling", P), ("rotation", P), ("alpha_logit", P), ("feature", P),
+      ("T_camera_world", P), ("projection", P),
+      ("n", I64), ("width", I32), ("height", I32),
+      ("near_plane", D), ("far_plane", D), ("blur_cov", D), ("clamp_margin", D), ("median_threshold", D),
+      ("use_sh", I32), ("sh_degree", I32), ("channels", I32), ("use_depth16", I32), ("want_median", I32),
+      ("reserved", I32),
+      ("config", RasterConfigC),
+      ("points", P), ("depths", P), ("ndc", P), ("indexes", P), ("features", P), ("digest", P),
+      ("visibility", P), ("heuristic", P), ("camera_pos", P), ("order", P), ("counts", P), ("cum", P),
+      ("ws_project", P), ("ws_project_bytes", SZ), ("ws_order", P), ("ws_order_bytes", SZ),
+      ("ws_scan", P), ("ws_scan_bytes", SZ),
+      ("image", P), ("image_alpha", P), ("median_image", P), ("tile_ranges", P),
+      ("ev_raster_start", P), ("ev_raster_end", P),
+  ]
+
+
+class RenderBwdArgsC(ctypes.Structure):
+  """struct gs_render_bwd_args"""
+  _fields_ = [
+      ("position", P), ("log_scaling", P), ("rotation", P), ("alpha_logit", P), ("feature", P),
+      ("T_camera_world", P), ("projection", P),
+      ("n", I64), ("v", I64), ("k", I64), ("width", I32), ("height", I32),
+      ("blur_cov", D), ("clamp_margin", D),
+      ("use_sh", I32), ("sh_degree", I32), ("channels", I32), ("reserved", I32),
+      ("config", RasterConfigC),
+      ("indexes", P), ("features", P), ("image", P), ("camera_pos", P), ("digest", P),
+      ("overlap_to_point", P), ("tile_ranges", P),
+      ("d_image", P), ("d_depths", P),
+      ("grad_points", P), ("grad_features", P), ("grad_points_preset", I32), ("grad_features_preset", I32),
+      ("heuristic", P),
+      ("d_position", P), ("d_log_scaling", P), ("d_rotation", P), ("d_alpha_logit", P),
+      ("d_T_camera_world", P), ("d_projection", P), ("d_feature", P),
+      ("ev_raster_start", P), ("ev_raster_end", P),
   ]
 
 
@@ -67,6 +107,9 @@ SIGNATURES = {
     "gs_raster_digest_f32": ([P, P, P, I64, I32, POINTER(RasterConfigC), P, P], c_int32),
     "gs_raster_fwd_digest_f32": ([P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_digest_f32": ([P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
+    "gs_render_stage_a_f32": ([POINTER(RenderArgsC), POINTER(I64), POINTER(I64), P], c_int32),
+    "gs_render_stage_b_f32": ([POINTER(RenderArgsC), I64, I64, P, P, P, SZ, P], c_int32),
+    "gs_render_backward_f32": ([POINTER(RenderBwdArgsC), P], c_int32),
 }
 
 _lib = None
@@ -107,6 +150,9 @@ OWN_KERNELS = {
     "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1,
     "gs_tile_ranges_from_tiles": 1, "gs_raster_fwd_f32": 2, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 2, "gs_raster_bwd_f32": 2,
     "gs_raster_bwd_f64": 1, "gs_raster_digest_f32": 1, "gs_raster_fwd_digest_f32": 1, "gs_raster_bwd_digest_f32": 1,
+    # whole-frame drivers: cull, camera position, write, SH, digest, depth key, count, scan tail | emit, ranges, raster |
+    # raster backward, projection backward, SH backward
+    "gs_render_stage_a_f32": 8, "gs_render_stage_b_f32": 3, "gs_render_backward_f32": 3,
 }
 
 
@@ -128,7 +174,9 @@ class Profiler:
 profiler = None   # set to a Profiler() to enable
 
 
-def call(name: str, *args) -> None:
+def call(name: str, *args, on=None) -> None:
+  """Calls a C-ABI entry point.  `on`: the torch stream the call was enqueued on when it is not the current one
+  (only used to place the profiler's events)."""
   fn = getattr(load(), name)
   prof = profiler
   if prof is None:
@@ -138,7 +186,7 @@ def call(name: str, *args) -> None:
   if prof.only is not None and name not in prof.only:
     check(fn(*args), name)
     return
-  stream = torch.cuda.current_stream()
+  stream = on if on is not None else torch.cuda.current_stream()
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   a.record(stream)
   check(fn(*args), name)
@@ -171,6 +219,18 @@ def ptr(t) -> int | None:
 
 def stream_ptr(device) -> int:
   return torch.cuda.current_stream(device).cuda_stream
+
+
+_side_streams = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+  """One auxiliary stream per device: the renderer runs work that is independent of the tile-mapping chain
+  (SH evaluation, raster digest, zero fills, SH backward) on it, fenced with events against the caller's stream."""
+  key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+  if key not in _side_streams:
+    _side_streams[key] = torch.cuda.Stream(device=device)
+  return _side_streams[key]
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:

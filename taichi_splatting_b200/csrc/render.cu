@@ -1,0 +1,232 @@
+// render.cu -- whole-frame host drivers: the render path of renderer.py:22-108 enqueued from C.
+//
+// Nothing here computes: each driver calls the per-stage entry points of this library (same kernels, same
+// arguments, same order as the Python operator chain), so results are bit-identical to chaining the operators.
+// What changes is who pays the launch cost.  Chained from Python, every launch costs 20-30 us of interpreter /
+// allocator / ctypes time; the front end is 13 short kernels with two host reads in it, so the GPU idled between
+// launches for ~0.2-0.3 ms per frame (torch.profiler timeline, profiles/).  From C a launch costs 2-3 us, and
+// the work that does not feed the tile mapper -- SH evaluation, raster digest, zero fills, SH backward -- is put on
+// an auxiliary stream so that it really runs beside the latency-bound mapper chain / raster backward.
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gs {
+
+struct DeviceAux {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fence = nullptr, side_done = nullptr, raster_done = nullptr, fills_done = nullptr, bwd_join = nullptr;
+  int32_t *host_words = nullptr;   // pinned: [0] V, [1] K
+};
+
+static DeviceAux *device_aux() {
+  static std::mutex mu;
+  static std::map<int, DeviceAux> table;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  DeviceAux &a = table[dev];
+  if (a.side == nullptr) {
+    if (cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&a.fence, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&a.side_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&a.raster_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&a.fills_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&a.bwd_join, cudaEventDisableTiming);
+    if (cudaHostAlloc((void **)&a.host_words, 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  }
+  return &a;
+}
+
+static bool render_supported(const gs_raster_config &c, int channels) {
+  return c.tile_size == 16 && !c.antialias && c.use_alpha_blending && channels >= 1 && channels <= 4;
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ src, const int64_t *__restrict__ indexes, int64_t v,
+                                   int c, float *__restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v * c) return;
+  dst[i] = src[indexes[i / c] * c + i % c];
+}
+
+__global__ void scatter_rows_kernel(const float *__restrict__ src, const int64_t *__restrict__ indexes, int64_t v,
+                                    int c, float *__restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v * c) return;
+  dst[indexes[i / c] * c + i % c] = src[i];
+}
+
+#define GS_TRY(expr)           \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != GS_OK) return _rc; \
+  } while (0)
+
+static inline int pad_to(int x, int ts) { return (x + ts - 1) / ts * ts; }
+
+static inline int tile_bits(int64_t num_tiles) {
+  int bits = 1;
+  while ((int64_t(1) << bits) < num_tiles) ++bits;
+  return bits;
+}
+
+}  // namespace gs
+
+extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, int64_t *k_out, void *stream_) {
+  using namespace gs;
+  GS_CHECK_ARG(a != nullptr && v_out != nullptr && k_out != nullptr, "render_stage_a: NULL argument");
+  GS_CHECK_ARG(render_supported(a->config, a->channels), "render_stage_a: needs tile_size 16, no antialias, alpha blending, 1..4 features");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceAux *aux = device_aux();
+  if (aux == nullptr) { set_error("render_stage_a: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
+  const gs_raster_config &c = a->config;
+  const int64_t n = a->n;
+  *v_out = 0; *k_out = 0;
+
+  // ---- projection: cull -> V -> compacted write (+ ndc depth) ----
+  GS_TRY(gs_project_cull_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
+                             a->projection, n, a->width, a->height, a->near_plane, a->far_plane, a->blur_cov,
+                             a->clamp_margin, c.alpha_threshold, a->ws_project, a->ws_project_bytes,
+                             &aux->host_words[0], stream));
+  if (a->use_sh) GS_TRY(gs_camera_position_f32(a->T_camera_world, a->camera_pos, stream));
+  GS_CUDA(cudaStreamSynchronize(stream));
+  const int64_t v = aux->host_words[0];
+  *v_out = v;
+  GS_TRY(gs_project_write_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
+                              a->projection, n, a->width, a->height, a->near_plane, a->far_plane, a->blur_cov,
+                              a->clamp_margin, a->ws_project, a->points, a->depths, a->indexes, a->ndc, stream));
+
+  // ---- auxiliary stream: features, zero fills, raster digest (none of it feeds the mapper) ----
+  GS_CUDA(cudaEventRecord(aux->fence, stream));
+  GS_CUDA(cudaStreamWaitEvent(aux->side, aux->fence, 0));
+  if (a->use_sh) {
+    GS_TRY(gs_sh_fwd_f32(a->feature, a->position, a->indexes, a->camera_pos, v, a->channels, a->sh_degree,
+                         a->features, aux->side));
+  } else if (v > 0) {
+    const int64_t total = v * a->channels;
+    gather_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, aux->side>>>(a->feature, a->indexes, v, a->channels,
+                                                                               a->features);
+    GS_LAUNCH_CHECK();
+  }
+  if (a->visibility != nullptr && v > 0) GS_CUDA(cudaMemsetAsync(a->visibility, 0, sizeof(float) * v, aux->side));
+  if (a->heuristic != nullptr && v > 0) GS_CUDA(cudaMemsetAsync(a->heuristic, 0, sizeof(float) * 2 * v, aux->side));
+  GS_TRY(gs_raster_digest_f32(a->points, a->features, a->want_median ? a->depths : nullptr, v, a->channels, &a->config,
+                              a->digest, aux->side));
+  GS_CUDA(cudaEventRecord(aux->side_done, aux->side));
+
+  // ---- tile mapper, first half: depth order -> counts -> scan -> K ----
+  const int ts = c.tile_size;
+  const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
+  GS_TRY(gs_depth_order(a->ndc, v, a->use_depth16, a->order, a->ws_order, a->ws_order_bytes, stream));
+  GS_TRY(gs_tile_count_ordered(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, stream));
+  GS_TRY(gs_tile_scan(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[1], stream));
+  GS_CUDA(cudaStreamSynchronize(stream));
+  *k_out = v > 0 ? (int64_t)aux->host_words[1] : 0;
+  return GS_OK;
+}
+
+extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t k, uint32_t *tiles,
+                                     int32_t *o2p, void *ws_sort, size_t ws_sort_bytes, void *stream_) {
+  using namespace gs;
+  GS_CHECK_ARG(a != nullptr, "render_stage_b: NULL argument");
+  GS_CHECK_ARG(render_supported(a->config, a->channels), "render_stage_b: unsupported raster configuration");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceAux *aux = device_aux();
+  if (aux == nullptr) { set_error("render_stage_b: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
+  const gs_raster_config &c = a->config;
+  const int ts = c.tile_size;
+  const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
+  const int64_t num_tiles = (int64_t)(w_pad / ts) * (h_pad / ts);
+  const int32_t *sorted_o2p = o2p + k;
+  if (k > 0) {
+    GS_TRY(gs_tile_emit_ordered(a->points, a->order, a->cum, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p,
+                                stream));
+    GS_TRY(gs_sort_pairs(tiles, o2p, tiles + k, o2p + k, k, 4, 0, tile_bits(num_tiles), ws_sort, ws_sort_bytes,
+                         stream));
+  }
+  GS_TRY(gs_tile_ranges_from_tiles(tiles + k, k, a->tile_ranges, num_tiles, stream));
+  GS_CUDA(cudaStreamWaitEvent(stream, aux->side_done, 0));
+  if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
+  GS_TRY(gs_raster_fwd_digest_f32(a->digest, a->tile_ranges, sorted_o2p, v, k, a->width, a->height, a->channels,
+                                  &a->config, a->median_threshold, a->image, a->image_alpha, a->visibility,
+                                  a->want_median ? a->median_image : nullptr, stream));
+  if (a->ev_raster_end != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_end, stream));
+  return GS_OK;
+}
+
+extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_) {
+  using namespace gs;
+  GS_CHECK_ARG(a != nullptr, "render_backward: NULL argument");
+  GS_CHECK_ARG(render_supported(a->config, a->channels), "render_backward: unsupported raster configuration");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceAux *aux = device_aux();
+  if (aux == nullptr) { set_error("render_backward: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
+  const int64_t n = a->n, v = a->v;
+  const int F = a->channels;
+  const int D = a->use_sh ? (a->sh_degree + 1) * (a->sh_degree + 1) : 1;
+  const bool need_geom = a->d_position || a->d_log_scaling || a->d_rotation || a->d_alpha_logit ||
+                         a->d_T_camera_world || a->d_projection;
+
+  // ---- auxiliary stream: zero fills of the dense parameter gradients, beside the raster backward ----
+  GS_CUDA(cudaEventRecord(aux->fence, stream));
+  GS_CUDA(cudaStreamWaitEvent(aux->side, aux->fence, 0));
+  if (a->d_position) GS_CUDA(cudaMemsetAsync(a->d_position, 0, sizeof(float) * 3 * n, aux->side));
+  if (a->d_log_scaling) GS_CUDA(cudaMemsetAsync(a->d_log_scaling, 0, sizeof(float) * 3 * n, aux->side));
+  if (a->d_rotation) GS_CUDA(cudaMemsetAsync(a->d_rotation, 0, sizeof(float) * 4 * n, aux->side));
+  if (a->d_alpha_logit) GS_CUDA(cudaMemsetAsync(a->d_alpha_logit, 0, sizeof(float) * n, aux->side));
+  if (a->d_T_camera_world) GS_CUDA(cudaMemsetAsync(a->d_T_camera_world, 0, sizeof(float) * 16, aux->side));
+  if (a->d_projection) GS_CUDA(cudaMemsetAsync(a->d_projection, 0, sizeof(float) * 4, aux->side));
+  // the SH backward stores whole coefficient rows of every visible Gaussian: nothing to clear when all are visible
+  if (a->d_feature && !(a->use_sh && v == n))
+    GS_CUDA(cudaMemsetAsync(a->d_feature, 0, sizeof(float) * n * F * D, aux->side));
+  GS_CUDA(cudaEventRecord(aux->fills_done, aux->side));
+
+  // ---- raster backward ----
+  if (v > 0) {
+    if (a->grad_points && !a->grad_points_preset) GS_CUDA(cudaMemsetAsync(a->grad_points, 0, sizeof(float) * 7 * v, stream));
+    if (a->grad_features && !a->grad_features_preset) GS_CUDA(cudaMemsetAsync(a->grad_features, 0, sizeof(float) * F * v, stream));
+    if (a->d_image != nullptr) {
+      if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
+      GS_TRY(gs_raster_bwd_digest_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image, v, a->k,
+                                      a->width, a->height, F, &a->config, need_geom ? a->grad_points : nullptr,
+                                      a->d_feature ? a->grad_features : nullptr, a->heuristic, stream));
+      if (a->ev_raster_end != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_end, stream));
+    }
+    GS_CUDA(cudaEventRecord(aux->raster_done, stream));
+
+    // ---- auxiliary stream: feature gradient (SH backward / row scatter) ----
+    if (a->d_feature) {
+      GS_CUDA(cudaStreamWaitEvent(aux->side, aux->raster_done, 0));
+      if (a->use_sh) {
+        GS_TRY(gs_sh_bwd_f32(a->feature, a->position, a->indexes, a->camera_pos, a->grad_features, a->features, v, F,
+                             a->sh_degree, 1, a->d_feature, nullptr, nullptr, aux->side));
+      } else {
+        const int64_t total = v * F;
+        scatter_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, aux->side>>>(a->grad_features, a->indexes, v, F,
+                                                                                    a->d_feature);
+        GS_LAUNCH_CHECK();
+      }
+    }
+
+    // ---- caller's stream: projection backward ----
+    GS_CUDA(cudaStreamWaitEvent(stream, aux->fills_done, 0));
+    if (need_geom) {
+      const float *dd = a->d_depths;
+      if (dd == nullptr) {   // no incoming depth gradient: a zeroed column from library scratch
+        float *z = (float *)stream_workspace(stream, sizeof(float) * v);
+        if (z == nullptr) return GS_ERR_CUDA;
+        GS_CUDA(cudaMemsetAsync(z, 0, sizeof(float) * v, stream));
+        dd = z;
+      }
+      GS_TRY(gs_project_bwd_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
+                                a->projection, a->indexes, v, a->width, a->height, a->blur_cov, a->clamp_margin,
+                                a->grad_points, dd, a->d_position, a->d_log_scaling, a->d_rotation, a->d_alpha_logit,
+                                a->d_T_camera_world, a->d_projection, stream));
+    }
+  }
+  // ---- join ----
+  GS_CUDA(cudaEventRecord(aux->bwd_join, aux->side));
+  GS_CUDA(cudaStreamWaitEvent(stream, aux->bwd_join, 0));
+  return GS_OK;
+}

@@ -1,5 +1,6 @@
 """Renderer facade (reference: taichi_splatting/renderer.py:22-121): project -> SH | gather -> map_to_tiles
 -> rasterize (-> median-depth raster), each stage one of this package's operators."""
+import os
 from dataclasses import replace
 
 import torch
@@ -10,10 +11,48 @@ from .data_types import Gaussians3D, RasterConfig
 from .mapper.tile_mapper import bin_and_sort, map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import apply_with_ndc, camera_position
-from .rasterizer.function import (fused_median_supported, make_digest, rasterize_with_tiles,
+from .rasterizer.function import (fused_median_supported, rasterize_with_tiles,
                                   rasterize_with_tiles_and_median, tuned_supported)
 from .rendering import RenderedPoints, Rendering, ndc_depth
 from .spherical_harmonics import check_sh_degree, evaluate_sh_at
+
+
+# GS_FUSED_HOST=0 chains the per-stage entry points from Python instead of calling the whole-frame drivers
+# (csrc/render.cu): same kernels and results, more host time per launch (A/B switch; also what bench.py uses for
+# its per-stage timings)
+_FUSED_HOST = os.environ.get("GS_FUSED_HOST", "1") != "0"
+_ws_sizes = {}
+
+
+def _workspace_sizes(n: int):
+  """Workspace bytes of the projection, depth-order and scan stages for n Gaussians (cached)."""
+  if n not in _ws_sizes:
+    out = []
+    for name in ("gs_project_workspace_bytes", "gs_depth_order_workspace_bytes", "gs_tile_scan_workspace_bytes"):
+      nbytes = _lib.c_size_t()
+      _lib.call(name, n, nbytes)
+      out.append(int(nbytes.value))
+    _ws_sizes[n] = tuple(out)
+  return _ws_sizes[n]
+
+
+def _event_handle(ev):
+  return ev.cuda_event if ev is not None else None
+
+
+# Optional lists of (start, end) torch.cuda.Event pairs, one pair consumed per frame, which the whole-frame drivers
+# record around the raster launches on the caller's stream (bench.py times the dominant kernel with them).  The
+# events must be created with enable_timing=True and recorded once beforehand so that their handles exist.
+raster_events = {"fwd": None, "bwd": None}
+
+
+def _next_event_pair(which):
+  pairs = raster_events[which]
+  return pairs.pop(0) if pairs else None
+
+
+# GS_OVERLAP_STREAMS=0 keeps every launch on the caller's stream (A/B switch for profiling and debugging)
+_OVERLAP_STREAMS = os.environ.get("GS_OVERLAP_STREAMS", "1") != "0"
 
 
 class _RenderFunction(torch.autograd.Function):
@@ -29,6 +68,13 @@ class _RenderFunction(torch.autograd.Function):
     _lib.require_cuda(position=position, log_scaling=log_scaling, rotation=rotation, alpha_logit=alpha_logit,
                       feature=feature, T_camera_world=T_camera_world, projection=projection)
     dtype, device = position.dtype, position.device
+    channels = feature.shape[1] if feature.ndim >= 2 else 0
+    ctx.fused_host = (_FUSED_HOST and dtype == torch.float32 and config.use_alpha_blending
+                      and tuned_supported(config, channels, dtype) and feature.ndim == (3 if use_sh else 2))
+    if ctx.fused_host:
+      return _RenderFunction._forward_fused_host(ctx, position, log_scaling, rotation, alpha_logit, feature,
+                                                 T_camera_world, projection, camera, config, use_sh, use_depth16,
+                                                 render_median_depth, sh_exchange)
     sfx = _lib.suffix(dtype)
     call, ptr = _lib.call, _lib.ptr
     stream = _lib.stream_ptr(device)
@@ -60,16 +106,55 @@ class _RenderFunction(torch.autograd.Function):
     call(f"gs_project_write_{sfx}", *pin, n, w, h, near, far, blur, margin, ws_proj.data_ptr(), ptr(g2d), ptr(depths),
          ptr(indexes), ptr(ndc), stream)
 
+    # Everything below that does not feed the tile mapper (SH evaluation, zero fills of the accumulated outputs,
+    # the raster digest) is enqueued on an auxiliary stream: the mapper chain is a string of short, latency-bound
+    # kernels with two host reads in it, the SH evaluation is HBM-bound, so they overlap almost perfectly.  All
+    # buffers are allocated on the caller's stream; the two streams are fenced with events.
+    main = torch.cuda.current_stream(device)
+    side = _lib.side_stream(device)
+    overlap = _OVERLAP_STREAMS and side != main
+    aux, aux_ptr = (side, side.cuda_stream) if overlap else (main, stream)
+    if overlap:
+      fence = torch.cuda.Event()
+      fence.record(main)
+      side.wait_event(fence)
+
     # ---- features: SH at the visible set, or a plain gather ----
     if use_sh:
       degree = check_sh_degree(feature_c)
       channels = feature_c.shape[1]
       features = torch.empty((v, channels), dtype=dtype, device=device)
-      call(f"gs_sh_fwd_{sfx}", ptr(feature_c), pin[0], ptr(indexes), ptr(cam_pos), v, channels, degree, ptr(features), stream)
+      call(f"gs_sh_fwd_{sfx}", ptr(feature_c), pin[0], ptr(indexes), ptr(cam_pos), v, channels, degree, ptr(features),
+           aux_ptr, on=aux)
     else:
       assert feature_c.ndim == 2, f"Features must be (N, C) if use_sh=False, got {feature_c.shape}"
       features = feature_c[indexes]
+      if overlap:   # produced on the caller's stream
+        fence2 = torch.cuda.Event()
+        fence2.record(main)
+        side.wait_event(fence2)
     F = features.shape[1]
+
+    # accumulated outputs (zeroed) and the raster digest, still on the auxiliary stream
+    image = torch.empty((h, w, F), dtype=dtype, device=device)
+    alpha = torch.empty((h, w), dtype=dtype, device=device)
+    heuristic = torch.empty((v, 2) if config.compute_point_heuristic else (0, 2), dtype=dtype, device=device)
+    visibility = torch.empty((v,) if config.compute_visibility else (0,), dtype=dtype, device=device)
+    median = torch.empty((0,), dtype=dtype, device=device)
+    digest = torch.empty((0, 16), dtype=torch.float32, device=device)
+    fused_median = render_median_depth and fused_median_supported(config, F, dtype)
+    use_digest = tuned_supported(config, F, dtype) and (fused_median or not render_median_depth)
+    with torch.cuda.stream(aux):
+      heuristic.zero_()
+      visibility.zero_()
+    if use_digest:   # raster records, written once and gathered by the forward and the backward kernel
+      digest = torch.empty((v, 16), dtype=torch.float32, device=device)
+      if v > 0:
+        call("gs_raster_digest_f32", ptr(g2d), ptr(features), ptr(depths) if fused_median else None, v, F,
+             _lib.raster_config_c(config), ptr(digest), aux_ptr, on=aux)
+    if overlap:
+      aux_done = torch.cuda.Event()
+      aux_done.record(side)
 
     # ---- tile mapper (fp32 only, like the reference): two-level ordering, one host read (K) ----
     g32 = g2d if dtype == torch.float32 else g2d.float()
@@ -79,20 +164,11 @@ class _RenderFunction(torch.autograd.Function):
     ranges = tile_ranges.view(-1, 2)
 
     # ---- rasteriser (+ fused median depth) ----
-    image = torch.empty((h, w, F), dtype=dtype, device=device)
-    alpha = torch.empty((h, w), dtype=dtype, device=device)
-    heuristic = (torch.zeros((v, 2), dtype=dtype, device=device) if config.compute_point_heuristic
-                 else torch.empty((0, 2), dtype=dtype, device=device))
-    visibility = (torch.zeros((v,), dtype=dtype, device=device) if config.compute_visibility
-                  else torch.empty((0,), dtype=dtype, device=device))
+    if overlap:
+      main.wait_event(aux_done)
     vis_ptr = ptr(visibility) if config.compute_visibility else None
     cfg = _lib.raster_config_c(config)
-    median = torch.empty((0,), dtype=dtype, device=device)
-    digest = torch.empty((0, 16), dtype=torch.float32, device=device)
-    fused_median = render_median_depth and fused_median_supported(config, F, dtype)
-    if tuned_supported(config, F, dtype) and (fused_median or not render_median_depth):
-      # raster records, written once and gathered by the forward and the backward kernel
-      digest = make_digest(g2d, features, depths.view(-1) if fused_median else None, config)
+    if use_digest:
       if fused_median:
         median = torch.empty((h, w), dtype=dtype, device=device)
       call("gs_raster_fwd_digest_f32", ptr(digest), ptr(ranges), ptr(overlap_to_point), v, k, w, h, F, cfg,
@@ -118,7 +194,108 @@ class _RenderFunction(torch.autograd.Function):
     return image, alpha, g2d, depths, indexes, features, visibility, heuristic, median, overlap_to_point, tile_ranges
 
   @staticmethod
+  def _forward_fused_host(ctx, position, log_scaling, rotation, alpha_logit, feature, T_camera_world, projection,
+                          camera, config, use_sh, use_depth16, render_median_depth, sh_exchange):
+    """Same stages through gs_render_stage_a/b_f32: two C calls instead of ~20, buffers still allocated here."""
+    device = position.device
+    f32, i32 = torch.float32, torch.int32
+    ptr = _lib.ptr
+    stream = _lib.stream_ptr(device)
+    n = position.shape[0]
+    w, h = int(camera.image_size[0]), int(camera.image_size[1])
+    tensors = [t.detach().contiguous() for t in (position, log_scaling, rotation, alpha_logit, T_camera_world, projection)]
+    feature_c = feature.detach().contiguous()
+    F = feature_c.shape[1]
+    degree = check_sh_degree(feature_c) if use_sh else 0
+    ts = config.tile_size
+    tile_shape = ((h + ts - 1) // ts, (w + ts - 1) // ts)
+    assert tile_shape[0] * tile_shape[1] < 65535, \
+        f"tile dimensions {tile_shape} for image size {(w, h)} exceed maximum tile count (16 bit id), try increasing tile_size"
+
+    def empty(shape, dtype=f32):
+      return torch.empty(shape, dtype=dtype, device=device)
+
+    # capacity-n buffers (V is only known inside stage A); narrowed to V rows below
+    g2d_n, depths_n, ndc_n, idx_n = empty((n, 7)), empty((n, 1)), empty((n, 1)), empty((n,), torch.int64)
+    feat_n, digest_n = empty((n, F)), empty((n, 16))
+    vis_n = empty((n,)) if config.compute_visibility else None
+    heur_n = empty((n, 2)) if config.compute_point_heuristic else None
+    cam_pos = empty((3,))
+    order, counts, cum = empty((n,), i32), empty((n,), i32), empty((n + 1,), i32)
+    ws_bytes = _workspace_sizes(n)
+    ws = [_lib.workspace(b, device) for b in ws_bytes]
+    image, alpha = empty((h, w, F)), empty((h, w))
+    median = empty((h, w)) if render_median_depth else empty((0,))
+    tile_ranges = empty((*tile_shape, 2), i32)
+    ev_fwd = _next_event_pair("fwd")
+
+    args = _lib.RenderArgsC(
+        ptr(tensors[0]), ptr(tensors[1]), ptr(tensors[2]), ptr(tensors[3]), ptr(feature_c), ptr(tensors[4]), ptr(tensors[5]),
+        n, w, h, float(camera.near_plane), float(camera.far_plane), float(config.blur_cov), float(config.clamp_margin),
+        float(config.median_threshold), int(use_sh), degree, F, int(use_depth16), int(render_median_depth), 0,
+        _lib.raster_config_c(config),
+        ptr(g2d_n), ptr(depths_n), ptr(ndc_n), ptr(idx_n), ptr(feat_n), ptr(digest_n),
+        ptr(vis_n), ptr(heur_n), ptr(cam_pos), ptr(order), ptr(counts), ptr(cum),
+        ws[0].data_ptr(), ws[0].numel(), ws[1].data_ptr(), ws[1].numel(), ws[2].data_ptr(), ws[2].numel(),
+        ptr(image), ptr(alpha), ptr(median) if render_median_depth else None, ptr(tile_ranges),
+        _event_handle(ev_fwd[0] if ev_fwd else None), _event_handle(ev_fwd[1] if ev_fwd else None))
+    v_out, k_out = _lib.c_int64(), _lib.c_int64()
+    _lib.call("gs_render_stage_a_f32", args, v_out, k_out, stream)
+    v, k = int(v_out.value), int(k_out.value)
+
+    tiles, o2p = empty((2, k), i32), empty((2, k), i32)
+    nbytes = _lib.c_size_t()
+    _lib.call("gs_sort_pairs_workspace_bytes", k, 4, nbytes)
+    ws_sort = _lib.workspace(nbytes.value, device)
+    _lib.call("gs_render_stage_b_f32", args, v, k, ptr(tiles), ptr(o2p), ws_sort.data_ptr(), ws_sort.numel(), stream)
+
+    g2d, depths, indexes, features, digest = g2d_n[:v], depths_n[:v], idx_n[:v], feat_n[:v], digest_n[:v]
+    visibility = vis_n[:v] if vis_n is not None else empty((0,))
+    heuristic = heur_n[:v] if heur_n is not None else empty((0, 2))
+    overlap_to_point, ranges = o2p[1], tile_ranges.view(-1, 2)
+    ctx.save_for_backward(*tensors, feature_c, indexes, g2d, features, image, overlap_to_point, ranges, cam_pos, digest)
+    ctx.meta = (config, (w, h), float(config.blur_cov), float(config.clamp_margin), bool(use_sh), heuristic)
+    ctx.sh_exchange = sh_exchange
+    ctx.set_materialize_grads(False)
+    ctx.mark_non_differentiable(alpha, indexes, visibility, heuristic, median, overlap_to_point, tile_ranges)
+    return image, alpha, g2d, depths, indexes, features, visibility, heuristic, median, overlap_to_point, tile_ranges
+
+  @staticmethod
+  def _backward_fused_host(ctx, d_image, d_g2d, d_depths, d_features):
+    """The backward through gs_render_backward_f32 (single GPU; view-parallel runs use the staged path)."""
+    (position, log_scaling, rotation, alpha_logit, T_camera_world, projection, feature, indexes, g2d, features, image,
+     overlap_to_point, ranges, cam_pos, digest) = ctx.saved_tensors
+    config, (w, h), blur, margin, use_sh, heuristic = ctx.meta
+    device = position.device
+    ptr = _lib.ptr
+    n, v, k, F = position.shape[0], g2d.shape[0], overlap_to_point.shape[0], features.shape[1]
+    need = ctx.needs_input_grad
+    grads = [torch.empty_like(t) if need[i] else None
+             for t, i in ((position, 0), (log_scaling, 1), (rotation, 2), (alpha_logit, 3), (T_camera_world, 5), (projection, 6))]
+    d_feature = torch.empty_like(feature) if need[4] else None
+    grad_g = d_g2d.clone() if d_g2d is not None else torch.empty_like(g2d)
+    grad_f = d_features.clone() if d_features is not None else torch.empty_like(features)
+    ev_bwd = _next_event_pair("bwd")
+    args = _lib.RenderBwdArgsC(
+        ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(feature), ptr(T_camera_world), ptr(projection),
+        n, v, k, w, h, blur, margin, int(use_sh), check_sh_degree(feature) if use_sh else 0, F, 0,
+        _lib.raster_config_c(config),
+        ptr(indexes), ptr(features), ptr(image), ptr(cam_pos), ptr(digest), ptr(overlap_to_point), ptr(ranges),
+        ptr(d_image.contiguous()) if d_image is not None else None,
+        ptr(d_depths.contiguous()) if d_depths is not None else None,
+        ptr(grad_g), ptr(grad_f), int(d_g2d is not None), int(d_features is not None),
+        ptr(heuristic) if config.compute_point_heuristic else None,
+        *[ptr(g) for g in grads], ptr(d_feature),
+        _event_handle(ev_bwd[0] if ev_bwd else None), _event_handle(ev_bwd[1] if ev_bwd else None))
+    _lib.call("gs_render_backward_f32", args, _lib.stream_ptr(device))
+    return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)
+
+  @staticmethod
   def backward(ctx, d_image, d_alpha, d_g2d, d_depths, d_indexes, d_features, *unused):
+    if ctx.fused_host:
+      exchange = ctx.sh_exchange
+      if exchange is None or exchange.world <= 1 or not (ctx.needs_input_grad[4] and ctx.meta[4]):
+        return _RenderFunction._backward_fused_host(ctx, d_image, d_g2d, d_depths, d_features)
     (position, log_scaling, rotation, alpha_logit, T_camera_world, projection, feature, indexes, g2d, features, image,
      overlap_to_point, ranges, cam_pos, digest) = ctx.saved_tensors
     config, (w, h), blur, margin, use_sh, heuristic = ctx.meta
@@ -129,6 +306,36 @@ class _RenderFunction(torch.autograd.Function):
     v, F = g2d.shape[0], features.shape[1]
     need = ctx.needs_input_grad
     need_geom = any(need[i] for i in (0, 1, 2, 3, 5, 6))
+
+    exchange = ctx.sh_exchange if (need[4] and use_sh and dtype == torch.float32) else None
+    if exchange is not None and exchange.world <= 1:
+      exchange = None
+
+    # The raster backward is bound by shared memory, not HBM: the zero fills of the dense parameter gradients run
+    # beside it on the auxiliary stream, and afterwards the SH backward (HBM-bound) beside the projection backward
+    # (latency-bound).  Buffers are allocated on the caller's stream; streams are fenced with events.
+    main = torch.cuda.current_stream(device)
+    side = _lib.side_stream(device)
+    overlap = _OVERLAP_STREAMS and side != main and exchange is None
+    aux, aux_ptr = (side, side.cuda_stream) if overlap else (main, stream)
+    grads = [torch.empty_like(t) if need[i] else None
+             for t, i in ((position, 0), (log_scaling, 1), (rotation, 2), (alpha_logit, 3), (T_camera_world, 5), (projection, 6))]
+    sh_direct = need[4] and exchange is None
+    all_rows_written = use_sh and v == feature.shape[0]
+    d_feature = torch.empty_like(feature) if sh_direct else None
+    if overlap:
+      fence = torch.cuda.Event()
+      fence.record(main)
+      side.wait_event(fence)
+    with torch.cuda.stream(aux):
+      for t in grads:
+        if t is not None:
+          t.zero_()
+      if sh_direct and not all_rows_written:
+        d_feature.zero_()
+    if overlap:
+      fills_done = torch.cuda.Event()
+      fills_done.record(side)
 
     # ---- rasteriser backward: gradients of the packed 2D Gaussians and per-point features ----
     grad_g = d_g2d.clone() if d_g2d is not None else torch.zeros_like(g2d)
@@ -145,34 +352,35 @@ class _RenderFunction(torch.autograd.Function):
              ptr(d_image.contiguous()), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
              *out_ptrs, stream)
 
-    # ---- features (part 1): view-parallel runs launch the exchange of the SH-gradient factors now, so that the
-    # all-gather overlaps the projection backward ----
-    d_feature = None
-    exchange = ctx.sh_exchange if (need[4] and use_sh and dtype == torch.float32) else None
-    if exchange is not None and exchange.world <= 1:
-      exchange = None
+    # ---- features: SH backward on the auxiliary stream; view-parallel runs launch the exchange of the SH-gradient
+    # factors instead, so that the all-gather overlaps the projection backward ----
     pending = exchange.start(feature, indexes, features, grad_f, cam_pos) if exchange is not None else None
+    if sh_direct and v > 0:
+      if overlap:
+        raster_done = torch.cuda.Event()
+        raster_done.record(main)
+        side.wait_event(raster_done)
+      if use_sh:
+        call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), ptr(features), v,
+             feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, aux_ptr, on=aux)
+      else:
+        with torch.cuda.stream(aux):
+          d_feature.index_copy_(0, indexes, grad_f)
 
     # ---- projection backward ----
-    grads = [torch.zeros_like(t) if need[i] else None
-             for t, i in ((position, 0), (log_scaling, 1), (rotation, 2), (alpha_logit, 3), (T_camera_world, 5), (projection, 6))]
+    if overlap:
+      main.wait_event(fills_done)
     if need_geom and v > 0:
       dd = d_depths.contiguous() if d_depths is not None else torch.zeros((v, 1), dtype=dtype, device=device)
       call(f"gs_project_bwd_{sfx}", ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(T_camera_world),
            ptr(projection), ptr(indexes), v, w, h, blur, margin, ptr(grad_g), ptr(dd), *[ptr(g) for g in grads], stream)
 
-    # ---- features (part 2) ----
     if exchange is not None:
       d_feature = exchange.finish(pending, feature, position, check_sh_degree(feature))
-    elif need[4]:
-      all_rows_written = use_sh and v == feature.shape[0]
-      d_feature = torch.empty_like(feature) if all_rows_written else torch.zeros_like(feature)
-      if v > 0:
-        if use_sh:
-          call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), ptr(features), v,
-               feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, stream)
-        else:
-          d_feature.index_copy_(0, indexes, grad_f)
+    if overlap:
+      sh_done = torch.cuda.Event()
+      sh_done.record(side)
+      main.wait_event(sh_done)
     return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)
 
 
