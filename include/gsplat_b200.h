@@ -294,9 +294,16 @@ typedef struct gs_render_args {
 } gs_render_args;
 
 int gs_render_stage_a_f32(const gs_render_args *args, int64_t *v_out, int64_t *k_out, void *stream);
-int gs_render_stage_b_f32(const gs_render_args *args, int64_t v, int64_t k, uint32_t *tiles /* (2,k) */,
-                          int32_t *overlap_to_point /* (2,k): sorted result in row 1 */, void *ws_sort,
+int gs_render_stage_b_f32(const gs_render_args *args, int64_t v, int64_t k, int64_t k_stride /* >= k */,
+                          uint32_t *tiles /* (2,k_stride) */,
+                          int32_t *overlap_to_point /* (2,k_stride): sorted result in row 1 */, void *ws_sort,
                           size_t ws_sort_bytes, void *stream);
+/* Stage A, then stage B straight away when the caller's K-sized buffers (capacity k_capacity, e.g. sized from the
+ * previous frame) are large enough: *stage_b_done = 1.  Otherwise *stage_b_done = 0 and the caller allocates and
+ * calls gs_render_stage_b_f32 itself. */
+int gs_render_forward_f32(const gs_render_args *args, int64_t k_capacity, uint32_t *tiles, int32_t *overlap_to_point,
+                          void *ws_sort, size_t ws_sort_bytes, int64_t *v_out, int64_t *k_out,
+                          int32_t *stage_b_done, void *stream);
 
 typedef struct gs_render_bwd_args {
   const float *position, *log_scaling, *rotation, *alpha_logit, *feature, *T_camera_world, *projection;

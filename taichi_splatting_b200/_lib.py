@@ -108,7 +108,8 @@ SIGNATURES = {
     "gs_raster_fwd_digest_f32": ([P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_digest_f32": ([P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
     "gs_render_stage_a_f32": ([POINTER(RenderArgsC), POINTER(I64), POINTER(I64), P], c_int32),
-    "gs_render_stage_b_f32": ([POINTER(RenderArgsC), I64, I64, P, P, P, SZ, P], c_int32),
+    "gs_render_stage_b_f32": ([POINTER(RenderArgsC), I64, I64, I64, P, P, P, SZ, P], c_int32),
+    "gs_render_forward_f32": ([POINTER(RenderArgsC), I64, P, P, P, SZ, POINTER(I64), POINTER(I64), POINTER(I32), P], c_int32),
     "gs_render_backward_f32": ([POINTER(RenderBwdArgsC), P], c_int32),
 }
 
@@ -152,7 +153,7 @@ OWN_KERNELS = {
     "gs_raster_bwd_f64": 1, "gs_raster_digest_f32": 1, "gs_raster_fwd_digest_f32": 1, "gs_raster_bwd_digest_f32": 1,
     # whole-frame drivers: cull, camera position, write, SH, digest, depth key, count, scan tail | emit, ranges, raster |
     # raster backward, projection backward, SH backward
-    "gs_render_stage_a_f32": 8, "gs_render_stage_b_f32": 3, "gs_render_backward_f32": 3,
+    "gs_render_stage_a_f32": 8, "gs_render_stage_b_f32": 3, "gs_render_backward_f32": 3, "gs_render_forward_f32": 8,
 }
 
 

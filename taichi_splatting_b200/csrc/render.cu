@@ -126,11 +126,13 @@ extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, in
   return GS_OK;
 }
 
-extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t k, uint32_t *tiles,
-                                     int32_t *o2p, void *ws_sort, size_t ws_sort_bytes, void *stream_) {
+extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t k, int64_t k_stride,
+                                     uint32_t *tiles, int32_t *o2p, void *ws_sort, size_t ws_sort_bytes,
+                                     void *stream_) {
   using namespace gs;
   GS_CHECK_ARG(a != nullptr, "render_stage_b: NULL argument");
   GS_CHECK_ARG(render_supported(a->config, a->channels), "render_stage_b: unsupported raster configuration");
+  GS_CHECK_ARG(k_stride >= k, "render_stage_b: k_stride %lld < k %lld", (long long)k_stride, (long long)k);
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceAux *aux = device_aux();
   if (aux == nullptr) { set_error("render_stage_b: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
@@ -138,20 +140,35 @@ extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t
   const int ts = c.tile_size;
   const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
   const int64_t num_tiles = (int64_t)(w_pad / ts) * (h_pad / ts);
-  const int32_t *sorted_o2p = o2p + k;
+  const int32_t *sorted_o2p = o2p + k_stride;
   if (k > 0) {
     GS_TRY(gs_tile_emit_ordered(a->points, a->order, a->cum, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p,
                                 stream));
-    GS_TRY(gs_sort_pairs(tiles, o2p, tiles + k, o2p + k, k, 4, 0, tile_bits(num_tiles), ws_sort, ws_sort_bytes,
-                         stream));
+    GS_TRY(gs_sort_pairs(tiles, o2p, tiles + k_stride, o2p + k_stride, k, 4, 0, tile_bits(num_tiles), ws_sort,
+                         ws_sort_bytes, stream));
   }
-  GS_TRY(gs_tile_ranges_from_tiles(tiles + k, k, a->tile_ranges, num_tiles, stream));
+  GS_TRY(gs_tile_ranges_from_tiles(tiles + k_stride, k, a->tile_ranges, num_tiles, stream));
   GS_CUDA(cudaStreamWaitEvent(stream, aux->side_done, 0));
   if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
   GS_TRY(gs_raster_fwd_digest_f32(a->digest, a->tile_ranges, sorted_o2p, v, k, a->width, a->height, a->channels,
                                   &a->config, a->median_threshold, a->image, a->image_alpha, a->visibility,
                                   a->want_median ? a->median_image : nullptr, stream));
   if (a->ev_raster_end != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_end, stream));
+  return GS_OK;
+}
+
+extern "C" int gs_render_forward_f32(const gs_render_args *a, int64_t k_capacity, uint32_t *tiles, int32_t *o2p,
+                                     void *ws_sort, size_t ws_sort_bytes, int64_t *v_out, int64_t *k_out,
+                                     int32_t *stage_b_done, void *stream) {
+  GS_CHECK_ARG(stage_b_done != nullptr, "render_forward: NULL argument");
+  *stage_b_done = 0;
+  GS_TRY(gs_render_stage_a_f32(a, v_out, k_out, stream));
+  size_t need = 0;
+  GS_TRY(gs_sort_pairs_workspace_bytes(*k_out, 4, &need));
+  if (*k_out > k_capacity || (*k_out > 0 && (tiles == nullptr || o2p == nullptr || ws_sort_bytes < need)))
+    return GS_OK;   // the caller allocates K-sized buffers and runs stage B itself
+  GS_TRY(gs_render_stage_b_f32(a, *v_out, *k_out, k_capacity, tiles, o2p, ws_sort, ws_sort_bytes, stream));
+  *stage_b_done = 1;
   return GS_OK;
 }
 

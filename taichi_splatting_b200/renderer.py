@@ -22,6 +22,7 @@ from .spherical_harmonics import check_sh_degree, evaluate_sh_at
 # its per-stage timings)
 _FUSED_HOST = os.environ.get("GS_FUSED_HOST", "1") != "0"
 _ws_sizes = {}
+_k_capacity = {}   # device index -> capacity (in overlaps) to give the K-sized buffers of the next frame
 
 
 def _workspace_sizes(n: int):
@@ -239,20 +240,32 @@ class _RenderFunction(torch.autograd.Function):
         ws[0].data_ptr(), ws[0].numel(), ws[1].data_ptr(), ws[1].numel(), ws[2].data_ptr(), ws[2].numel(),
         ptr(image), ptr(alpha), ptr(median) if render_median_depth else None, ptr(tile_ranges),
         _event_handle(ev_fwd[0] if ev_fwd else None), _event_handle(ev_fwd[1] if ev_fwd else None))
-    v_out, k_out = _lib.c_int64(), _lib.c_int64()
-    _lib.call("gs_render_stage_a_f32", args, v_out, k_out, stream)
-    v, k = int(v_out.value), int(k_out.value)
-
-    tiles, o2p = empty((2, k), i32), empty((2, k), i32)
+    # K-sized buffers: sized from the previous frame on this device (+25 %), so that the driver can go from the
+    # host read of K straight into key emission; if K outgrew them, allocate exactly and run stage B from here
+    v_out, k_out, done = _lib.c_int64(), _lib.c_int64(), _lib.c_int32()
     nbytes = _lib.c_size_t()
-    _lib.call("gs_sort_pairs_workspace_bytes", k, 4, nbytes)
-    ws_sort = _lib.workspace(nbytes.value, device)
-    _lib.call("gs_render_stage_b_f32", args, v, k, ptr(tiles), ptr(o2p), ws_sort.data_ptr(), ws_sort.numel(), stream)
+    dev_key = device.index if device.index is not None else torch.cuda.current_device()
+    cap = _k_capacity.get(dev_key, 0)
+    tiles = o2p = ws_sort = None
+    if cap > 0:
+      tiles, o2p = empty((2, cap), i32), empty((2, cap), i32)
+      _lib.call("gs_sort_pairs_workspace_bytes", cap, 4, nbytes)
+      ws_sort = _lib.workspace(nbytes.value, device)
+    _lib.call("gs_render_forward_f32", args, cap, ptr(tiles), ptr(o2p), ws_sort.data_ptr() if cap > 0 else None,
+              ws_sort.numel() if cap > 0 else 0, v_out, k_out, done, stream)
+    v, k = int(v_out.value), int(k_out.value)
+    if not done.value:
+      cap = k
+      tiles, o2p = empty((2, k), i32), empty((2, k), i32)
+      _lib.call("gs_sort_pairs_workspace_bytes", k, 4, nbytes)
+      ws_sort = _lib.workspace(nbytes.value, device)
+      _lib.call("gs_render_stage_b_f32", args, v, k, k, ptr(tiles), ptr(o2p), ws_sort.data_ptr(), ws_sort.numel(), stream)
+    _k_capacity[dev_key] = max(int(k * 1.25), 1024)
 
     g2d, depths, indexes, features, digest = g2d_n[:v], depths_n[:v], idx_n[:v], feat_n[:v], digest_n[:v]
     visibility = vis_n[:v] if vis_n is not None else empty((0,))
     heuristic = heur_n[:v] if heur_n is not None else empty((0, 2))
-    overlap_to_point, ranges = o2p[1], tile_ranges.view(-1, 2)
+    overlap_to_point, ranges = o2p[1, :k], tile_ranges.view(-1, 2)
     ctx.save_for_backward(*tensors, feature_c, indexes, g2d, features, image, overlap_to_point, ranges, cam_pos, digest)
     ctx.meta = (config, (w, h), float(config.blur_cov), float(config.clamp_margin), bool(use_sh), heuristic)
     ctx.sh_exchange = sh_exchange
