@@ -186,6 +186,27 @@ int gs_tile_emit_ordered(const float *gaussians, const int32_t *order, const int
 int gs_tile_ranges_from_tiles(const uint32_t *sorted_tiles, int64_t k, int32_t *tile_ranges, int64_t num_tiles,
                               void *stream);
 
+/* Binned ordering: identical final order once more, without any global sort.  Overlaps are counted per TILE
+ * (atomics), the counts become the tile ranges, every overlap takes a slot inside its tile's segment in arrival
+ * order, and each segment is sorted on (depth bits << 32 | Gaussian index) in shared memory (keys are distinct, so
+ * the result is independent of the arrival order).  Segments longer than gs_tile_bin_max_per_tile() are not
+ * supported (GS_ERR_UNSUPPORTED): the caller reads the largest population with K and falls back to the two-level
+ * ordering.
+ *   gs_tile_bin_count    tile_counts (T) i32 (zeroed here)
+ *   gs_tile_bin_offsets  tile_ranges (T,2), cursor (T) = segment starts, totals {K, max per tile} -> device + pinned host
+ *   gs_tile_bin_emit     keys (K) u64 in segment slots (advances cursor)
+ *   gs_tile_bin_sort     overlap_to_point (K) i32                                                            */
+int gs_tile_bin_count(const float *gaussians, int64_t v, int32_t width_padded, int32_t height_padded,
+                      int32_t tile_size, double alpha_threshold, int32_t *tile_counts, void *stream);
+int gs_tile_bin_offsets(const int32_t *tile_counts, int64_t num_tiles, int32_t *tile_ranges, int32_t *cursor,
+                        int32_t *totals_dev /* 2 */, int32_t *totals_host /* 2, pinned */, void *stream);
+int gs_tile_bin_emit(const float *gaussians, const float *depths, int64_t v, int32_t width_padded,
+                     int32_t height_padded, int32_t tile_size, double alpha_threshold, int32_t use_depth16,
+                     int32_t *cursor, uint64_t *keys, void *stream);
+int gs_tile_bin_max_per_tile(void);
+int gs_tile_bin_sort(const uint64_t *keys, const int32_t *tile_ranges, int64_t num_tiles, int32_t max_per_tile,
+                     int32_t *overlap_to_point, void *stream);
+
 /* ---- R8: rasteriser forward ---------------------------------------------------------------------
  * replaces _forward_kernel (rasterizer/forward.py:22-135).  image (H,W,F), image_alpha (H,W),
  * visibility (V) zero-initialised by the caller (NULL unless compute_visibility).            */
@@ -260,10 +281,15 @@ int gs_raster_bwd_digest_f32(const void *digest, const int32_t *tile_ranges, con
  *             [host read K];  on the library's auxiliary stream, beside the mapper chain: SH evaluation (or the
  *             feature gather), zero fills of visibility / heuristic, the raster digest.
  *   stage B : ordered key emit -> stable tile sort -> tile ranges -> join the auxiliary stream -> raster forward.
+ *             (ordering = GS_ORDERING_BINNED: per-tile counts / slot emission / per-tile shared-memory sort
+ *             instead, falling back to the above when a tile is too crowded for it.)
  *   backward: zero fills (auxiliary stream, beside the raster backward) -> raster backward -> projection backward
  *             on the caller's stream beside the SH backward (or feature scatter) on the auxiliary stream -> join.
  * The auxiliary stream is owned by the library (one per device) and fenced against `stream` with events.
  * ev_* : optional cudaEvent_t handles recorded around the raster launch on `stream` (NULL: not recorded).      */
+#define GS_ORDERING_TWO_LEVEL 0
+#define GS_ORDERING_BINNED 1
+
 typedef struct gs_render_args {
   const float *position, *log_scaling, *rotation, *alpha_logit;   /* (n,3) (n,3) (n,4) (n,1) */
   const float *feature;            /* use_sh: SH coefficients (n,channels,(degree+1)^2); else features (n,channels) */
@@ -271,7 +297,8 @@ typedef struct gs_render_args {
   int64_t n;
   int32_t width, height;
   double near_plane, far_plane, blur_cov, clamp_margin, median_threshold;
-  int32_t use_sh, sh_degree, channels, use_depth16, want_median, reserved;
+  int32_t use_sh, sh_degree, channels, use_depth16, want_median;
+  int32_t ordering;                /* GS_ORDERING_TWO_LEVEL (default) | GS_ORDERING_BINNED; same result */
   gs_raster_config config;
   /* outputs with capacity n rows (V rows are written) */
   float *points;                   /* (n,7) */
@@ -291,10 +318,14 @@ typedef struct gs_render_args {
   float *image, *image_alpha, *median_image /* NULL unless want_median */;
   int32_t *tile_ranges;            /* (tiles,2) */
   void *ev_raster_start, *ev_raster_end;
+  int32_t *tile_counts, *tile_cursor;   /* (tiles) each: binned ordering */
+  int32_t *tile_totals;                 /* (2) */
 } gs_render_args;
 
-int gs_render_stage_a_f32(const gs_render_args *args, int64_t *v_out, int64_t *k_out, void *stream);
-int gs_render_stage_b_f32(const gs_render_args *args, int64_t v, int64_t k, int64_t k_stride /* >= k */,
+int gs_render_stage_a_f32(const gs_render_args *args, int64_t *v_out, int64_t *k_out, int64_t *max_per_tile_out,
+                          void *stream);
+int gs_render_stage_b_f32(const gs_render_args *args, int64_t v, int64_t k, int64_t max_per_tile,
+                          int64_t k_stride /* >= k */,
                           uint32_t *tiles /* (2,k_stride) */,
                           int32_t *overlap_to_point /* (2,k_stride): sorted result in row 1 */, void *ws_sort,
                           size_t ws_sort_bytes, void *stream);
@@ -303,7 +334,7 @@ int gs_render_stage_b_f32(const gs_render_args *args, int64_t v, int64_t k, int6
  * calls gs_render_stage_b_f32 itself. */
 int gs_render_forward_f32(const gs_render_args *args, int64_t k_capacity, uint32_t *tiles, int32_t *overlap_to_point,
                           void *ws_sort, size_t ws_sort_bytes, int64_t *v_out, int64_t *k_out,
-                          int32_t *stage_b_done, void *stream);
+                          int64_t *max_per_tile_out, int32_t *stage_b_done, void *stream);
 
 typedef struct gs_render_bwd_args {
   const float *position, *log_scaling, *rotation, *alpha_logit, *feature, *T_camera_world, *projection;

@@ -38,7 +38,7 @@ class RenderArgsC(ctypes.Structure):
       ("n", I64), ("width", I32), ("height", I32),
       ("near_plane", D), ("far_plane", D), ("blur_cov", D), ("clamp_margin", D), ("median_threshold", D),
       ("use_sh", I32), ("sh_degree", I32), ("channels", I32), ("use_depth16", I32), ("want_median", I32),
-      ("reserved", I32),
+      ("ordering", I32),
       ("config", RasterConfigC),
       ("points", P), ("depths", P), ("ndc", P), ("indexes", P), ("features", P), ("digest", P),
       ("visibility", P), ("heuristic", P), ("camera_pos", P), ("order", P), ("counts", P), ("cum", P),
@@ -46,6 +46,7 @@ class RenderArgsC(ctypes.Structure):
       ("ws_scan", P), ("ws_scan_bytes", SZ),
       ("image", P), ("image_alpha", P), ("median_image", P), ("tile_ranges", P),
       ("ev_raster_start", P), ("ev_raster_end", P),
+      ("tile_counts", P), ("tile_cursor", P), ("tile_totals", P),
   ]
 
 
@@ -100,6 +101,11 @@ SIGNATURES = {
     "gs_tile_count_ordered": ([P, P, I64, I32, I32, I32, D, P, P], c_int32),
     "gs_tile_emit_ordered": ([P, P, P, I64, I32, I32, I32, D, P, P, P], c_int32),
     "gs_tile_ranges_from_tiles": ([P, I64, P, I64, P], c_int32),
+    "gs_tile_bin_count": ([P, I64, I32, I32, I32, D, P, P], c_int32),
+    "gs_tile_bin_offsets": ([P, I64, P, P, P, P, P], c_int32),
+    "gs_tile_bin_emit": ([P, P, I64, I32, I32, I32, D, I32, P, P, P], c_int32),
+    "gs_tile_bin_max_per_tile": ([], c_int32),
+    "gs_tile_bin_sort": ([P, P, I64, I32, P, P], c_int32),
     "gs_raster_fwd_f32": (_RASTER_FWD, c_int32), "gs_raster_fwd_f64": (_RASTER_FWD, c_int32),
     "gs_raster_fwd_median_f32": ([P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_f32": (_RASTER_BWD, c_int32), "gs_raster_bwd_f64": (_RASTER_BWD, c_int32),
@@ -107,9 +113,10 @@ SIGNATURES = {
     "gs_raster_digest_f32": ([P, P, P, I64, I32, POINTER(RasterConfigC), P, P], c_int32),
     "gs_raster_fwd_digest_f32": ([P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_digest_f32": ([P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
-    "gs_render_stage_a_f32": ([POINTER(RenderArgsC), POINTER(I64), POINTER(I64), P], c_int32),
-    "gs_render_stage_b_f32": ([POINTER(RenderArgsC), I64, I64, I64, P, P, P, SZ, P], c_int32),
-    "gs_render_forward_f32": ([POINTER(RenderArgsC), I64, P, P, P, SZ, POINTER(I64), POINTER(I64), POINTER(I32), P], c_int32),
+    "gs_render_stage_a_f32": ([POINTER(RenderArgsC), POINTER(I64), POINTER(I64), POINTER(I64), P], c_int32),
+    "gs_render_stage_b_f32": ([POINTER(RenderArgsC), I64, I64, I64, I64, P, P, P, SZ, P], c_int32),
+    "gs_render_forward_f32": ([POINTER(RenderArgsC), I64, P, P, P, SZ, POINTER(I64), POINTER(I64), POINTER(I64),
+                               POINTER(I32), P], c_int32),
     "gs_render_backward_f32": ([POINTER(RenderBwdArgsC), P], c_int32),
 }
 
@@ -149,7 +156,8 @@ OWN_KERNELS = {
     "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_camera_position_f32": 1, "gs_camera_position_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
     "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_sh_bwd_views_f32": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
     "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1,
-    "gs_tile_ranges_from_tiles": 1, "gs_raster_fwd_f32": 2, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 2, "gs_raster_bwd_f32": 2,
+    "gs_tile_ranges_from_tiles": 1, "gs_tile_bin_count": 1, "gs_tile_bin_offsets": 1, "gs_tile_bin_emit": 1,
+    "gs_tile_bin_sort": 1, "gs_raster_fwd_f32": 2, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 2, "gs_raster_bwd_f32": 2,
     "gs_raster_bwd_f64": 1, "gs_raster_digest_f32": 1, "gs_raster_fwd_digest_f32": 1, "gs_raster_bwd_digest_f32": 1,
     # whole-frame drivers: cull, camera position, write, SH, digest, depth key, count, scan tail | emit, ranges, raster |
     # raster backward, projection backward, SH backward
@@ -246,6 +254,14 @@ def host_word(device) -> torch.Tensor:
   key = (device.type, device.index)
   if key not in _host_words:
     _host_words[key] = torch.zeros((1,), dtype=torch.int32).pin_memory()
+  return _host_words[key]
+
+
+def host_words(device, count: int) -> torch.Tensor:
+  """`count` pinned int32 words per device (asynchronous multi-word read-backs)."""
+  key = (device.type, device.index, count)
+  if key not in _host_words:
+    _host_words[key] = torch.zeros((count,), dtype=torch.int32).pin_memory()
   return _host_words[key]
 
 

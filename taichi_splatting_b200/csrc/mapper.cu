@@ -154,6 +154,126 @@ tile_emit_ordered_kernel(const float *__restrict__ gaussians, const int32_t *__r
       }
 }
 
+// ---- binned ordering (same final order again, no global sort at all) --------------------------------------------
+// The final order is: by tile, then by depth bits, ties by ascending Gaussian index.  Count overlaps per TILE
+// (atomics), turn the counts into tile offsets (= the tile ranges), let every overlap grab a slot inside its
+// tile's segment in arrival order (atomic cursor), then sort each tile's segment on the 64-bit key
+// (depth bits << 32 | Gaussian index) in shared memory.  The keys of a segment are distinct, so the result does not
+// depend on the arrival order.  ~234 keys per tile at the bench workload: one small bitonic network per CTA instead
+// of six onesweep passes over V + K pairs.
+__global__ void __launch_bounds__(128)
+tile_bin_count_kernel(const float *__restrict__ gaussians, int64_t v, int w_pad, int h_pad, int ts, float thr,
+                      int32_t *__restrict__ tile_counts) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= v) return;
+  ObbQuery q = obb_grid_query(gaussians + 7 * i, w_pad, h_pad, ts, thr);
+  const int tiles_wide = w_pad / ts;
+  for (int u = 0; u < q.spanx; ++u)
+    for (int w = 0; w < q.spany; ++w)
+      if (test_tile(q, u, w, ts)) atomicAdd(tile_counts + (q.minx + u) + (q.miny + w) * tiles_wide, 1);
+}
+
+// one CTA: exclusive scan of the tile counts -> tile ranges (empty tiles stay (0,0), tile_mapper.py:188), slot
+// cursors, total K and the largest tile population (both to pinned host words)
+__global__ void __launch_bounds__(1024)
+tile_bin_offsets_kernel(const int32_t *__restrict__ tile_counts, int num_tiles, int32_t *__restrict__ ranges,
+                        int32_t *__restrict__ cursor, int32_t *__restrict__ totals) {
+  __shared__ int32_t warp_sum[32], warp_max[32];
+  __shared__ int32_t part[1024];
+  __shared__ int32_t pmax[1024];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (num_tiles + 1023) / 1024;
+  const int lo = tid * per, hi = min(lo + per, num_tiles);
+  int32_t sum = 0, mx = 0;
+  for (int t = lo; t < hi; ++t) { int32_t c = tile_counts[t]; sum += c; mx = max(mx, c); }
+  // inclusive scan of the per-thread sums: warp shuffles, then the 32 warp totals
+  int32_t incl = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    int32_t a = __shfl_up_sync(0xffffffffu, incl, off);
+    int32_t b = __shfl_xor_sync(0xffffffffu, mx, off);
+    if (lane >= off) incl += a;
+    mx = max(mx, b);
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  if (lane == 0) warp_max[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    int32_t w = warp_sum[lane], m = warp_max[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      int32_t a = __shfl_up_sync(0xffffffffu, w, off);
+      int32_t b = __shfl_xor_sync(0xffffffffu, m, off);
+      if (lane >= off) w += a;
+      m = max(m, b);
+    }
+    warp_sum[lane] = w;    // inclusive over warps
+    warp_max[lane] = m;    // global maximum in every lane
+  }
+  __syncthreads();
+  part[tid] = incl + (warp > 0 ? warp_sum[warp - 1] : 0);
+  pmax[tid] = warp_max[0];
+  __syncthreads();
+  int32_t run = part[tid] - sum;
+  for (int t = lo; t < hi; ++t) {
+    const int32_t c = tile_counts[t];
+    ranges[2 * t] = c > 0 ? run : 0;
+    ranges[2 * t + 1] = c > 0 ? run + c : 0;
+    cursor[t] = run;
+    run += c;
+  }
+  if (tid == 1023) { totals[0] = part[1023]; totals[1] = pmax[1023]; }
+}
+
+template <bool DEPTH16>
+__global__ void __launch_bounds__(128)
+tile_bin_emit_kernel(const float *__restrict__ gaussians, const float *__restrict__ depths, int64_t v, int w_pad,
+                     int h_pad, int ts, float thr, int32_t *__restrict__ cursor, uint64_t *__restrict__ keys) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= v) return;
+  ObbQuery q = obb_grid_query(gaussians + 7 * i, w_pad, h_pad, ts, thr);
+  const int tiles_wide = w_pad / ts;
+  const float depth = depths[i];
+  const uint32_t dbits = DEPTH16 ? (uint32_t)__fmul_rn(fminf(fmaxf(depth, 0.0f), 1.0f), 65535.0f) : __float_as_uint(depth);
+  const uint64_t key = ((uint64_t)dbits << 32) | (uint32_t)i;
+  for (int u = 0; u < q.spanx; ++u)
+    for (int w = 0; w < q.spany; ++w)
+      if (test_tile(q, u, w, ts)) {
+        const int32_t slot = atomicAdd(cursor + (q.minx + u) + (q.miny + w) * tiles_wide, 1);
+        keys[slot] = key;
+      }
+}
+
+// one CTA per tile: bitonic sort of the tile's (depth bits | index) keys in shared memory
+template <int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+tile_bin_sort_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ ranges,
+                     int32_t *__restrict__ overlap_to_point) {
+  __shared__ uint64_t sk[CAP];
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int start = ranges[2 * tile], n = ranges[2 * tile + 1] - start;
+  if (n <= 0) return;
+  int p = 2;
+  while (p < n) p <<= 1;
+  for (int i = tid; i < p; i += THREADS) sk[i] = i < n ? keys[start + i] : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= p; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < (p >> 1); i += THREADS) {
+        const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1)), b = a | j;
+        const uint64_t x = sk[a], y = sk[b];
+        const bool up = (a & k) == 0;
+        if ((x > y) == up) { sk[a] = y; sk[b] = x; }
+      }
+      // With one pair per thread, pairs at distance j <= 32 stay inside the 64 elements a warp owns, so a run of
+      // such steps only needs warp-level ordering; a CTA barrier separates it from any longer-distance step.
+      const int next_j = j > 1 ? (j >> 1) : k;
+      if (j > 32 || next_j > 32 || p > 2 * THREADS) __syncthreads(); else __syncwarp();
+    }
+  __syncthreads();
+  for (int i = tid; i < n; i += THREADS) overlap_to_point[start + i] = (int32_t)(uint32_t)sk[i];
+}
+
 __global__ void finish_scan_kernel(const int32_t *__restrict__ counts, int32_t *__restrict__ cum, int64_t v,
                                    int32_t *__restrict__ total_dev) {
   // cum[0..v-1] holds the exclusive scan; complete entry v (cuda_lib/full_cumsum.cu:6-10)
@@ -351,6 +471,67 @@ extern "C" int gs_tile_ranges_from_tiles(const uint32_t *sorted_tiles, int64_t k
   GS_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * num_tiles, stream));
   if (k == 0) return GS_OK;
   gs::tile_ranges_kernel<uint32_t><<<(unsigned)gs::ceil_div(k, 256), 256, 0, stream>>>(sorted_tiles, k, 0, tile_ranges);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+// ---- binned ordering --------------------------------------------------------------------------------------------
+extern "C" int gs_tile_bin_count(const float *gaussians, int64_t v, int32_t w_pad, int32_t h_pad, int32_t ts,
+                                 double alpha_threshold, int32_t *tile_counts, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_bin_count: image %dx%d not padded to tile %d", w_pad, h_pad, ts);
+  const int64_t num_tiles = (int64_t)(w_pad / ts) * (h_pad / ts);
+  GS_CHECK_ARG(num_tiles < 65535, "tile dimensions (%d, %d) exceed maximum tile count (16 bit id), try increasing tile_size", h_pad / ts, w_pad / ts);
+  GS_CUDA(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * num_tiles, stream));
+  if (v == 0) return GS_OK;
+  gs::tile_bin_count_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, stream>>>(gaussians, v, w_pad, h_pad, ts,
+                                                                                 (float)alpha_threshold, tile_counts);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_tile_bin_offsets(const int32_t *tile_counts, int64_t num_tiles, int32_t *tile_ranges,
+                                   int32_t *cursor, int32_t *totals_dev, int32_t *totals_host, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CHECK_ARG(num_tiles > 0 && num_tiles < 65535, "tile_bin_offsets: bad tile count %lld", (long long)num_tiles);
+  GS_CHECK_ARG(totals_dev != nullptr && totals_host != nullptr, "tile_bin_offsets: totals is NULL");
+  gs::tile_bin_offsets_kernel<<<1, 1024, 0, stream>>>(tile_counts, (int)num_tiles, tile_ranges, cursor, totals_dev);
+  GS_LAUNCH_CHECK();
+  GS_CUDA(cudaMemcpyAsync(totals_host, totals_dev, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  return GS_OK;
+}
+
+extern "C" int gs_tile_bin_emit(const float *gaussians, const float *depths, int64_t v, int32_t w_pad, int32_t h_pad,
+                                int32_t ts, double alpha_threshold, int32_t use_depth16, int32_t *cursor,
+                                uint64_t *keys, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_bin_emit: image not padded to tile size");
+  if (v == 0) return GS_OK;
+  const unsigned grid = (unsigned)gs::ceil_div(v, 128);
+  if (use_depth16)
+    gs::tile_bin_emit_kernel<true><<<grid, 128, 0, stream>>>(gaussians, depths, v, w_pad, h_pad, ts, (float)alpha_threshold, cursor, keys);
+  else
+    gs::tile_bin_emit_kernel<false><<<grid, 128, 0, stream>>>(gaussians, depths, v, w_pad, h_pad, ts, (float)alpha_threshold, cursor, keys);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_tile_bin_max_per_tile(void) { return 4096; }
+
+extern "C" int gs_tile_bin_sort(const uint64_t *keys, const int32_t *tile_ranges, int64_t num_tiles,
+                                int32_t max_per_tile, int32_t *overlap_to_point, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (max_per_tile > gs_tile_bin_max_per_tile()) {
+    gs::set_error("tile_bin_sort: %d overlaps in one tile exceed the shared-memory sort capacity (%d); use the "
+                  "two-level ordering", max_per_tile, gs_tile_bin_max_per_tile());
+    return GS_ERR_UNSUPPORTED;
+  }
+  if (num_tiles == 0 || max_per_tile <= 0) return GS_OK;
+  const unsigned grid = (unsigned)num_tiles;
+  if (max_per_tile <= 512) gs::tile_bin_sort_kernel<512, 128><<<grid, 128, 0, stream>>>(keys, tile_ranges, overlap_to_point);
+  else if (max_per_tile <= 1024) gs::tile_bin_sort_kernel<1024, 256><<<grid, 256, 0, stream>>>(keys, tile_ranges, overlap_to_point);
+  else if (max_per_tile <= 2048) gs::tile_bin_sort_kernel<2048, 512><<<grid, 512, 0, stream>>>(keys, tile_ranges, overlap_to_point);
+  else gs::tile_bin_sort_kernel<4096, 1024><<<grid, 1024, 0, stream>>>(keys, tile_ranges, overlap_to_point);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

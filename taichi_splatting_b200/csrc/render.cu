@@ -17,7 +17,7 @@ namespace gs {
 struct DeviceAux {
   cudaStream_t side = nullptr;
   cudaEvent_t fence = nullptr, side_done = nullptr, raster_done = nullptr, fills_done = nullptr, bwd_join = nullptr;
-  int32_t *host_words = nullptr;   // pinned: [0] V, [1] K
+  int32_t *host_words = nullptr;   // pinned: [0] V, [1] K, [2] largest tile population (binned ordering), [4] K (fallback)
 };
 
 static DeviceAux *device_aux() {
@@ -73,16 +73,18 @@ static inline int tile_bits(int64_t num_tiles) {
 
 }  // namespace gs
 
-extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, int64_t *k_out, void *stream_) {
+extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, int64_t *k_out,
+                                     int64_t *max_per_tile_out, void *stream_) {
   using namespace gs;
-  GS_CHECK_ARG(a != nullptr && v_out != nullptr && k_out != nullptr, "render_stage_a: NULL argument");
+  GS_CHECK_ARG(a != nullptr && v_out != nullptr && k_out != nullptr && max_per_tile_out != nullptr,
+               "render_stage_a: NULL argument");
   GS_CHECK_ARG(render_supported(a->config, a->channels), "render_stage_a: needs tile_size 16, no antialias, alpha blending, 1..4 features");
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceAux *aux = device_aux();
   if (aux == nullptr) { set_error("render_stage_a: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
   const gs_raster_config &c = a->config;
   const int64_t n = a->n;
-  *v_out = 0; *k_out = 0;
+  *v_out = 0; *k_out = 0; *max_per_tile_out = 0;
 
   // ---- projection: cull -> V -> compacted write (+ ndc depth) ----
   GS_TRY(gs_project_cull_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
@@ -115,9 +117,20 @@ extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, in
                               a->digest, aux->side));
   GS_CUDA(cudaEventRecord(aux->side_done, aux->side));
 
-  // ---- tile mapper, first half: depth order -> counts -> scan -> K ----
   const int ts = c.tile_size;
   const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
+  if (a->ordering == GS_ORDERING_BINNED) {
+    // ---- tile mapper, first half (binned ordering): per-tile counts -> tile ranges / slot cursors -> K ----
+    const int64_t num_tiles = (int64_t)(w_pad / ts) * (h_pad / ts);
+    GS_TRY(gs_tile_bin_count(a->points, v, w_pad, h_pad, ts, c.alpha_threshold, a->tile_counts, stream));
+    GS_TRY(gs_tile_bin_offsets(a->tile_counts, num_tiles, a->tile_ranges, a->tile_cursor, a->tile_totals,
+                               &aux->host_words[1], stream));
+    GS_CUDA(cudaStreamSynchronize(stream));
+    *k_out = (int64_t)aux->host_words[1];
+    *max_per_tile_out = (int64_t)aux->host_words[2];
+    return GS_OK;
+  }
+  // ---- tile mapper, first half (two-level ordering): depth order -> counts -> scan -> K ----
   GS_TRY(gs_depth_order(a->ndc, v, a->use_depth16, a->order, a->ws_order, a->ws_order_bytes, stream));
   GS_TRY(gs_tile_count_ordered(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, stream));
   GS_TRY(gs_tile_scan(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[1], stream));
@@ -126,9 +139,9 @@ extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, in
   return GS_OK;
 }
 
-extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t k, int64_t k_stride,
-                                     uint32_t *tiles, int32_t *o2p, void *ws_sort, size_t ws_sort_bytes,
-                                     void *stream_) {
+extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t k, int64_t max_per_tile,
+                                     int64_t k_stride, uint32_t *tiles, int32_t *o2p, void *ws_sort,
+                                     size_t ws_sort_bytes, void *stream_) {
   using namespace gs;
   GS_CHECK_ARG(a != nullptr, "render_stage_b: NULL argument");
   GS_CHECK_ARG(render_supported(a->config, a->channels), "render_stage_b: unsupported raster configuration");
@@ -141,13 +154,32 @@ extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t
   const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
   const int64_t num_tiles = (int64_t)(w_pad / ts) * (h_pad / ts);
   const int32_t *sorted_o2p = o2p + k_stride;
-  if (k > 0) {
-    GS_TRY(gs_tile_emit_ordered(a->points, a->order, a->cum, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p,
-                                stream));
-    GS_TRY(gs_sort_pairs(tiles, o2p, tiles + k_stride, o2p + k_stride, k, 4, 0, tile_bits(num_tiles), ws_sort,
-                         ws_sort_bytes, stream));
+  const bool binned = a->ordering == GS_ORDERING_BINNED;
+  if (binned && max_per_tile <= gs_tile_bin_max_per_tile()) {
+    // binned ordering, second half: slot emission, then one shared-memory sort per tile.  `tiles` (2 k_stride u32)
+    // holds the k 64-bit keys.
+    if (k > 0) {
+      GS_TRY(gs_tile_bin_emit(a->points, a->ndc, v, w_pad, h_pad, ts, c.alpha_threshold, a->use_depth16, a->tile_cursor,
+                              reinterpret_cast<uint64_t *>(tiles), stream));
+      GS_TRY(gs_tile_bin_sort(reinterpret_cast<const uint64_t *>(tiles), a->tile_ranges, num_tiles,
+                              (int32_t)max_per_tile, o2p + k_stride, stream));
+    }
+  } else {
+    // two-level ordering, second half (depth sort on V done in stage A, tile sort on K here); after a binned
+    // stage A that met a tile too crowded for the shared-memory sort, its first half runs here too
+    if (binned) {
+      GS_TRY(gs_depth_order(a->ndc, v, a->use_depth16, a->order, a->ws_order, a->ws_order_bytes, stream));
+      GS_TRY(gs_tile_count_ordered(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, stream));
+      GS_TRY(gs_tile_scan(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[4], stream));
+    }
+    if (k > 0) {
+      GS_TRY(gs_tile_emit_ordered(a->points, a->order, a->cum, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p,
+                                  stream));
+      GS_TRY(gs_sort_pairs(tiles, o2p, tiles + k_stride, o2p + k_stride, k, 4, 0, tile_bits(num_tiles), ws_sort,
+                           ws_sort_bytes, stream));
+    }
+    GS_TRY(gs_tile_ranges_from_tiles(tiles + k_stride, k, a->tile_ranges, num_tiles, stream));
   }
-  GS_TRY(gs_tile_ranges_from_tiles(tiles + k_stride, k, a->tile_ranges, num_tiles, stream));
   GS_CUDA(cudaStreamWaitEvent(stream, aux->side_done, 0));
   if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
   GS_TRY(gs_raster_fwd_digest_f32(a->digest, a->tile_ranges, sorted_o2p, v, k, a->width, a->height, a->channels,
@@ -159,15 +191,16 @@ extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t
 
 extern "C" int gs_render_forward_f32(const gs_render_args *a, int64_t k_capacity, uint32_t *tiles, int32_t *o2p,
                                      void *ws_sort, size_t ws_sort_bytes, int64_t *v_out, int64_t *k_out,
-                                     int32_t *stage_b_done, void *stream) {
+                                     int64_t *max_per_tile_out, int32_t *stage_b_done, void *stream) {
   GS_CHECK_ARG(stage_b_done != nullptr, "render_forward: NULL argument");
   *stage_b_done = 0;
-  GS_TRY(gs_render_stage_a_f32(a, v_out, k_out, stream));
+  GS_TRY(gs_render_stage_a_f32(a, v_out, k_out, max_per_tile_out, stream));
   size_t need = 0;
   GS_TRY(gs_sort_pairs_workspace_bytes(*k_out, 4, &need));
   if (*k_out > k_capacity || (*k_out > 0 && (tiles == nullptr || o2p == nullptr || ws_sort_bytes < need)))
     return GS_OK;   // the caller allocates K-sized buffers and runs stage B itself
-  GS_TRY(gs_render_stage_b_f32(a, *v_out, *k_out, k_capacity, tiles, o2p, ws_sort, ws_sort_bytes, stream));
+  GS_TRY(gs_render_stage_b_f32(a, *v_out, *k_out, *max_per_tile_out, k_capacity, tiles, o2p, ws_sort, ws_sort_bytes,
+                               stream));
   *stage_b_done = 1;
   return GS_OK;
 }

@@ -8,7 +8,7 @@ from beartype import beartype
 
 from . import _lib
 from .data_types import Gaussians3D, RasterConfig
-from .mapper.tile_mapper import bin_and_sort, map_to_tiles
+from .mapper.tile_mapper import ORDERING, bin_and_sort, bin_and_sort_binned, map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import apply_with_ndc, camera_position
 from .rasterizer.function import (fused_median_supported, rasterize_with_tiles,
@@ -160,7 +160,11 @@ class _RenderFunction(torch.autograd.Function):
     # ---- tile mapper (fp32 only, like the reference): two-level ordering, one host read (K) ----
     g32 = g2d if dtype == torch.float32 else g2d.float()
     d32 = (ndc if dtype == torch.float32 else ndc.float()).view(-1)
-    overlap_to_point, tile_ranges, _, _, _ = bin_and_sort(g32, d32, (w, h), config, use_depth16)
+    binned = bin_and_sort_binned(g32, d32, (w, h), config, use_depth16) if ORDERING == "binned" else None
+    if binned is not None:
+      overlap_to_point, tile_ranges = binned
+    else:
+      overlap_to_point, tile_ranges, _, _, _ = bin_and_sort(g32, d32, (w, h), config, use_depth16)
     k = overlap_to_point.shape[0]
     ranges = tile_ranges.view(-1, 2)
 
@@ -228,21 +232,25 @@ class _RenderFunction(torch.autograd.Function):
     image, alpha = empty((h, w, F)), empty((h, w))
     median = empty((h, w)) if render_median_depth else empty((0,))
     tile_ranges = empty((*tile_shape, 2), i32)
+    num_tiles = tile_shape[0] * tile_shape[1]
+    tile_counts, tile_cursor, tile_totals = empty((num_tiles,), i32), empty((num_tiles,), i32), empty((2,), i32)
     ev_fwd = _next_event_pair("fwd")
 
     args = _lib.RenderArgsC(
         ptr(tensors[0]), ptr(tensors[1]), ptr(tensors[2]), ptr(tensors[3]), ptr(feature_c), ptr(tensors[4]), ptr(tensors[5]),
         n, w, h, float(camera.near_plane), float(camera.far_plane), float(config.blur_cov), float(config.clamp_margin),
-        float(config.median_threshold), int(use_sh), degree, F, int(use_depth16), int(render_median_depth), 0,
+        float(config.median_threshold), int(use_sh), degree, F, int(use_depth16), int(render_median_depth),
+        int(ORDERING == "binned"),
         _lib.raster_config_c(config),
         ptr(g2d_n), ptr(depths_n), ptr(ndc_n), ptr(idx_n), ptr(feat_n), ptr(digest_n),
         ptr(vis_n), ptr(heur_n), ptr(cam_pos), ptr(order), ptr(counts), ptr(cum),
         ws[0].data_ptr(), ws[0].numel(), ws[1].data_ptr(), ws[1].numel(), ws[2].data_ptr(), ws[2].numel(),
         ptr(image), ptr(alpha), ptr(median) if render_median_depth else None, ptr(tile_ranges),
-        _event_handle(ev_fwd[0] if ev_fwd else None), _event_handle(ev_fwd[1] if ev_fwd else None))
+        _event_handle(ev_fwd[0] if ev_fwd else None), _event_handle(ev_fwd[1] if ev_fwd else None),
+        ptr(tile_counts), ptr(tile_cursor), ptr(tile_totals))
     # K-sized buffers: sized from the previous frame on this device (+25 %), so that the driver can go from the
     # host read of K straight into key emission; if K outgrew them, allocate exactly and run stage B from here
-    v_out, k_out, done = _lib.c_int64(), _lib.c_int64(), _lib.c_int32()
+    v_out, k_out, max_out, done = _lib.c_int64(), _lib.c_int64(), _lib.c_int64(), _lib.c_int32()
     nbytes = _lib.c_size_t()
     dev_key = device.index if device.index is not None else torch.cuda.current_device()
     cap = _k_capacity.get(dev_key, 0)
@@ -252,14 +260,15 @@ class _RenderFunction(torch.autograd.Function):
       _lib.call("gs_sort_pairs_workspace_bytes", cap, 4, nbytes)
       ws_sort = _lib.workspace(nbytes.value, device)
     _lib.call("gs_render_forward_f32", args, cap, ptr(tiles), ptr(o2p), ws_sort.data_ptr() if cap > 0 else None,
-              ws_sort.numel() if cap > 0 else 0, v_out, k_out, done, stream)
+              ws_sort.numel() if cap > 0 else 0, v_out, k_out, max_out, done, stream)
     v, k = int(v_out.value), int(k_out.value)
     if not done.value:
       cap = k
       tiles, o2p = empty((2, k), i32), empty((2, k), i32)
       _lib.call("gs_sort_pairs_workspace_bytes", k, 4, nbytes)
       ws_sort = _lib.workspace(nbytes.value, device)
-      _lib.call("gs_render_stage_b_f32", args, v, k, k, ptr(tiles), ptr(o2p), ws_sort.data_ptr(), ws_sort.numel(), stream)
+      _lib.call("gs_render_stage_b_f32", args, v, k, int(max_out.value), k, ptr(tiles), ptr(o2p), ws_sort.data_ptr(),
+                ws_sort.numel(), stream)
     _k_capacity[dev_key] = max(int(k * 1.25), 1024)
 
     g2d, depths, indexes, features, digest = g2d_n[:v], depths_n[:v], idx_n[:v], feat_n[:v], digest_n[:v]

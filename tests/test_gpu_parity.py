@@ -177,9 +177,13 @@ def _mapper_case(ts, n, size, seed, scale_factor, use_depth16=False, tile_size=1
   o2p_ref, ranges_ref, keys_ref, counts_ref = cbind.map_to_tiles(pts.numpy(), g.depths.numpy(), size, oc,
                                                                  use_depth16=use_depth16, return_keys=True)
   # both the two-level ordering (default) and the reference's own count/scan/emit/48-bit-sort sequence
-  for two_level in (True, False):
-    o2p, ranges, keys, counts = map_to_tiles_full(pts.to(DEV), g.depths.to(DEV), size, to_cfg(ts, oc), use_depth16,
-                                                  two_level=two_level)
+  for two_level in (True, False, "binned"):
+    out = map_to_tiles_full(pts.to(DEV), g.depths.to(DEV), size, to_cfg(ts, oc), use_depth16,
+                            two_level=two_level is True, binned=two_level == "binned")
+    if out is None:   # binned ordering: a tile beyond the shared-memory sort capacity (map_to_tiles falls back)
+      assert two_level == "binned"
+      continue
+    o2p, ranges, keys, counts = out
     assert np.array_equal(counts.cpu().numpy(), counts_ref), "overlap counts differ"
     k = keys.cpu().numpy()
     k = k.astype(np.uint32).astype(np.uint64) if use_depth16 else k.view(np.uint64)
@@ -399,6 +403,55 @@ def test_fused_render_equals_operator_composition(ts):
     assert rel_err(ca.T_camera_world.grad, cb.T_camera_world.grad) < 1e-4
     assert rel_err(ca.projection.grad, cb.projection.grad) < 1e-4
     assert rel_err(a.points.split_score, b.points.split_score) < 1e-5
+
+
+def test_host_drivers_and_orderings_agree(ts):
+  """render_gaussians through (a) the whole-frame C drivers (default), (b) the same stages chained from Python,
+  (c) the drivers with the binned ordering: identical overlap order / image, gradients equal to atomic-order
+  rounding.  Also a fully culled cloud (V = 0) through the drivers."""
+  from taichi_splatting_b200 import renderer
+  from taichi_splatting_b200.mapper import tile_mapper
+  torch.manual_seed(4)
+  size = (312, 200)   # not a multiple of the tile size: blocks fully outside the image exist
+  cam = random_data.fixed_camera(size, yaw_deg=-2.0)
+  g = random_data.random_3d_gaussians(20000, cam, scale_factor=1.5, margin=0.3, sh_degree=3)
+  cfg = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True)
+  R = torch.rand((size[1], size[0], 3), device=DEV)
+
+  def run(fused_host, ordering):
+    saved = renderer._FUSED_HOST, renderer.ORDERING, tile_mapper.ORDERING
+    renderer._FUSED_HOST, renderer.ORDERING, tile_mapper.ORDERING = fused_host, ordering, ordering
+    try:
+      gauss = ts.Gaussians3D(**{k: v.to(DEV).requires_grad_(True) for k, v in vars(g).items()})
+      camera = ts.perspective.CameraParams(projection=cam.projection.to(DEV), T_camera_world=cam.T_camera_world.to(DEV),
+                                           near_plane=cam.near_plane, far_plane=cam.far_plane, image_size=size)
+      out = ts.render_gaussians(gauss, camera, cfg, use_sh=True, render_median_depth=True)
+      (out.image * R).sum().backward()
+      return out, gauss
+    finally:
+      renderer._FUSED_HOST, renderer.ORDERING, tile_mapper.ORDERING = saved
+
+  ref_out, ref_g = run(True, "two_level")
+  for fused_host, ordering in ((False, "two_level"), (True, "binned"), (False, "binned")):
+    out, gauss = run(fused_host, ordering)
+    assert torch.equal(out.points.idx, ref_out.points.idx)
+    assert torch.equal(out.image, ref_out.image), (fused_host, ordering)
+    assert torch.equal(out.median_depth_image, ref_out.median_depth_image)
+    assert rel_err(out.points.visibility, ref_out.points.visibility) < 1e-6
+    assert rel_err(out.points.prune_cost, ref_out.points.prune_cost) < 1e-5
+    for k in ("position", "log_scaling", "rotation", "alpha_logit", "feature"):
+      assert rel_err(getattr(gauss, k).grad, getattr(ref_g, k).grad) < 1e-5, (k, fused_host, ordering)
+
+  # nothing visible: every stage must cope with V = 0 / K = 0
+  far = ts.Gaussians3D(**{k: v.to(DEV).requires_grad_(True) for k, v in vars(g).items()})
+  with torch.no_grad():
+    far.position[:, 2] -= 1.0e4
+  camera = ts.perspective.CameraParams(projection=cam.projection.to(DEV), T_camera_world=cam.T_camera_world.to(DEV),
+                                       near_plane=cam.near_plane, far_plane=cam.far_plane, image_size=size)
+  out = ts.render_gaussians(far, camera, cfg, use_sh=True, render_median_depth=True)
+  out.image.sum().backward()
+  assert out.points.idx.numel() == 0 and float(out.image.detach().abs().max()) == 0.0
+  assert float(far.position.grad.abs().max()) == 0.0 and float(far.feature.grad.abs().max()) == 0.0
 
 
 # --------------------------------------------------------------------------------------- BASELINE.json configs
