@@ -31,4 +31,4 @@ lib.gs_debug_counters(buf, 1)
 v = out.points.idx.shape[0]
 it, hits, live, batches = [int(x) for x in buf]
 print(f"V={v} batches={batches} warp_iterations={it} ({it / v:.2f}/Gaussian) hit_entries={hits} ({hits / v:.2f}/Gaussian) "
-      f"live_lanes={live} ({live / v:.1f}/Gaussian, {100 * live / (32 * max(it, 1)):.1f}% of swept lanes)")
+      f"live_lanes={live} ({live / v:.1f}/Gaussian, {100 * live / (64 * max(it, 1)):.1f}% of the 64 pixels swept per iteration)")

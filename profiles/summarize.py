@@ -1,6 +1,7 @@
 """Turns gpurun_out ncu artefacts into the committed summaries under profiles/.
 
-  python profiles/summarize.py <tag>      (expects gpurun_out/launches_<tag>.csv and gpurun_out/raster_<tag>.ncu-rep)
+  python profiles/summarize.py <tag> [steps]   (expects gpurun_out/launches_<tag>.csv and gpurun_out/raster_<tag>.ncu-rep;
+                                                `steps`: the launch list covers that many steps, keep the last one)
 """
 import csv
 import json
@@ -16,6 +17,10 @@ lines = [f"# ncu summary `{tag}` (cfg3: 1 M Gaussians, 2048x2048, SH deg 3, vis 
 # ---- launch list: per-kernel device time (cold cache, serialised: compare shares) ----
 path = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 rows = list(csv.DictReader([l for l in open(path) if not l.startswith("==")]))
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+if steps > 1:   # warm step only: the first steps pay module loading and cold caches
+  starts = [i for i, r in enumerate(rows) if "project_cull" in r["Kernel Name"]]
+  rows = rows[starts[-1]:]
 agg, tot = {}, 0.0
 for r in rows:
   name = r["Kernel Name"]
@@ -43,7 +48,10 @@ want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occup
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "smsp__warps_eligible.avg.per_cycle_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 traffic = {}
