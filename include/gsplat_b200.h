@@ -364,6 +364,29 @@ typedef struct gs_render_bwd_args {
 
 int gs_render_backward_f32(const gs_render_bwd_args *args, void *stream);
 
+/* ---- N3: sparse, visibility-weighted optimiser step (the step right after backward) ---------------------------
+ * gs_optim_step_f32 replaces the four Taichi kernels of optim/fractional_adam.py:7-86 and
+ * optim/fractional_laprop.py:6-76 (algorithm x scalar | vector second moment) and, when `param` is not NULL, the torch
+ * passes that follow them in optim/fractional.py:131-147,184-199: clip to +-lr*clip (clip <= 0: none), * mask_lr[j],
+ * * point_lr[idx], non-finite -> 0, param[idx] -= step * (1 - exp(-2 w)).  Rows: indexes (M) i64 into the (N, D)
+ * tensors; weight (M); m_state (N,D); v_state (N,D) scalar kinds | (N) vector kinds; total_weight (N) already
+ * advanced by the caller.  grad_scale (M, may be NULL): gradients are divided by (grad_scale[i] + grad_smooth)
+ * first (optim/visibility_aware.py:97-99).  lr_step (M,D) receives the reference kernels' output (before clip /
+ * masks) and may be NULL when param is given.
+ * gs_optim_update_visibility_f32 replaces update_visibility + the step-count update
+ * (optim/visibility_aware.py:37-48,90-91): running_vis[idx] = lerp(beta, vis^4, running_vis[idx]^4)^(1/4),
+ * weight_out[i] = vis / max(running_vis[idx], eps), total_weight[idx] += weight_out[i].                       */
+#define GS_OPTIM_ADAM 0
+#define GS_OPTIM_LAPROP 1
+int gs_optim_step_f32(int32_t algorithm, int32_t vector, int32_t bias_correction, const int64_t *indexes,
+                      const float *weight, const float *grad_scale, double grad_smooth, int64_t m_rows, int32_t d,
+                      float *m_state, float *v_state, const float *total_weight, const float *grad, double lr,
+                      double beta1, double beta2, double eps, float *lr_step, float *param, double clip,
+                      const float *mask_lr, const float *point_lr, void *stream);
+int gs_optim_update_visibility_f32(float *running_vis, const float *visibility, const int64_t *indexes,
+                                   float *total_weight, double beta, double eps, int64_t m_rows, float *weight_out,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif
