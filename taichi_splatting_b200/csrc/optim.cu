@@ -32,42 +32,81 @@ __device__ __forceinline__ float finish_step(float step, float w, int j, int64_t
   return step;
 }
 
-// scalar kinds: one thread per (visible row, component)
-template <bool LAPROP, bool BIAS>
+// scalar kinds: one thread per (visible row, group of 4 components).  The per-row factors (beta^w, bias correction,
+// saturate(w): five transcendental calls) are formed once per thread instead of once per component, and rows whose
+// width is a multiple of 4 move as float4.
+template <bool LAPROP, bool BIAS, bool VEC4>
 __global__ void __launch_bounds__(256)
 optim_scalar_kernel(const int64_t *__restrict__ indexes, const float *__restrict__ weight,
                     const float *__restrict__ grad_scale, float *__restrict__ m_arr, float *__restrict__ v_arr,
                     const float *__restrict__ total_weight, const float *__restrict__ grad, OptimParams p,
                     float *__restrict__ lr_step, float *__restrict__ param, const float *__restrict__ mask_lr,
                     const float *__restrict__ point_lr) {
+  const int groups = (p.d + 3) >> 2;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.m_rows * p.d) return;
-  const int64_t i = t / p.d;
-  const int j = (int)(t - i * p.d);
+  if (t >= p.m_rows * groups) return;
+  const int64_t i = t / groups;
+  const int j0 = (int)(t - i * groups) * 4;
+  const int cnt = min(4, p.d - j0);
   const int64_t idx = indexes[i];
   const float w = weight[i], tw = total_weight[idx];
-  const int64_t e = idx * p.d + j;
-  float g = grad[e];
-  if (grad_scale != nullptr) g = g / (grad_scale[i] + p.grad_smooth);   // visibility_aware.py:97-99
   const float b1w = powf(p.beta1, w), b2w = powf(p.beta2, w);
-  float m, v, step;
-  if (LAPROP) {
-    const float bias1 = BIAS ? 1.0f - powf(p.beta1, tw) : 1.0f, bias2 = BIAS ? 1.0f - powf(p.beta2, tw) : 1.0f;
-    v = lerp_ref(b2w, v_arr[e], g * g);
-    m = lerp_ref(b1w, m_arr[e], g / fmaxf(sqrtf(v / bias2), p.eps));
-    step = m * p.lr / bias1;
-  } else {
-    const float bias = BIAS ? sqrtf(1.0f - powf(p.beta2, tw)) / (1.0f - powf(p.beta1, tw)) : 1.0f;
-    m = lerp_ref(b1w, m_arr[e], g);
-    v = lerp_ref(b2w, v_arr[e], g * g);
-    step = m / fmaxf(sqrtf(v), p.eps) * bias * p.lr;
+  float bias1 = 1.0f, bias2 = 1.0f;   // ADAM: bias1 holds the combined factor
+  if (BIAS) {
+    if (LAPROP) { bias1 = 1.0f - powf(p.beta1, tw); bias2 = 1.0f - powf(p.beta2, tw); }
+    else bias1 = sqrtf(1.0f - powf(p.beta2, tw)) / (1.0f - powf(p.beta1, tw));
   }
-  m_arr[e] = m;
-  v_arr[e] = v;
-  if (lr_step != nullptr) lr_step[t] = step;
-  if (param != nullptr) {
-    step = finish_step(step, w, j, idx, p, mask_lr, point_lr);
-    param[e] -= step * (1.0f - 1.0f / expf(2.0f * w));   // saturate, fractional.py:149-150
+  const float sat = 1.0f - 1.0f / expf(2.0f * w);   // saturate, fractional.py:149-150
+  const float gdiv = grad_scale != nullptr ? grad_scale[i] + p.grad_smooth : 1.0f;   // visibility_aware.py:97-99
+  const int64_t e0 = idx * p.d + j0;
+  float g[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
+  if (VEC4) {
+    const float4 g4 = *reinterpret_cast<const float4 *>(grad + e0), m4 = *reinterpret_cast<const float4 *>(m_arr + e0);
+    const float4 v4 = *reinterpret_cast<const float4 *>(v_arr + e0);
+    g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+    m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+    v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+    if (param != nullptr) {
+      const float4 x4 = *reinterpret_cast<const float4 *>(param + e0);
+      x[0] = x4.x; x[1] = x4.y; x[2] = x4.z; x[3] = x4.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < cnt) {
+        g[c] = grad[e0 + c]; m[c] = m_arr[e0 + c]; v[c] = v_arr[e0 + c];
+        if (param != nullptr) x[c] = param[e0 + c];
+      }
+  }
+  float step[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float gc = g[c];
+    if (grad_scale != nullptr) gc = gc / gdiv;
+    if (LAPROP) {
+      v[c] = lerp_ref(b2w, v[c], gc * gc);
+      m[c] = lerp_ref(b1w, m[c], gc / fmaxf(sqrtf(v[c] / bias2), p.eps));
+      step[c] = m[c] * p.lr / bias1;
+    } else {
+      m[c] = lerp_ref(b1w, m[c], gc);
+      v[c] = lerp_ref(b2w, v[c], gc * gc);
+      step[c] = m[c] / fmaxf(sqrtf(v[c]), p.eps) * bias1 * p.lr;
+    }
+    if (param != nullptr && c < cnt) x[c] -= finish_step(step[c], w, j0 + c, idx, p, mask_lr, point_lr) * sat;
+  }
+  if (VEC4) {
+    *reinterpret_cast<float4 *>(m_arr + e0) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4 *>(v_arr + e0) = make_float4(v[0], v[1], v[2], v[3]);
+    if (param != nullptr) *reinterpret_cast<float4 *>(param + e0) = make_float4(x[0], x[1], x[2], x[3]);
+    if (lr_step != nullptr) *reinterpret_cast<float4 *>(lr_step + i * p.d + j0) = make_float4(step[0], step[1], step[2], step[3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < cnt) {
+        m_arr[e0 + c] = m[c]; v_arr[e0 + c] = v[c];
+        if (param != nullptr) param[e0 + c] = x[c];
+        if (lr_step != nullptr) lr_step[i * p.d + j0 + c] = step[c];
+      }
   }
 }
 
@@ -154,19 +193,25 @@ extern "C" int gs_optim_step_f32(int32_t algorithm, int32_t vector, int32_t bias
   OptimParams p;
   p.lr = (float)lr; p.beta1 = (float)beta1; p.beta2 = (float)beta2; p.eps = (float)eps; p.clip = (float)clip;
   p.grad_smooth = (float)grad_smooth; p.d = d; p.m_rows = m_rows;
-  const int64_t threads = vector ? m_rows : m_rows * d;
+  const int64_t threads = vector ? m_rows : m_rows * ((d + 3) / 4);
   const unsigned grid = (unsigned)ceil_div(threads, 256);
-#define GS_OPT(KERNEL, LAPROP_, BIAS_)                                                                             \
-  KERNEL<LAPROP_, BIAS_><<<grid, 256, 0, stream>>>(indexes, weight, grad_scale, m_state, v_state, total_weight,   \
-                                                   grad, p, lr_step, param, mask_lr, point_lr)
+  auto aligned16 = [](const void *q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec4 = !vector && d % 4 == 0 && aligned16(m_state) && aligned16(v_state) && aligned16(grad) &&
+                    aligned16(param) && aligned16(lr_step);
+#define GS_OPT(KERNEL, ...)                                                                                        \
+  KERNEL<__VA_ARGS__><<<grid, 256, 0, stream>>>(indexes, weight, grad_scale, m_state, v_state, total_weight, grad, \
+                                                p, lr_step, param, mask_lr, point_lr)
+#define GS_OPT_SCALAR(LAPROP_, BIAS_) \
+  do { if (vec4) GS_OPT(optim_scalar_kernel, LAPROP_, BIAS_, true); else GS_OPT(optim_scalar_kernel, LAPROP_, BIAS_, false); } while (0)
   const bool laprop = algorithm == GS_OPTIM_LAPROP, bias = bias_correction != 0;
   if (vector) {
     if (laprop) { if (bias) GS_OPT(optim_vector_kernel, true, true); else GS_OPT(optim_vector_kernel, true, false); }
     else        { if (bias) GS_OPT(optim_vector_kernel, false, true); else GS_OPT(optim_vector_kernel, false, false); }
   } else {
-    if (laprop) { if (bias) GS_OPT(optim_scalar_kernel, true, true); else GS_OPT(optim_scalar_kernel, true, false); }
-    else        { if (bias) GS_OPT(optim_scalar_kernel, false, true); else GS_OPT(optim_scalar_kernel, false, false); }
+    if (laprop) { if (bias) GS_OPT_SCALAR(true, true); else GS_OPT_SCALAR(true, false); }
+    else        { if (bias) GS_OPT_SCALAR(false, true); else GS_OPT_SCALAR(false, false); }
   }
+#undef GS_OPT_SCALAR
 #undef GS_OPT
   GS_LAUNCH_CHECK();
   return GS_OK;
