@@ -454,6 +454,44 @@ def test_host_drivers_and_orderings_agree(ts):
   assert float(far.position.grad.abs().max()) == 0.0 and float(far.feature.grad.abs().max()) == 0.0
 
 
+def test_binned_ordering_falls_back_on_crowded_tile(ts):
+  """More overlaps in one tile than the shared-memory sort takes: the binned ordering must hand over to the two-level
+  one (mapper operator, and stage B of the whole-frame driver) with the identical result."""
+  from taichi_splatting_b200 import _lib, renderer
+  from taichi_splatting_b200.mapper import tile_mapper
+  cap = _lib.load().gs_tile_bin_max_per_tile()
+  torch.manual_seed(2)
+  size = (96, 64)
+  cam = random_data.fixed_camera(size)
+  g = random_data.random_3d_gaussians(cap + 1500, cam, scale_factor=0.5)
+  with torch.no_grad():   # pile every Gaussian onto the image centre: one tile holds all of them
+    centre = g.position.mean(dim=0, keepdim=True)
+    g.position.copy_(centre + 0.002 * (g.position - centre))
+
+  def run(ordering):
+    saved = renderer.ORDERING, tile_mapper.ORDERING
+    renderer.ORDERING = tile_mapper.ORDERING = ordering
+    try:
+      gauss = ts.Gaussians3D(**{k: v.to(DEV).requires_grad_(True) for k, v in vars(g).items()})
+      camera = ts.perspective.CameraParams(projection=cam.projection.to(DEV), T_camera_world=cam.T_camera_world.to(DEV),
+                                           near_plane=cam.near_plane, far_plane=cam.far_plane, image_size=size)
+      out = ts.render_gaussians(gauss, camera, ts.RasterConfig())
+      out.image.sum().backward()
+      ndc = ts.rendering.ndc_depth(out.points.depths.detach(), camera.near_plane, camera.far_plane)
+      o2p, ranges = ts.map_to_tiles(out.points.gaussians2d.detach(), ndc, size, ts.RasterConfig())
+      return out, gauss, o2p, ranges
+    finally:
+      renderer.ORDERING, tile_mapper.ORDERING = saved
+
+  a, ga, o2p_a, ranges_a = run("two_level")
+  b, gb, o2p_b, ranges_b = run("binned")
+  r = ranges_a.view(-1, 2)
+  assert int((r[:, 1] - r[:, 0]).max()) > cap, "scene does not exceed the shared-memory sort capacity"
+  assert torch.equal(o2p_a, o2p_b) and torch.equal(ranges_a, ranges_b)
+  assert torch.equal(a.image, b.image)
+  assert rel_err(ga.position.grad, gb.position.grad) < 1e-5
+
+
 # --------------------------------------------------------------------------------------- BASELINE.json configs
 def test_cfg1_fit_image_shape(ts):
   """configs[0]: 2000 2D Gaussians at 256x256 (examples/fit_image_gaussians.py:264 inputs), forward + backward."""
