@@ -364,6 +364,13 @@ typedef struct gs_render_bwd_args {
 
 int gs_render_backward_f32(const gs_render_bwd_args *args, void *stream);
 
+/* ---- N4: Morton ordering of a point cloud (misc/morton_sort.py:95-130) ------------------------------------------
+ * gs_morton_codes64 replaces code_points64_kernel: codes[i] = 63-bit Morton code of the grid cell of points[i]
+ * (cell = clamp((p - lower) / inc, 0, grid_size - 1) per axis, 21 bits each, x lowest), ids[i] = i.  lower / inc are
+ * HOST arrays of 3 floats.  Follow with gs_sort_pairs(codes, ids, 8-byte keys, bits [0, 63)) = cuda_lib.radix_argsort. */
+int gs_morton_codes64(const float *points, int64_t n, const float *lower_host, const float *inc_host,
+                      int64_t grid_size, uint64_t *codes, int32_t *ids, void *stream);
+
 /* ---- N3: sparse, visibility-weighted optimiser step (the step right after backward) ---------------------------
  * gs_optim_step_f32 replaces the four Taichi kernels of optim/fractional_adam.py:7-86 and
  * optim/fractional_laprop.py:6-76 (algorithm x scalar | vector second moment) and, when `param` is not NULL, the torch

@@ -118,6 +118,7 @@ SIGNATURES = {
     "gs_render_forward_f32": ([POINTER(RenderArgsC), I64, P, P, P, SZ, POINTER(I64), POINTER(I64), POINTER(I64),
                                POINTER(I32), P], c_int32),
     "gs_render_backward_f32": ([POINTER(RenderBwdArgsC), P], c_int32),
+    "gs_morton_codes64": ([P, I64, POINTER(ctypes.c_float), POINTER(ctypes.c_float), I64, P, P, P], c_int32),
     "gs_optim_step_f32": ([I32, I32, I32, P, P, P, D, I64, I32, P, P, P, P, D, D, D, D, P, P, D, P, P, P], c_int32),
     "gs_optim_update_visibility_f32": ([P, P, P, P, D, D, I64, P, P], c_int32),
 }
@@ -164,7 +165,7 @@ OWN_KERNELS = {
     # whole-frame drivers: cull, camera position, write, SH, digest, depth key, count, scan tail | emit, ranges, raster |
     # raster backward, projection backward, SH backward
     "gs_render_stage_a_f32": 8, "gs_render_stage_b_f32": 3, "gs_render_backward_f32": 3, "gs_render_forward_f32": 8,
-    "gs_optim_step_f32": 1, "gs_optim_update_visibility_f32": 1,
+    "gs_optim_step_f32": 1, "gs_optim_update_visibility_f32": 1, "gs_morton_codes64": 1,
 }
 
 

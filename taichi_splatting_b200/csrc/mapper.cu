@@ -535,3 +535,44 @@ extern "C" int gs_tile_bin_sort(const uint64_t *keys, const int32_t *tile_ranges
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
+
+// ---- N4: Morton ordering of a point cloud (misc/morton_sort.py:13-130) --------------------------------------------
+namespace gs {
+__device__ __forceinline__ uint64_t spread_bits64(uint64_t x) {   // morton_sort.py:23-31
+  x &= 0x1fffffull;
+  x = (x | (x << 32)) & 0x1f00000000ffffull;
+  x = (x | (x << 16)) & 0x1f0000ff0000ffull;
+  x = (x | (x << 8)) & 0x100f00f00f00f00full;
+  x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void __launch_bounds__(256)
+morton_codes64_kernel(const float *__restrict__ points, int64_t n, float lx, float ly, float lz, float ix, float iy,
+                      float iz, float max_cell, uint64_t *__restrict__ codes, int32_t *__restrict__ ids) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // Grid.grid_cell (morton_sort.py:49-53): cast(clamp((p - lower) / inc, 0, size - 1), u32)
+  const float vx = __fdiv_rn(__fsub_rn(points[3 * i + 0], lx), ix);
+  const float vy = __fdiv_rn(__fsub_rn(points[3 * i + 1], ly), iy);
+  const float vz = __fdiv_rn(__fsub_rn(points[3 * i + 2], lz), iz);
+  const uint64_t cx = (uint64_t)fminf(fmaxf(vx, 0.0f), max_cell), cy = (uint64_t)fminf(fmaxf(vy, 0.0f), max_cell);
+  const uint64_t cz = (uint64_t)fminf(fmaxf(vz, 0.0f), max_cell);
+  codes[i] = spread_bits64(cx) | (spread_bits64(cy) << 1) | (spread_bits64(cz) << 2);
+  ids[i] = (int32_t)i;
+}
+}  // namespace gs
+
+extern "C" int gs_morton_codes64(const float *points, int64_t n, const float *lower_host, const float *inc_host,
+                                 int64_t grid_size, uint64_t *codes, int32_t *ids, void *stream) {
+  GS_CHECK_ARG(n >= 0 && n < (int64_t(1) << 31), "morton_codes64: n out of range");
+  GS_CHECK_ARG(grid_size >= 1 && grid_size <= (int64_t(1) << 21), "morton_codes64: grid size must be in [1, 2^21]");
+  GS_CHECK_ARG(lower_host != nullptr && inc_host != nullptr, "morton_codes64: lower / inc is NULL");
+  if (n == 0) return GS_OK;
+  gs::morton_codes64_kernel<<<(unsigned)gs::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      points, n, lower_host[0], lower_host[1], lower_host[2], inc_host[0], inc_host[1], inc_host[2],
+      (float)(grid_size - 1), codes, ids);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}

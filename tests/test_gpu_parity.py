@@ -657,3 +657,22 @@ def test_fit_image_example_converges(ts):
   first = fit_image_gaussians.main(["--n", "2000", "--size", "256,256", "--iters", "1"])
   final = fit_image_gaussians.main(["--n", "2000", "--size", "256,256", "--iters", "150"])
   assert final > first + 3.0, (first, final)
+
+
+# --------------------------------------------------------------------------------------- N4: Morton ordering
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,res", [(1, 0.1), (1000, 0.01), (200000, 0.003)])
+def test_morton_sort_bit_exact(ts, n, res):
+  """misc/morton_sort.py:119-130: codes and the stable argsort, bit for bit against the numpy oracle."""
+  from oracle import morton
+  from taichi_splatting_b200.misc import morton_sort
+  torch.manual_seed(n)
+  pts = torch.randn(n, 3) * 3.0
+  pts[::7] = pts[0].clone()              # repeated points: ties keep their input order
+  codes, ids = morton_sort.morton_codes(pts.to(DEV), res)
+  ref = morton.morton_codes64(pts.numpy(), res)
+  assert np.array_equal(codes.cpu().numpy().view(np.uint64), ref)
+  assert np.array_equal(ids.cpu().numpy(), np.arange(n, dtype=np.int32))
+  order = morton_sort.argsort(pts.to(DEV), res)
+  assert np.array_equal(order.cpu().numpy(), morton.argsort(pts.numpy(), res))
+  assert torch.equal(morton_sort.sort(pts.to(DEV), res).cpu(), pts[order.cpu().long()])

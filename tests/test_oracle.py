@@ -218,3 +218,17 @@ def test_tile_mapper_edge_cases():
   o32, r32 = cbind.map_to_tiles(p, g.depths.numpy(), (64, 48), cfg)
   o16, r16 = cbind.map_to_tiles(p, g.depths.numpy(), (64, 48), cfg, use_depth16=True)
   assert np.array_equal(r32, r16) and sorted(o32.tolist()) == sorted(o16.tolist())
+
+
+def test_morton_oracle_bit_interleaving():
+  """N4: the spreading trick of the Morton oracle against a bit-by-bit interleave; codes sort cells in Z-order."""
+  from oracle import morton
+  rng = np.random.default_rng(0)
+  cells = rng.integers(0, 2**21, size=(200, 3), dtype=np.uint64)
+  fast = morton.spread_bits64(cells[:, 0]) | (morton.spread_bits64(cells[:, 1]) << np.uint64(1)) | (morton.spread_bits64(cells[:, 2]) << np.uint64(2))
+  slow = np.array([morton.interleave_slow(int(a), int(b), int(c)) for a, b, c in cells], dtype=np.uint64)
+  assert np.array_equal(fast, slow)
+  pts = rng.uniform(-5, 5, size=(1000, 3)).astype(np.float32)
+  order = morton.argsort(pts, 0.01)
+  codes = morton.morton_codes64(pts, 0.01)
+  assert np.all(np.diff(codes[order].astype(np.float64)) >= 0) and sorted(order.tolist()) == list(range(1000))
