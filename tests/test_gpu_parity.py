@@ -676,3 +676,43 @@ def test_morton_sort_bit_exact(ts, n, res):
   order = morton_sort.argsort(pts.to(DEV), res)
   assert np.array_equal(order.cpu().numpy(), morton.argsort(pts.numpy(), res))
   assert torch.equal(morton_sort.sort(pts.to(DEV), res).cpu(), pts[order.cpu().long()])
+
+
+# --------------------------------------------------------------------------------------- R4 / R6 against the reference's own CUDA code
+@pytest.mark.gpu
+def test_scan_and_sort_match_reference_cuda_lib(ts):
+  """oracle/_ref/ref_cuda_lib.so is the reference's own cuda_lib (full_cumsum.cu, radix_sort_pairs.cu) compiled for
+  sm_100a by oracle/build_ref.py: gs_tile_scan and gs_sort_pairs must reproduce it bit for bit."""
+  from oracle import build_ref
+  from taichi_splatting_b200 import _lib
+  ref = build_ref.load_module()
+  if ref is None:
+    pytest.skip("oracle/_ref/ref_cuda_lib.so not built (needs /root/reference at build time)")
+  torch.manual_seed(0)
+  call, ptr = _lib.call, _lib.ptr
+  stream = _lib.stream_ptr(torch.device(DEV))
+  nbytes = _lib.c_size_t()
+  for v in (1, 1000, 1_000_003):
+    counts = torch.randint(0, 9, (v,), dtype=torch.int32, device=DEV)
+    out = counts.new_empty((v + 1,))
+    total_ref = ref.full_cumsum(counts, out)          # cuda_lib/__init__.py:16-25
+    cum = torch.empty((v + 1,), dtype=torch.int32, device=DEV)
+    call("gs_tile_scan_workspace_bytes", v, nbytes)
+    ws = _lib.workspace(nbytes.value, torch.device(DEV))
+    word = _lib.host_word(torch.device(DEV))
+    call("gs_tile_scan", ptr(counts), v, ptr(cum), ws.data_ptr(), ws.numel(), word.data_ptr(), stream)
+    total = _lib.read_host_word(word, torch.device(DEV))
+    # full_cumsum.cu:16-47: exclusive scan in out[0:v], total in out[v] and on the host
+    assert total == int(total_ref) == int(counts.sum())
+    assert torch.equal(cum, out)
+  for k, bits in ((5, 48), (100_000, 48), (3_000_017, 46)):
+    tiles = torch.randint(0, 1 << (bits - 32), (k,), dtype=torch.int64, device=DEV)
+    keys = (tiles << 32) | torch.randint(0, 1 << 31, (k,), dtype=torch.int64, device=DEV)
+    keys[::5] = keys[0].clone()                        # duplicates: stability decides
+    values = torch.arange(k, dtype=torch.int32, device=DEV)
+    keys_ref, values_ref = ref.radix_sort_pairs(keys, values, 0, bits)     # mapper/tile_mapper.py:156
+    keys_out, values_out = torch.empty_like(keys), torch.empty_like(values)
+    call("gs_sort_pairs_workspace_bytes", k, 8, nbytes)
+    ws = _lib.workspace(nbytes.value, torch.device(DEV))
+    call("gs_sort_pairs", ptr(keys), ptr(values), ptr(keys_out), ptr(values_out), k, 8, 0, bits, ws.data_ptr(), ws.numel(), stream)
+    assert torch.equal(keys_out, keys_ref) and torch.equal(values_out, values_ref)
