@@ -41,7 +41,6 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kBatch = kThreads;   // splats staged per round: thread j stages and finally flushes splat j
 constexpr int kChunk = 8;          // splats per phase-1 / phase-2 round
 constexpr int kRow = 33;           // panel row stride in float4 (32 lanes + 1 pad: conflict-free transposed reads)
-constexpr int kRowG = 9;           // gpix row stride in float4 (8 pixels + 1 pad)
 constexpr int kAcc = 13;           // accumulator stride: 6 moments, 4 features, 2 heuristics, 1 pad (odd)
 constexpr float kExpScale = 0.84932180028801904f;
 
@@ -62,7 +61,6 @@ struct Smem {
   float4 f[kBatch + 1];
   float4 c[kBatch];                // mean - tile centre, 1/sigma.x, 1/sigma.y  (read by the flush only)
   float acc[kBatch * kAcc];
-  float4 gpix[kWarps][8 * kRowG];  // dL/dimage of each warp's 64 pixels, rows padded (conflict-free phase-2 reads)
   float4 panel0[kWarps][kChunk * kRow];  // per-warp [splat][lane] scratch: {S, D, sum G^2, sum |G dpdf/dmean|}
   float4 panel1[kWarps][kChunk * kRow];  //                                 {sum weight dL/dimage[c]}
   // byte offsets (16 j) of the staged records a warp must visit; entry k lives at index k + 3, so that the eight
@@ -111,7 +109,6 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
         for (int c = 0; c < F; ++c) { g[p][c] = gi[c]; rneg[p] = fmaf(-img[c], g[p][c], rneg[p]); }
         trans[p] = 1.0f;
       }
-      sm.gpix[warp][((lane >> 3) + 4 * p) * kRowG + (lane & 7)] = make_float4(g[p][0], g[p][1], g[p][2], g[p][3]);
     }
 #pragma unroll
     for (int c = 0; c < F; ++c) gpix2[c] = pk(g[0][c], g[1][c]);
@@ -407,7 +404,10 @@ int launch_bwd_transpose(const float4 *digest, const int32_t *ranges, const int3
                          const float *image, const float *grad_image, const RasterParams<float> &P, int tiles,
                          float *grad_points, float *grad_features, float *heuristic, cudaStream_t stream) {
   const bool gp = grad_points != nullptr, gf = grad_features != nullptr, he = P.heur && heuristic != nullptr;
-  const size_t smem = sizeof(bwdt::Smem);
+#ifndef GS_BWDT_EXTRA_SMEM
+#define GS_BWDT_EXTRA_SMEM 0   // profiling aid: extra dynamic shared memory per CTA lowers the residency
+#endif
+  const size_t smem = sizeof(bwdt::Smem) + GS_BWDT_EXTRA_SMEM;
 #define GS_BWDT(GP_, GF_, HE_)                                                                                  \
   do {                                                                                                          \
     auto kern = bwdt::raster_bwd_t_kernel<F, GP_, GF_, HE_>;                                                    \
