@@ -1,11 +1,12 @@
 """2D image fitting with Gaussians: the reference's only end-to-end training entry, reduced to the render path.
 
 Reference: taichi_splatting/examples/fit_image_gaussians.py:89-147,234-358 (BASELINE config 1: 256x256, n=2000).
-The reference drives its own visibility-aware LaProp optimiser and split/prune densification (optim/, out of scope
-here); this version keeps the same forward / loss / backward through `rasterize` and uses
-torch.optim.Adam so that the loop exercises exactly the hot path this package replaces.
+Same forward / loss / backward through `rasterize` as the reference, and by default the reference's optimiser setup
+(:267-281): VisibilityAwareLaProp over the visible points with a `local_vector` position group stepped in each
+Gaussian's own basis, through `taichi_splatting_b200.optim`.  `--opt adam` uses torch.optim.Adam instead.  The
+reference's split / prune densification (host-side torch, :190-230) is not part of this version.
 
-  python -m taichi_splatting_b200.examples.fit_image_gaussians [--image path.png] [--n 2000] [--iters 200]
+  python -m taichi_splatting_b200.examples.fit_image_gaussians [--image path.png] [--n 2000] [--iters 200] [--opt laprop]
 """
 import argparse
 import math
@@ -14,7 +15,8 @@ import torch
 
 from ..benchmarks.scenes import random_2d_gaussians
 from ..data_types import RasterConfig
-from ..misc.renderer2d import project_gaussians2d
+from ..misc.renderer2d import point_basis, project_gaussians2d
+from ..optim import SparseAdam, VisibilityAwareLaProp
 from ..rasterizer import rasterize
 
 
@@ -35,6 +37,8 @@ def main(argv=None):
   ap.add_argument("--iters", type=int, default=200)
   ap.add_argument("--lr", type=float, default=0.02)
   ap.add_argument("--tile_size", type=int, default=16)
+  ap.add_argument("--opt", type=str, default="laprop", choices=["laprop", "sparse_adam", "adam"],
+                  help="laprop: VisibilityAwareLaProp (the reference's choice); sparse_adam: SparseAdam; adam: torch Adam")
   ap.add_argument("--device", type=str, default="cuda:0")
   args = ap.parse_args(argv)
   device = torch.device(args.device)
@@ -52,7 +56,18 @@ def main(argv=None):
   params = [g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature]
   for p in params:
     p.requires_grad_(True)
-  opt = torch.optim.Adam([{"params": [g.position], "lr": args.lr * 10}, {"params": params[1:], "lr": args.lr}])
+  if args.opt == "adam":
+    opt = torch.optim.Adam([{"params": [g.position], "lr": args.lr * 10}, {"params": params[1:], "lr": args.lr}])
+  else:   # parameter groups of the reference (:267-274)
+    groups = [dict(params=[g.position], name="position", lr=0.5, type="local_vector"),
+              dict(params=[g.log_scaling], name="log_scaling", lr=0.1, type="scalar"),
+              dict(params=[g.rotation], name="rotation", lr=1.0, type="scalar"),
+              dict(params=[g.alpha_logit], name="alpha_logit", lr=0.1, type="scalar"),
+              dict(params=[g.feature], name="feature", lr=0.025, type="vector")]
+    if args.opt == "laprop":
+      opt = VisibilityAwareLaProp(groups, vis_smooth=0.1, vis_beta=0.8, betas=(0.9, 0.9), eps=1e-16, bias_correction=True)
+    else:
+      opt = SparseAdam(groups, betas=(0.9, 0.95), eps=1e-16, bias_correction=True)
   config = RasterConfig(tile_size=args.tile_size, compute_visibility=True)
 
   for it in range(args.iters):
@@ -60,7 +75,16 @@ def main(argv=None):
     raster = rasterize(project_gaussians2d(g), torch.clamp(g.depths, 0, 1), g.feature, (w, h), config)
     loss = torch.nn.functional.mse_loss(raster.image, ref_image)
     loss.backward()
-    opt.step()
+    if args.opt == "adam":
+      opt.step()
+    else:   # step the visible points only (:125-136)
+      visible = (raster.visibility > 1e-8).nonzero().squeeze(1)
+      with torch.no_grad():
+        basis = point_basis(g[visible])
+      if args.opt == "laprop":
+        opt.step(indexes=visible, visibility=raster.visibility[visible], basis=basis)
+      else:
+        opt.step(indexes=visible, basis=basis)
     if it % 50 == 0 or it == args.iters - 1:
       visible = int((raster.visibility > 0).sum())
       print(f"iter {it:5d}  psnr {psnr(raster.image.detach(), ref_image):6.2f} dB  visible {visible}/{args.n}")

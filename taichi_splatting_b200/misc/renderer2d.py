@@ -16,6 +16,15 @@ def project_gaussians2d(points: Gaussians2D) -> torch.Tensor:
   return torch.cat([points.position, v1, points.scaling, alpha.reshape(-1, 1)], dim=-1)
 
 
+def point_basis(points: Gaussians2D, eps: float = 1e-4) -> torch.Tensor:
+  """(N, 2, 2) basis of each Gaussian: its two axes as columns, scaled by sigma (reference :37-43).  The optimisers'
+  `local_vector` groups step positions in this basis."""
+  scale = torch.clamp_min(points.scaling, eps)
+  v1 = points.rotation / torch.norm(points.rotation, dim=1, keepdim=True)
+  v2 = torch.stack([-v1[..., 1], v1[..., 0]], dim=-1)
+  return torch.stack([v1, v2], dim=2) * scale.unsqueeze(-2)
+
+
 def render_gaussians(gaussians: Gaussians2D, image_size: Tuple[Integral, Integral],
                      raster_config: RasterConfig = RasterConfig()):
   gaussians2d = project_gaussians2d(gaussians)

@@ -654,9 +654,10 @@ def test_fit_image_example_converges(ts):
   forward + backward."""
   from taichi_splatting_b200.examples import fit_image_gaussians
   torch.manual_seed(0)
-  first = fit_image_gaussians.main(["--n", "2000", "--size", "256,256", "--iters", "1"])
-  final = fit_image_gaussians.main(["--n", "2000", "--size", "256,256", "--iters", "150"])
-  assert final > first + 3.0, (first, final)
+  for opt in ("laprop", "sparse_adam", "adam"):   # the reference's optimiser setup, its commented-out one, torch Adam
+    first = fit_image_gaussians.main(["--n", "2000", "--size", "256,256", "--iters", "1", "--opt", opt])
+    final = fit_image_gaussians.main(["--n", "2000", "--size", "256,256", "--iters", "150", "--opt", opt])
+    assert final > first + 3.0, (opt, first, final)
 
 
 # --------------------------------------------------------------------------------------- N4: Morton ordering
