@@ -234,18 +234,6 @@ def stream_ptr(device) -> int:
   return torch.cuda.current_stream(device).cuda_stream
 
 
-_side_streams = {}
-
-
-def side_stream(device) -> "torch.cuda.Stream":
-  """One auxiliary stream per device: the renderer runs work that is independent of the tile-mapping chain
-  (SH evaluation, raster digest, zero fills, SH backward) on it, fenced with events against the caller's stream."""
-  key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-  if key not in _side_streams:
-    _side_streams[key] = torch.cuda.Stream(device=device)
-  return _side_streams[key]
-
-
 def workspace(nbytes: int, device) -> torch.Tensor:
   return torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=device)
 

@@ -52,10 +52,6 @@ def _next_event_pair(which):
   return pairs.pop(0) if pairs else None
 
 
-# GS_OVERLAP_STREAMS=0 keeps every launch on the caller's stream (A/B switch for profiling and debugging)
-_OVERLAP_STREAMS = os.environ.get("GS_OVERLAP_STREAMS", "1") != "0"
-
-
 class _RenderFunction(torch.autograd.Function):
   """The whole render path as ONE autograd node.
 
@@ -107,36 +103,19 @@ class _RenderFunction(torch.autograd.Function):
     call(f"gs_project_write_{sfx}", *pin, n, w, h, near, far, blur, margin, ws_proj.data_ptr(), ptr(g2d), ptr(depths),
          ptr(indexes), ptr(ndc), stream)
 
-    # Everything below that does not feed the tile mapper (SH evaluation, zero fills of the accumulated outputs,
-    # the raster digest) is enqueued on an auxiliary stream: the mapper chain is a string of short, latency-bound
-    # kernels with two host reads in it, the SH evaluation is HBM-bound, so they overlap almost perfectly.  All
-    # buffers are allocated on the caller's stream; the two streams are fenced with events.
-    main = torch.cuda.current_stream(device)
-    side = _lib.side_stream(device)
-    overlap = _OVERLAP_STREAMS and side != main
-    aux, aux_ptr = (side, side.cuda_stream) if overlap else (main, stream)
-    if overlap:
-      fence = torch.cuda.Event()
-      fence.record(main)
-      side.wait_event(fence)
-
     # ---- features: SH at the visible set, or a plain gather ----
     if use_sh:
       degree = check_sh_degree(feature_c)
       channels = feature_c.shape[1]
       features = torch.empty((v, channels), dtype=dtype, device=device)
       call(f"gs_sh_fwd_{sfx}", ptr(feature_c), pin[0], ptr(indexes), ptr(cam_pos), v, channels, degree, ptr(features),
-           aux_ptr, on=aux)
+           stream)
     else:
       assert feature_c.ndim == 2, f"Features must be (N, C) if use_sh=False, got {feature_c.shape}"
       features = feature_c[indexes]
-      if overlap:   # produced on the caller's stream
-        fence2 = torch.cuda.Event()
-        fence2.record(main)
-        side.wait_event(fence2)
     F = features.shape[1]
 
-    # accumulated outputs (zeroed) and the raster digest, still on the auxiliary stream
+    # accumulated outputs (zeroed) and the raster digest
     image = torch.empty((h, w, F), dtype=dtype, device=device)
     alpha = torch.empty((h, w), dtype=dtype, device=device)
     heuristic = torch.empty((v, 2) if config.compute_point_heuristic else (0, 2), dtype=dtype, device=device)
@@ -145,17 +124,13 @@ class _RenderFunction(torch.autograd.Function):
     digest = torch.empty((0, 16), dtype=torch.float32, device=device)
     fused_median = render_median_depth and fused_median_supported(config, F, dtype)
     use_digest = tuned_supported(config, F, dtype) and (fused_median or not render_median_depth)
-    with torch.cuda.stream(aux):
-      heuristic.zero_()
-      visibility.zero_()
+    heuristic.zero_()
+    visibility.zero_()
     if use_digest:   # raster records, written once and gathered by the forward and the backward kernel
       digest = torch.empty((v, 16), dtype=torch.float32, device=device)
       if v > 0:
         call("gs_raster_digest_f32", ptr(g2d), ptr(features), ptr(depths) if fused_median else None, v, F,
-             _lib.raster_config_c(config), ptr(digest), aux_ptr, on=aux)
-    if overlap:
-      aux_done = torch.cuda.Event()
-      aux_done.record(side)
+             _lib.raster_config_c(config), ptr(digest), stream)
 
     # ---- tile mapper (fp32 only, like the reference): two-level ordering, one host read (K) ----
     g32 = g2d if dtype == torch.float32 else g2d.float()
@@ -169,8 +144,6 @@ class _RenderFunction(torch.autograd.Function):
     ranges = tile_ranges.view(-1, 2)
 
     # ---- rasteriser (+ fused median depth) ----
-    if overlap:
-      main.wait_event(aux_done)
     vis_ptr = ptr(visibility) if config.compute_visibility else None
     cfg = _lib.raster_config_c(config)
     if use_digest:
@@ -333,31 +306,16 @@ class _RenderFunction(torch.autograd.Function):
     if exchange is not None and exchange.world <= 1:
       exchange = None
 
-    # The raster backward is bound by shared memory, not HBM: the zero fills of the dense parameter gradients run
-    # beside it on the auxiliary stream, and afterwards the SH backward (HBM-bound) beside the projection backward
-    # (latency-bound).  Buffers are allocated on the caller's stream; streams are fenced with events.
-    main = torch.cuda.current_stream(device)
-    side = _lib.side_stream(device)
-    overlap = _OVERLAP_STREAMS and side != main and exchange is None
-    aux, aux_ptr = (side, side.cuda_stream) if overlap else (main, stream)
     grads = [torch.empty_like(t) if need[i] else None
              for t, i in ((position, 0), (log_scaling, 1), (rotation, 2), (alpha_logit, 3), (T_camera_world, 5), (projection, 6))]
     sh_direct = need[4] and exchange is None
     all_rows_written = use_sh and v == feature.shape[0]
     d_feature = torch.empty_like(feature) if sh_direct else None
-    if overlap:
-      fence = torch.cuda.Event()
-      fence.record(main)
-      side.wait_event(fence)
-    with torch.cuda.stream(aux):
-      for t in grads:
-        if t is not None:
-          t.zero_()
-      if sh_direct and not all_rows_written:
-        d_feature.zero_()
-    if overlap:
-      fills_done = torch.cuda.Event()
-      fills_done.record(side)
+    for t in grads:
+      if t is not None:
+        t.zero_()
+    if sh_direct and not all_rows_written:
+      d_feature.zero_()
 
     # ---- rasteriser backward: gradients of the packed 2D Gaussians and per-point features ----
     grad_g = d_g2d.clone() if d_g2d is not None else torch.zeros_like(g2d)
@@ -374,24 +332,17 @@ class _RenderFunction(torch.autograd.Function):
              ptr(d_image.contiguous()), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
              *out_ptrs, stream)
 
-    # ---- features: SH backward on the auxiliary stream; view-parallel runs launch the exchange of the SH-gradient
-    # factors instead, so that the all-gather overlaps the projection backward ----
+    # ---- features: SH backward; view-parallel runs launch the exchange of the SH-gradient factors instead, so that
+    # the all-gather overlaps the projection backward ----
     pending = exchange.start(feature, indexes, features, grad_f, cam_pos) if exchange is not None else None
     if sh_direct and v > 0:
-      if overlap:
-        raster_done = torch.cuda.Event()
-        raster_done.record(main)
-        side.wait_event(raster_done)
       if use_sh:
         call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), ptr(features), v,
-             feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, aux_ptr, on=aux)
+             feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, stream)
       else:
-        with torch.cuda.stream(aux):
-          d_feature.index_copy_(0, indexes, grad_f)
+        d_feature.index_copy_(0, indexes, grad_f)
 
     # ---- projection backward ----
-    if overlap:
-      main.wait_event(fills_done)
     if need_geom and v > 0:
       dd = d_depths.contiguous() if d_depths is not None else torch.zeros((v, 1), dtype=dtype, device=device)
       call(f"gs_project_bwd_{sfx}", ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(T_camera_world),
@@ -399,10 +350,6 @@ class _RenderFunction(torch.autograd.Function):
 
     if exchange is not None:
       d_feature = exchange.finish(pending, feature, position, check_sh_degree(feature))
-    if overlap:
-      sh_done = torch.cuda.Event()
-      sh_done.record(side)
-      main.wait_event(sh_done)
     return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)
 
 
