@@ -7,6 +7,8 @@
 // launches for ~0.2-0.3 ms per frame (torch.profiler timeline, profiles/).  From C a launch costs 2-3 us, and
 // the work that does not feed the tile mapper -- SH evaluation, raster digest, zero fills, SH backward -- is put on
 // an auxiliary stream so that it really runs beside the latency-bound mapper chain / raster backward.
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 
@@ -15,7 +17,7 @@
 namespace gs {
 
 struct DeviceAux {
-  cudaStream_t side = nullptr;
+  cudaStream_t side_stream = nullptr;
   cudaEvent_t fence = nullptr, side_done = nullptr, raster_done = nullptr, fills_done = nullptr, bwd_join = nullptr;
   int32_t *host_words = nullptr;   // pinned: [0] V, [1] K, [2] largest tile population (binned ordering), [4] K (fallback)
 };
@@ -27,8 +29,8 @@ static DeviceAux *device_aux() {
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
   DeviceAux &a = table[dev];
-  if (a.side == nullptr) {
-    if (cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  if (a.side_stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&a.side_stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&a.fence, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&a.side_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&a.raster_done, cudaEventDisableTiming);
@@ -37,6 +39,16 @@ static DeviceAux *device_aux() {
     if (cudaHostAlloc((void **)&a.host_words, 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
   }
   return &a;
+}
+
+// GS_SIDE_STREAM=0: enqueue the auxiliary work on the caller's stream as well (A/B switch)
+static bool use_side_stream() {
+  static int choice = -1;
+  if (choice < 0) {
+    const char *e = getenv("GS_SIDE_STREAM");
+    choice = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return choice == 1;
 }
 
 static bool render_supported(const gs_raster_config &c, int channels) {
@@ -82,6 +94,7 @@ extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, in
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceAux *aux = device_aux();
   if (aux == nullptr) { set_error("render_stage_a: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
+  cudaStream_t side = use_side_stream() ? aux->side_stream : stream;
   const gs_raster_config &c = a->config;
   const int64_t n = a->n;
   *v_out = 0; *k_out = 0; *max_per_tile_out = 0;
@@ -101,21 +114,21 @@ extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, in
 
   // ---- auxiliary stream: features, zero fills, raster digest (none of it feeds the mapper) ----
   GS_CUDA(cudaEventRecord(aux->fence, stream));
-  GS_CUDA(cudaStreamWaitEvent(aux->side, aux->fence, 0));
+  GS_CUDA(cudaStreamWaitEvent(side, aux->fence, 0));
   if (a->use_sh) {
     GS_TRY(gs_sh_fwd_f32(a->feature, a->position, a->indexes, a->camera_pos, v, a->channels, a->sh_degree,
-                         a->features, aux->side));
+                         a->features, side));
   } else if (v > 0) {
     const int64_t total = v * a->channels;
-    gather_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, aux->side>>>(a->feature, a->indexes, v, a->channels,
+    gather_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, side>>>(a->feature, a->indexes, v, a->channels,
                                                                                a->features);
     GS_LAUNCH_CHECK();
   }
-  if (a->visibility != nullptr && v > 0) GS_CUDA(cudaMemsetAsync(a->visibility, 0, sizeof(float) * v, aux->side));
-  if (a->heuristic != nullptr && v > 0) GS_CUDA(cudaMemsetAsync(a->heuristic, 0, sizeof(float) * 2 * v, aux->side));
+  if (a->visibility != nullptr && v > 0) GS_CUDA(cudaMemsetAsync(a->visibility, 0, sizeof(float) * v, side));
+  if (a->heuristic != nullptr && v > 0) GS_CUDA(cudaMemsetAsync(a->heuristic, 0, sizeof(float) * 2 * v, side));
   GS_TRY(gs_raster_digest_f32(a->points, a->features, a->want_median ? a->depths : nullptr, v, a->channels, &a->config,
-                              a->digest, aux->side));
-  GS_CUDA(cudaEventRecord(aux->side_done, aux->side));
+                              a->digest, side));
+  GS_CUDA(cudaEventRecord(aux->side_done, side));
 
   const int ts = c.tile_size;
   const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
@@ -212,6 +225,7 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceAux *aux = device_aux();
   if (aux == nullptr) { set_error("render_backward: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
+  cudaStream_t side = use_side_stream() ? aux->side_stream : stream;
   const int64_t n = a->n, v = a->v;
   const int F = a->channels;
   const int D = a->use_sh ? (a->sh_degree + 1) * (a->sh_degree + 1) : 1;
@@ -220,17 +234,17 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
 
   // ---- auxiliary stream: zero fills of the dense parameter gradients, beside the raster backward ----
   GS_CUDA(cudaEventRecord(aux->fence, stream));
-  GS_CUDA(cudaStreamWaitEvent(aux->side, aux->fence, 0));
-  if (a->d_position) GS_CUDA(cudaMemsetAsync(a->d_position, 0, sizeof(float) * 3 * n, aux->side));
-  if (a->d_log_scaling) GS_CUDA(cudaMemsetAsync(a->d_log_scaling, 0, sizeof(float) * 3 * n, aux->side));
-  if (a->d_rotation) GS_CUDA(cudaMemsetAsync(a->d_rotation, 0, sizeof(float) * 4 * n, aux->side));
-  if (a->d_alpha_logit) GS_CUDA(cudaMemsetAsync(a->d_alpha_logit, 0, sizeof(float) * n, aux->side));
-  if (a->d_T_camera_world) GS_CUDA(cudaMemsetAsync(a->d_T_camera_world, 0, sizeof(float) * 16, aux->side));
-  if (a->d_projection) GS_CUDA(cudaMemsetAsync(a->d_projection, 0, sizeof(float) * 4, aux->side));
+  GS_CUDA(cudaStreamWaitEvent(side, aux->fence, 0));
+  if (a->d_position) GS_CUDA(cudaMemsetAsync(a->d_position, 0, sizeof(float) * 3 * n, side));
+  if (a->d_log_scaling) GS_CUDA(cudaMemsetAsync(a->d_log_scaling, 0, sizeof(float) * 3 * n, side));
+  if (a->d_rotation) GS_CUDA(cudaMemsetAsync(a->d_rotation, 0, sizeof(float) * 4 * n, side));
+  if (a->d_alpha_logit) GS_CUDA(cudaMemsetAsync(a->d_alpha_logit, 0, sizeof(float) * n, side));
+  if (a->d_T_camera_world) GS_CUDA(cudaMemsetAsync(a->d_T_camera_world, 0, sizeof(float) * 16, side));
+  if (a->d_projection) GS_CUDA(cudaMemsetAsync(a->d_projection, 0, sizeof(float) * 4, side));
   // the SH backward stores whole coefficient rows of every visible Gaussian: nothing to clear when all are visible
   if (a->d_feature && !(a->use_sh && v == n))
-    GS_CUDA(cudaMemsetAsync(a->d_feature, 0, sizeof(float) * n * F * D, aux->side));
-  GS_CUDA(cudaEventRecord(aux->fills_done, aux->side));
+    GS_CUDA(cudaMemsetAsync(a->d_feature, 0, sizeof(float) * n * F * D, side));
+  GS_CUDA(cudaEventRecord(aux->fills_done, side));
 
   // ---- raster backward ----
   if (v > 0) {
@@ -247,13 +261,13 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
 
     // ---- auxiliary stream: feature gradient (SH backward / row scatter) ----
     if (a->d_feature) {
-      GS_CUDA(cudaStreamWaitEvent(aux->side, aux->raster_done, 0));
+      GS_CUDA(cudaStreamWaitEvent(side, aux->raster_done, 0));
       if (a->use_sh) {
         GS_TRY(gs_sh_bwd_f32(a->feature, a->position, a->indexes, a->camera_pos, a->grad_features, a->features, v, F,
-                             a->sh_degree, 1, a->d_feature, nullptr, nullptr, aux->side));
+                             a->sh_degree, 1, a->d_feature, nullptr, nullptr, side));
       } else {
         const int64_t total = v * F;
-        scatter_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, aux->side>>>(a->grad_features, a->indexes, v, F,
+        scatter_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, side>>>(a->grad_features, a->indexes, v, F,
                                                                                     a->d_feature);
         GS_LAUNCH_CHECK();
       }
@@ -276,7 +290,7 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
     }
   }
   // ---- join ----
-  GS_CUDA(cudaEventRecord(aux->bwd_join, aux->side));
+  GS_CUDA(cudaEventRecord(aux->bwd_join, side));
   GS_CUDA(cudaStreamWaitEvent(stream, aux->bwd_join, 0));
   return GS_OK;
 }
