@@ -133,22 +133,30 @@ def apply_step(group: Group, weight, indexes, total_weight, algorithm: int, basi
           None, group.param)
 
 
+def resolve_algorithm(kernels) -> int:
+  """ADAM / LAPROP; a reference-style kernel module (fractional_adam / fractional_laprop) is accepted too."""
+  if isinstance(kernels, types.ModuleType):
+    kernels = LAPROP if "laprop" in kernels.__name__ else ADAM
+  assert kernels in (ADAM, LAPROP), f"unknown optimiser kernels {kernels!r}"
+  return kernels
+
+
+def group_defaults(lr, betas, eps, bias_correction, clip) -> dict:
+  """Validated per-group defaults shared by every optimiser of this package (same checks and messages as upstream)."""
+  for ok, what in ((lr > 0, f"learning rate: {lr}"), (eps > 0, f"epsilon: {eps}"),
+                   (0.0 <= betas[0] < 1.0, f"beta1: {betas[0]}"), (0.0 <= betas[1] < 1.0, f"beta2: {betas[1]}")):
+    assert ok, "Invalid " + what
+  return dict(lr=lr, betas=betas, eps=eps, mask_lr=None, point_lr=None, type="scalar", bias_correction=bias_correction,
+              clip=clip)
+
+
 class FractionalOpt(torch.optim.Optimizer):
   """Reference :153-199.  `kernels` is ADAM or LAPROP (the reference passes the Taichi kernel module)."""
 
   def __init__(self, kernels, param_groups: list, lr=0.001, betas=(0.9, 0.999), eps=1e-16, bias_correction=True,
                clip: Optional[float] = None):
-    assert lr > 0, f"Invalid learning rate: {lr}"
-    assert eps > 0, f"Invalid epsilon: {eps}"
-    assert 0.0 <= betas[0] < 1.0, f"Invalid beta1: {betas[0]}"
-    assert 0.0 <= betas[1] < 1.0, f"Invalid beta2: {betas[1]}"
-    if isinstance(kernels, types.ModuleType):   # a reference-style kernel module: fractional_adam / fractional_laprop
-      kernels = LAPROP if "laprop" in kernels.__name__ else ADAM
-    assert kernels in (ADAM, LAPROP)
-    defaults = dict(lr=lr, betas=betas, eps=eps, mask_lr=None, point_lr=None, type="scalar",
-                    bias_correction=bias_correction, clip=clip)
-    self.kernels = kernels
-    super().__init__(param_groups, defaults)
+    self.kernels = resolve_algorithm(kernels)
+    super().__init__(param_groups, group_defaults(lr, betas, eps, bias_correction, clip))
 
   @torch.no_grad()
   def step(self, indexes: torch.Tensor, weight: torch.Tensor, basis: Optional[torch.Tensor] = None):
