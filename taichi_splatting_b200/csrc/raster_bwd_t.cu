@@ -39,7 +39,11 @@ constexpr int kTile = 16;
 constexpr int kWarps = 4;          // one warp per 8x8 pixel block; every lane owns two pixels (rows r and r + 4)
 constexpr int kThreads = kWarps * 32;
 constexpr int kBatch = kThreads;   // splats staged per round: thread j stages and finally flushes splat j
-constexpr int kChunk = 8;          // splats per phase-1 / phase-2 round
+#ifndef GS_BWDT_CHUNK
+#define GS_BWDT_CHUNK 8
+#endif
+constexpr int kChunk = GS_BWDT_CHUNK;   // splats per phase-1 / phase-2 round: 8 | 4 (4: half the panel, more CTAs per SM)
+static_assert(kChunk == 8 || kChunk == 4, "phase 2 is written for chunks of 8 or 4 splats");
 constexpr int kRow = 33;           // panel row stride in float4 (32 lanes + 1 pad: conflict-free transposed reads)
 constexpr int kAcc = 13;           // accumulator stride: 6 moments, 4 features, 2 heuristics, 1 pad (odd)
 constexpr float kExpScale = 0.84932180028801904f;
@@ -115,10 +119,14 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
   }
 
   // phase-2 role of this lane: splat s of the chunk, pixel rows q and q + 4 of the warp's block
-  const int s = lane & 7, q = lane >> 3;
-  const float bx0 = (float)((warp & 1) * 8) - 7.5f;           // tile-centred x of a row's first pixel
-  const float lya = (float)((warp >> 1) * 8 + q) - 7.5f;      // tile-centred y of the upper row (the other: + 4)
-  const int slot_base = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0);
+  // phase-2 role of this lane.  Chunk 8: splat s = lane & 7, row pair q = lane >> 3 (8 lane entries).  Chunk 4: splat
+  // s = lane & 3, half a row pair q = lane >> 2 (4 lane entries: columns 4 (q & 1) .. + 3 of row pair q >> 1).
+  const int s = kChunk == 8 ? (lane & 7) : (lane & 3), q = kChunk == 8 ? (lane >> 3) : (lane >> 2);
+  const int entries = kChunk == 8 ? 8 : 4;
+  const float bx0 = (float)((warp & 1) * 8 + (kChunk == 8 ? 0 : 4 * (q & 1))) - 7.5f;   // tile-centred x of the first entry
+  const float lya = (float)((warp >> 1) * 8 + (kChunk == 8 ? q : (q >> 1))) - 7.5f;   // y of the upper row (other: + 4)
+  const int slot_base = kChunk == 8 ? ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0)
+                                    : ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0);
   float4 *panel0 = sm.panel0[warp], *panel1 = sm.panel1[warp];
   const unsigned char *rec_a = reinterpret_cast<const unsigned char *>(sm.a);
   const unsigned char *rec_b = reinterpret_cast<const unsigned char *>(sm.b);
@@ -209,8 +217,8 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
     for (int h0 = 0; h0 < nhit; h0 += kChunk) {
       // ---- phase 1: lane = two pixels; 8 splats in depth order ----
       const uint4 nx0 = *reinterpret_cast<const uint4 *>(&sm.list[warp][h0 + 4]);
-      const uint4 nx1 = *reinterpret_cast<const uint4 *>(&sm.list[warp][h0 + 8]);
-      const unsigned next_off[kChunk] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
+      const uint4 nx1 = kChunk == 8 ? *reinterpret_cast<const uint4 *>(&sm.list[warp][h0 + 8]) : nx0;
+      const unsigned next_off[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
       constexpr int kUnroll1 = GS_BWDT_UNROLL;
 #pragma unroll kUnroll1
       for (int u = 0; u < kChunk; ++u) {
@@ -292,9 +300,9 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
       f32x2 md = pk(0.f, 0.f), sd1 = pk(0.f, 0.f), hh = pk(0.f, 0.f), f01 = pk(0.f, 0.f), f23 = pk(0.f, 0.f);
       float s2 = 0.f;
       {
-        const float4 *row0 = panel0 + s * kRow + q * 8, *row1 = panel1 + s * kRow + q * 8;
+        const float4 *row0 = panel0 + s * kRow + q * entries, *row1 = panel1 + s * kRow + q * entries;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < entries; ++i) {
           const float4 e0 = row0[i];
           const f32x2 sd = pk(e0.x, e0.y);
           md = add2(md, sd);                                         // (sum S, sum D)
@@ -341,7 +349,11 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
           v[i] = keep + __shfl_xor_sync(full, send, 8);
         }
       }
-      if (h0 + s < nhit) {
+      if (kChunk == 4) {   // third stage: the two halves of a row pair (both lanes end with the sums; one adds them)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[i] += __shfl_xor_sync(full, v[i], 4);
+      }
+      if (h0 + s < nhit && (kChunk == 8 || (lane & 4) == 0)) {
         float *dst = sm.acc + (sm.list[warp][3 + h0 + s] >> 4) * kAcc + slot_base;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
