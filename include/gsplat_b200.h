@@ -265,6 +265,14 @@ int gs_raster_bwd_digest_f32(const void *digest, const int32_t *tile_ranges, con
                              const float *image, const float *grad_image, int64_t v, int64_t k, int32_t width,
                              int32_t height, int32_t num_features, const gs_raster_config *config,
                              float *grad_points, float *grad_features, float *point_heuristic, void *stream);
+/* As above with dL/dimage addressed through three element strides (y, x, channel; host array): the gradient torch
+ * hands a backward is often not contiguous -- an expanded scalar for sum()/mean() losses (strides 0,0,0), a permuted
+ * (C,H,W) tensor -- and the reference pays a full-image copy for it (rasterizer/function.py:91 .contiguous()). */
+int gs_raster_bwd_digest_strided_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point,
+                                     const float *image, const float *grad_image,
+                                     const int64_t *grad_image_strides_host, int64_t v, int64_t k, int32_t width,
+                                     int32_t height, int32_t num_features, const gs_raster_config *config,
+                                     float *grad_points, float *grad_features, float *point_heuristic, void *stream);
 
 /* ---- Whole-frame host drivers (renderer.py:22-108 in one call per phase) --------------------------------------
  * The per-stage entry points above mirror the reference's operators one to one, and a Python caller that chains
@@ -341,7 +349,8 @@ typedef struct gs_render_bwd_args {
   int64_t n, v, k;
   int32_t width, height;
   double blur_cov, clamp_margin;
-  int32_t use_sh, sh_degree, channels, reserved;
+  int32_t use_sh, sh_degree, channels;
+  int32_t d_image_strided;         /* != 0: d_image is addressed through d_image_strides (below) */
   gs_raster_config config;
   /* saved by the forward */
   const int64_t *indexes;
@@ -349,7 +358,7 @@ typedef struct gs_render_bwd_args {
   const void *digest;
   const int32_t *overlap_to_point, *tile_ranges;
   /* incoming gradients */
-  const float *d_image;            /* (H,W,channels) contiguous */
+  const float *d_image;            /* (H,W,channels): contiguous, or any element strides with d_image_strided */
   const float *d_depths;           /* (v,1) or NULL (zero) */
   /* scratch / accumulated: grad_points (v,7) and grad_features (v,channels) are zero-filled here unless
    * grad_*_preset != 0 (the caller already stored incoming gradients in them) */
@@ -360,6 +369,7 @@ typedef struct gs_render_bwd_args {
   float *d_position, *d_log_scaling, *d_rotation, *d_alpha_logit, *d_T_camera_world, *d_projection;
   float *d_feature;                /* same shape as feature */
   void *ev_raster_start, *ev_raster_end;
+  int64_t d_image_strides[3];      /* element strides (y, x, channel) of d_image when d_image_strided */
 } gs_render_bwd_args;
 
 int gs_render_backward_f32(const gs_render_bwd_args *args, void *stream);

@@ -57,7 +57,7 @@ class RenderBwdArgsC(ctypes.Structure):
       ("T_camera_world", P), ("projection", P),
       ("n", I64), ("v", I64), ("k", I64), ("width", I32), ("height", I32),
       ("blur_cov", D), ("clamp_margin", D),
-      ("use_sh", I32), ("sh_degree", I32), ("channels", I32), ("reserved", I32),
+      ("use_sh", I32), ("sh_degree", I32), ("channels", I32), ("d_image_strided", I32),
       ("config", RasterConfigC),
       ("indexes", P), ("features", P), ("image", P), ("camera_pos", P), ("digest", P),
       ("overlap_to_point", P), ("tile_ranges", P),
@@ -67,6 +67,7 @@ class RenderBwdArgsC(ctypes.Structure):
       ("d_position", P), ("d_log_scaling", P), ("d_rotation", P), ("d_alpha_logit", P),
       ("d_T_camera_world", P), ("d_projection", P), ("d_feature", P),
       ("ev_raster_start", P), ("ev_raster_end", P),
+      ("d_image_strides", I64 * 3),
   ]
 
 
@@ -113,6 +114,7 @@ SIGNATURES = {
     "gs_raster_digest_f32": ([P, P, P, I64, I32, POINTER(RasterConfigC), P, P], c_int32),
     "gs_raster_fwd_digest_f32": ([P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_digest_f32": ([P, P, P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
+    "gs_raster_bwd_digest_strided_f32": ([P, P, P, P, P, POINTER(I64), I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
     "gs_render_stage_a_f32": ([POINTER(RenderArgsC), POINTER(I64), POINTER(I64), POINTER(I64), P], c_int32),
     "gs_render_stage_b_f32": ([POINTER(RenderArgsC), I64, I64, I64, I64, P, P, P, SZ, P], c_int32),
     "gs_render_forward_f32": ([POINTER(RenderArgsC), I64, P, P, P, SZ, POINTER(I64), POINTER(I64), POINTER(I64),
@@ -161,7 +163,7 @@ OWN_KERNELS = {
     "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1,
     "gs_tile_ranges_from_tiles": 1, "gs_tile_bin_count": 1, "gs_tile_bin_offsets": 1, "gs_tile_bin_emit": 1,
     "gs_tile_bin_sort": 1, "gs_raster_fwd_f32": 2, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 2, "gs_raster_bwd_f32": 2,
-    "gs_raster_bwd_f64": 1, "gs_raster_digest_f32": 1, "gs_raster_fwd_digest_f32": 1, "gs_raster_bwd_digest_f32": 1,
+    "gs_raster_bwd_f64": 1, "gs_raster_digest_f32": 1, "gs_raster_fwd_digest_f32": 1, "gs_raster_bwd_digest_f32": 1, "gs_raster_bwd_digest_strided_f32": 1,
     # whole-frame drivers: cull, camera position, write, SH, digest, depth key, count, scan tail | emit, ranges, raster |
     # raster backward, projection backward, SH backward
     "gs_render_stage_a_f32": 8, "gs_render_stage_b_f32": 3, "gs_render_backward_f32": 3, "gs_render_forward_f32": 8,

@@ -32,7 +32,8 @@ static bool bwd_tuned(const gs_raster_config *cfg, int F) {
 static int raster_bwd_digest_impl(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point,
                                   const float *image, const float *grad_image, int64_t v, int32_t width,
                                   int32_t height, int32_t F, const gs_raster_config *cfg, float *grad_points,
-                                  float *grad_features, float *point_heuristic, cudaStream_t stream) {
+                                  float *grad_features, float *point_heuristic, cudaStream_t stream,
+                                  const int64_t *grad_image_strides = nullptr) {
   GS_CHECK_ARG(cfg != nullptr, "raster_bwd: config is NULL");
   GS_CHECK_ARG(width > 0 && height > 0, "raster_bwd: bad image size %dx%d", width, height);
   GS_CHECK_ARG(!cfg->compute_point_heuristic || point_heuristic != nullptr || v == 0, "raster_bwd: compute_point_heuristic needs a buffer");
@@ -43,6 +44,9 @@ static int raster_bwd_digest_impl(const void *digest, const int32_t *tile_ranges
   }
   if (v == 0) return GS_OK;
   RasterParams<float> P = make_params<float>(cfg, width, height, F);
+  if (grad_image_strides != nullptr) {
+    P.gs_y = grad_image_strides[0]; P.gs_x = grad_image_strides[1]; P.gs_c = grad_image_strides[2];
+  }
   const int tiles = P.tiles_wide * ((height + kTileB - 1) / kTileB);
   const float4 *d = reinterpret_cast<const float4 *>(digest);
   switch (F) {
@@ -89,6 +93,19 @@ extern "C" int gs_raster_bwd_digest_f32(const void *digest, const int32_t *tile_
   (void)k;
   return gs::raster_bwd_digest_impl(digest, tile_ranges, overlap_to_point, image, grad_image, v, width, height, F,
                                     cfg, grad_points, grad_features, point_heuristic, (cudaStream_t)stream_);
+}
+
+extern "C" int gs_raster_bwd_digest_strided_f32(const void *digest, const int32_t *tile_ranges,
+                                                const int32_t *overlap_to_point, const float *image,
+                                                const float *grad_image, const int64_t *grad_image_strides_host,
+                                                int64_t v, int64_t k, int32_t width, int32_t height, int32_t F,
+                                                const gs_raster_config *cfg, float *grad_points, float *grad_features,
+                                                float *point_heuristic, void *stream_) {
+  (void)k;
+  GS_CHECK_ARG(grad_image_strides_host != nullptr, "raster_bwd (strided): strides is NULL");
+  return gs::raster_bwd_digest_impl(digest, tile_ranges, overlap_to_point, image, grad_image, v, width, height, F,
+                                    cfg, grad_points, grad_features, point_heuristic, (cudaStream_t)stream_,
+                                    grad_image_strides_host);
 }
 
 extern "C" int gs_raster_bwd_f64(const double *points, const double *features, const int32_t *tile_ranges,

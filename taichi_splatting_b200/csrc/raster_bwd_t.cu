@@ -108,9 +108,9 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
     for (int p = 0; p < 2; ++p) {
       if (in_bounds[p]) {
         const float *img = image + ((int64_t)py[p] * P.width + px) * F;
-        const float *gi = grad_image + ((int64_t)py[p] * P.width + px) * F;
+        const float *gi = grad_image + (int64_t)py[p] * P.gs_y + (int64_t)px * P.gs_x;   // any strides (expanded, CHW, ...)
 #pragma unroll
-        for (int c = 0; c < F; ++c) { g[p][c] = gi[c]; rneg[p] = fmaf(-img[c], g[p][c], rneg[p]); }
+        for (int c = 0; c < F; ++c) { g[p][c] = gi[c * P.gs_c]; rneg[p] = fmaf(-img[c], g[p][c], rneg[p]); }
         trans[p] = 1.0f;
       }
     }

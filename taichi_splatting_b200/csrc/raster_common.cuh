@@ -10,6 +10,7 @@ struct RasterParams {
   int width, height, tiles_wide, num_features, tile_size;
   int antialias, blend, vis, heur;
   real clamp_max, thr, sat, fwd_eps;
+  int64_t gs_y, gs_x, gs_c;   // element strides of dL/dimage (tuned backward kernel); contiguous (H,W,F) by default
 };
 
 template <typename real>
@@ -21,6 +22,7 @@ inline RasterParams<real> make_params(const gs_raster_config *c, int width, int 
   p.vis = c->compute_visibility; p.heur = c->compute_point_heuristic;
   p.clamp_max = (real)c->clamp_max_alpha; p.thr = (real)c->alpha_threshold;
   p.sat = (real)c->saturate_threshold; p.fwd_eps = (real)c->forward_saturate_eps;
+  p.gs_y = (int64_t)width * F; p.gs_x = F; p.gs_c = 1;
   return p;
 }
 

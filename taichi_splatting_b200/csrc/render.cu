@@ -252,9 +252,14 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
     if (a->grad_features && !a->grad_features_preset) GS_CUDA(cudaMemsetAsync(a->grad_features, 0, sizeof(float) * F * v, stream));
     if (a->d_image != nullptr) {
       if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
-      GS_TRY(gs_raster_bwd_digest_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image, v, a->k,
-                                      a->width, a->height, F, &a->config, need_geom ? a->grad_points : nullptr,
-                                      a->d_feature ? a->grad_features : nullptr, a->heuristic, stream));
+      float *gp = need_geom ? a->grad_points : nullptr, *gf = a->d_feature ? a->grad_features : nullptr;
+      if (a->d_image_strided)
+        GS_TRY(gs_raster_bwd_digest_strided_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image,
+                                                a->d_image_strides, v, a->k, a->width, a->height, F, &a->config, gp, gf,
+                                                a->heuristic, stream));
+      else
+        GS_TRY(gs_raster_bwd_digest_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image, v, a->k,
+                                        a->width, a->height, F, &a->config, gp, gf, a->heuristic, stream));
       if (a->ev_raster_end != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_end, stream));
     }
     GS_CUDA(cudaEventRecord(aux->raster_done, stream));

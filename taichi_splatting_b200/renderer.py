@@ -271,17 +271,21 @@ class _RenderFunction(torch.autograd.Function):
     grad_g = d_g2d.clone() if d_g2d is not None else torch.empty_like(g2d)
     grad_f = d_features.clone() if d_features is not None else torch.empty_like(features)
     ev_bwd = _next_event_pair("bwd")
+    # dL/dimage goes to the kernel with whatever strides autograd gave it (an expanded scalar after image.sum(), a
+    # permuted CHW tensor, ...): no .contiguous() copy of a full image
+    strided = d_image is not None and not d_image.is_contiguous()
+    d_image_strides = (_lib.c_int64 * 3)(*(d_image.stride() if strided else (0, 0, 0)))
     args = _lib.RenderBwdArgsC(
         ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(feature), ptr(T_camera_world), ptr(projection),
-        n, v, k, w, h, blur, margin, int(use_sh), check_sh_degree(feature) if use_sh else 0, F, 0,
+        n, v, k, w, h, blur, margin, int(use_sh), check_sh_degree(feature) if use_sh else 0, F, int(strided),
         _lib.raster_config_c(config),
         ptr(indexes), ptr(features), ptr(image), ptr(cam_pos), ptr(digest), ptr(overlap_to_point), ptr(ranges),
-        ptr(d_image.contiguous()) if d_image is not None else None,
+        (d_image.data_ptr() if strided else ptr(d_image)) if d_image is not None else None,
         ptr(d_depths.contiguous()) if d_depths is not None else None,
         ptr(grad_g), ptr(grad_f), int(d_g2d is not None), int(d_features is not None),
         ptr(heuristic) if config.compute_point_heuristic else None,
         *[ptr(g) for g in grads], ptr(d_feature),
-        _event_handle(ev_bwd[0] if ev_bwd else None), _event_handle(ev_bwd[1] if ev_bwd else None))
+        _event_handle(ev_bwd[0] if ev_bwd else None), _event_handle(ev_bwd[1] if ev_bwd else None), d_image_strides)
     _lib.call("gs_render_backward_f32", args, _lib.stream_ptr(device))
     return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)
 

@@ -454,6 +454,38 @@ def test_host_drivers_and_orderings_agree(ts):
   assert float(far.position.grad.abs().max()) == 0.0 and float(far.feature.grad.abs().max()) == 0.0
 
 
+def test_backward_takes_strided_image_gradients(ts):
+  """dL/dimage as autograd hands it over -- an expanded scalar (image.sum()), a permuted CHW product -- goes to the
+  backward driver with its strides; results must equal the staged path, which copies it contiguous first."""
+  from taichi_splatting_b200 import renderer
+  torch.manual_seed(6)
+  size = (200, 120)
+  cam = random_data.fixed_camera(size)
+  g = random_data.random_3d_gaussians(8000, cam, scale_factor=1.5, margin=0.2, sh_degree=1)
+  R = torch.rand((3, size[1], size[0]), device=DEV)
+  losses = {"sum": lambda img: img.sum() * 0.37, "chw": lambda img: (img.permute(2, 0, 1) * R).sum(),
+            "contiguous": lambda img: (img * R.permute(1, 2, 0).contiguous()).sum()}
+
+  def run(fused_host, loss):
+    saved = renderer._FUSED_HOST
+    renderer._FUSED_HOST = fused_host
+    try:
+      gauss = ts.Gaussians3D(**{k: v.to(DEV).requires_grad_(True) for k, v in vars(g).items()})
+      camera = ts.perspective.CameraParams(projection=cam.projection.to(DEV), T_camera_world=cam.T_camera_world.to(DEV),
+                                           near_plane=cam.near_plane, far_plane=cam.far_plane, image_size=size)
+      out = ts.render_gaussians(gauss, camera, ts.RasterConfig(compute_point_heuristic=True), use_sh=True)
+      loss(out.image).backward()
+      return gauss, out
+    finally:
+      renderer._FUSED_HOST = saved
+
+  for name, loss in losses.items():
+    (ga, oa), (gb, ob) = run(True, loss), run(False, loss)
+    for k in ("position", "log_scaling", "rotation", "alpha_logit", "feature"):
+      assert rel_err(getattr(ga, k).grad, getattr(gb, k).grad) < 1e-5, (name, k)
+    assert rel_err(oa.points.split_score, ob.points.split_score) < 1e-5, name
+
+
 def test_binned_ordering_falls_back_on_crowded_tile(ts):
   """More overlaps in one tile than the shared-memory sort takes: the binned ordering must hand over to the two-level
   one (mapper operator, and stage B of the whole-frame driver) with the identical result."""
