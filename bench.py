@@ -307,10 +307,15 @@ def run_ours(args):
   stage_bytes, total_bytes = algorithmic_bytes(n, V, K, P, T, 3, (deg + 1)**2)
   hbm_peak, peak_kind = peaks()
   bwd_ms = stage_hot.get("gs_raster_bwd_digest_f32")
-  traffic = None
+  traffic, limiter = None, None
   try:
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-      traffic = json.load(f).get("raster_bwd_kernel", {}).get("dram_bytes_per_launch")
+      cap = json.load(f).get("raster_bwd_kernel", {})
+    traffic = cap.get("dram_bytes_per_launch")
+    if "l1_data_pipe_pct" in cap:   # from the committed ncu --set full capture of this kernel (profiles/)
+      limiter = {"unit": "L1/shared-memory data pipe (ncu l1tex__data_pipe_lsu_wavefronts, % of peak)",
+                 "frac": round(cap["l1_data_pipe_pct"] / 100, 4), "issue_slots_frac": round(cap.get("issue_slots_pct", 0) / 100, 4),
+                 "source": "profiles/" + cap.get("capture", "traffic.json")}
   except Exception:
     pass
   roofline = {
@@ -319,8 +324,10 @@ def run_ours(args):
       "peak": hbm_peak, "peak_source": peak_kind,
       "frac": round(stage_bytes["raster_bwd"] / (bwd_ms * 1e-3) / 1e9 / hbm_peak, 5) if bwd_ms else None,
       "traffic": traffic, "algorithmic_bytes_per_launch": stage_bytes["raster_bwd"], "kernel_ms": round(bwd_ms, 4) if bwd_ms else None,
-      "note": "raster kernels are FP32/MUFU/shared-memory bound (~150 flop per gathered byte), so their HBM fraction is low "
-              "by construction; pipeline-level figure in pipeline_hbm",
+      "note": "raster kernels are bound by the L1/shared-memory data pipe (broadcast loads of the per-splat records, the "
+              "backward's transpose panel), not by HBM (~100 flop per gathered byte), so their HBM fraction is low by "
+              "construction; see limiter and the pipeline-level figure in pipeline_hbm",
+      "limiter": limiter,
       "pipeline_hbm": {"algorithmic_bytes_per_step": total_bytes,
                        "achieved": round(total_bytes / (ms_per_step * 1e-3) / 1e9, 2),
                        "frac": round(total_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak, 5)},

@@ -74,6 +74,12 @@ for r in rr[2:]:
   key = "raster_bwd_kernel" if "raster_bwd" in name else name.split("(")[0]
   traffic[key] = {"dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
                   "capture": f"raster_{tag}.ncu-rep", "kernel": name[:100]}
+  # what actually bounds the kernel: utilisation of the L1/shared-memory data pipe and of the issue slots
+  for metric, short in (("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1_data_pipe_pct"),
+                        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_slots_pct"),
+                        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct")):
+    if metric in vals:
+      traffic[key][short] = float(vals[metric].replace(",", ""))
 open(out_md, "w").write("\n".join(lines) + "\n")
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(out_md)
