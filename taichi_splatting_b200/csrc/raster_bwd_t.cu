@@ -1,22 +1,26 @@
-// raster_bwd_t.cu -- R9, "transpose" variant of the tuned backward kernel (fp32, 16x16 tiles, plain pdf).
+// raster_bwd_t.cu -- R9: the tuned backward kernel (fp32, 16x16 tiles, plain pdf, 1..4 features).
 //
-// Same semantics, tile / warp-rectangle / hit-list structure and moment formulation as raster_bwd.cu.  What
-// changes is how the per-(pixel, splat) quantities become per-splat sums.  raster_bwd.cu reduces 11 values
-// across the 32 pixel lanes with shuffles for EVERY splat (15 SHFL + ~30 issue slots per splat, and the LSU
-// pipe -- LDS + SHFL at one warp instruction per cycle per SM -- co-limits the kernel).  Here a warp
+// Semantics: _backward_kernel, rasterizer/backward.py:50-225 (C ABI and dispatch: raster_bwd.cu).  Same tile / 8x8
+// block per warp / two pixels per lane / digest / hit-list structure as raster_fwd.cu, and like it bound by the
+// L1/shared-memory data pipe (DESIGN.md section 4 has the measurements).
 //
-//   phase 1  sweeps 8 splats of its hit list pixel-parallel (lane = pixel) and parks the four per-pixel scalars
-//            {Gp, weight, G^2, |G dpdf/dmean|_1} of each in a padded shared-memory panel [splat][pixel] with one
-//            conflict-free STS.128 per splat;
-//   phase 2  re-reads the panel transposed (lane = (splat, pixel row)): each lane walks the 8 pixels of one row
-//            of the 8x4 rectangle for ONE splat and accumulates in registers -- the row-local moments are just
-//            sum Gp, sum Gp*i, sum Gp*i^2 with the column index i an immediate, features need the row's
-//            dL/dimage (broadcast LDS) -- then a 2-stage transposed butterfly over the 4 rows (9 shuffles per
-//            8 splats) leaves 3 finished sums per lane, added to the batch accumulators with 3 conflict-free
-//            shared atomics per 8 splats.
+// Per (pixel, splat) only six tile-local moments of Gp = alpha * dL/dalpha * pdf are needed, {1, lx, ly, lx^2, lx ly,
+// ly^2} * Gp (l = pixel centre - tile centre), plus weight * dL/dimage and the two densification heuristics: every
+// parameter gradient is linear in those sums (the pdf is exp of a quadratic form in the pixel position), so
+// mean / axis / sigma enter once per (splat, tile) at flush time and dL/dalpha_point = M0 / alpha_point.  The sums
+// over the 64 pixels of a block are formed by a shared-memory transpose:
 //
-// Per splat this is ~1 STS.128 + 2 LDS.128 + ~1 SHFL on the LSU pipe and ~20 issue slots for the reduction,
-// against 15 SHFL and ~50 issue slots before.
+//   phase 1  sweeps 8 splats of the hit list (lane = two pixels sharing a column), pre-sums the pair and parks
+//            {S = Gp0 + Gp1, D = Gp1, sum G^2, sum |G dpdf/dmean|_1} and {sum_pixels weight * dL/dimage[c]} per lane
+//            in two padded panel planes [splat][lane] (conflict-free STS.128); the NEXT splat's records are loaded
+//            before the current one is computed, so their latency hides behind the arithmetic;
+//   phase 2  re-reads the planes transposed -- lane = (splat s, row pair q) walks the 8 lanes of its row pair with
+//            the column index an immediate (sum S, sum i S, sum i^2 S, sum D, sum i D as FADD2 / FFMA2) -- then a
+//            2-stage transposed butterfly over the four row pairs (9 shuffles per 8 splats) leaves 3 finished sums
+//            per lane, added to the batch accumulators with 3 conflict-free shared atomics per 8 splats.
+//
+// Per splat iteration the data pipe is charged 3 x 2.69 (records) + 0.7 (list) + 2 x 4.04 (panel stores) + 2 x 4.04
+// (panel loads) + ~2 (shuffles, atomics) = ~27 cycles; the kernel runs at 81 % of that pipe.
 #include "packed_f32.cuh"
 #include "raster_common.cuh"
 

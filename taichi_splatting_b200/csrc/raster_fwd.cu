@@ -5,18 +5,23 @@
 // reproduces the reference's second raster pass (renderer.py:77-82: use_alpha_blending=False,
 // saturate_threshold=median_threshold, features=depths) from the same walk.
 //
-// B200 design (not the reference's):
-//   * one CTA per 16x16 tile, 8 warps, warp w owns an 8x4 pixel rectangle;
-//   * splats of the tile are staged 256 at a time into shared memory as pre-digested 16-byte records
-//     {mean, axis/sigma} {perp/sigma, alpha, depth} {features}: per pixel 2 FADD + 6 FMUL/FFMA +
-//     1 MUFU.EX2 + blend, read with broadcast LDS.128;
-//   * the staging thread classifies its splat against the eight warp rectangles (AABB + oriented-box
-//     test, conservative) and each warp compacts its own ordered hit list, so a warp only iterates over
-//     splats that can exceed the alpha threshold somewhere in its 32 pixels.  Skipped splats contribute
-//     exactly zero in the reference too (alpha <= threshold), so results are unchanged;
-//   * the inner loop is branch-free and unrolled by 16; per-splat visibility (sum of blend weights over
-//     pixels) is reduced 16 splats at a time with one transposed butterfly (16 shuffles per 16 splats
-//     instead of 5 per splat) and one shared-memory atomic instruction per 16 splats.
+// B200 design (not the reference's; measurements and the reasoning behind each point: DESIGN.md section 4):
+//   * the kernel is bound by the L1/shared-memory data pipe -- a broadcast LDS.128 of a splat record costs 2.69
+//     pipe cycles -- so one CTA per 16x16 tile runs 4 warps, each owning an 8x8 pixel block with TWO pixels per lane
+//     (column lane & 7, rows lane >> 3 and + 4): one record load feeds 64 pixel evaluations;
+//   * splats are gathered from the 64-byte raster digest (raster_digest.cu, four LDG.128) and staged 256 at a time
+//     into shared memory as tile-centred 16-byte records {tx0, ty0, ux, wx} {uy, wy, alpha, depth} {features}:
+//     (tx, ty) = X (ux, wx) + Y (uy, wy) + (tx0, ty0) is three packed FFMA2 for both pixels of a lane, and the
+//     rest of the per-pixel arithmetic runs as FMUL2 / FFMA2 / FADD2 on (pixel 0, pixel 1) register pairs;
+//   * the staging thread classifies its splat against the four 8x8 blocks (separating-axis test against the
+//     oriented box of the support ellipse, conservative) and each warp compacts its own ordered hit list, so a warp
+//     only iterates over splats that can exceed the alpha threshold somewhere in its 64 pixels.  Skipped splats
+//     contribute exactly zero in the reference too (alpha <= threshold), so results are unchanged;
+//   * per-pixel state is the transmittance T (w = alpha T, T -= w; T = 0 outside the image), so the inner loop has no
+//     bounds / done predicate; it is branch-free and unrolled by 16, with the median-depth bookkeeping compiled out
+//     once every pixel of the warp has crossed the median limit; per-splat visibility (sum of blend weights over
+//     pixels) is reduced 16 splats at a time with one transposed butterfly (16 shuffles per 16 splats instead of 5
+//     per splat) and one shared-memory atomic instruction per 16 splats.
 #include <type_traits>
 
 #include "packed_f32.cuh"
