@@ -101,3 +101,28 @@ def test_no_cpu_fallback():
   src = "".join(open(os.path.join(dp, f)).read() for dp, _, fs in os.walk(os.path.join(ROOT, "taichi_splatting_b200"))
                 for f in fs if f.endswith(".py"))
   assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+  """The ctypes mirrors of gs_raster_config / gs_render_args / gs_render_bwd_args must have the C compiler's size
+  and field offsets (a drifted field silently shifts every pointer after it)."""
+  import ctypes
+  import subprocess
+  from taichi_splatting_b200 import _lib
+  structs = {"gs_raster_config": _lib.RasterConfigC, "gs_render_args": _lib.RenderArgsC,
+             "gs_render_bwd_args": _lib.RenderBwdArgsC}
+  lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gsplat_b200.h"', 'int main(void) {']
+  for cname, cls in structs.items():
+    lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+    for field, _ in cls._fields_:
+      lines.append(f'  printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+  lines += ['  return 0;', '}']
+  src = tmp_path / "layout.c"
+  src.write_text("\n".join(lines))
+  exe = tmp_path / "layout"
+  subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+  out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+  for cname, cls in structs.items():
+    assert int(out[cname]) == ctypes.sizeof(cls), (cname, out[cname], ctypes.sizeof(cls))
+    for field, _ in cls._fields_:
+      assert int(out[f"{cname}.{field}"]) == getattr(cls, field).offset, (cname, field)
