@@ -114,7 +114,7 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
 }
 
 #ifndef GS_FWD_MIN_BLOCKS
-#define GS_FWD_MIN_BLOCKS 6
+#define GS_FWD_MIN_BLOCKS 8
 #endif
 // Every lane owns TWO pixels of its warp's 8x8 block -- column (lane & 7), rows (lane >> 3) and (lane >> 3) + 4 --
 // so one broadcast LDS.128 of a splat record feeds 64 pixel evaluations (the kernel is bound by the shared-memory
