@@ -192,7 +192,10 @@ __device__ __forceinline__ void block_reduce_atomic(real (&v)[N], real *__restri
 }
 
 template <typename real>
-__global__ void __launch_bounds__(128)
+#ifndef GS_PBWD_MIN_BLOCKS
+#define GS_PBWD_MIN_BLOCKS 8   // fp32: 64 registers, a few spilled words, 32 warps per SM (latency-bound kernel: 69 -> 61 us)
+#endif
+__global__ void __launch_bounds__(128, sizeof(real) == 4 ? GS_PBWD_MIN_BLOCKS : 2)
 project_bwd_kernel(const real *__restrict__ position, const real *__restrict__ log_scaling,
                    const real *__restrict__ rotation, const real *__restrict__ alpha_logit,
                    const real *__restrict__ T, const real *__restrict__ proj,
