@@ -26,6 +26,9 @@
 
 namespace gs {
 
+#ifndef GS_EXACT_CULL
+#define GS_EXACT_CULL 1   // exact block-vs-ellipse test after the box tests: 7.72 -> 7.33 hit entries per Gaussian (1.131 -> 1.118 ms)
+#endif
 #ifndef GS_BWDT_UNROLL
 #define GS_BWDT_UNROLL 8
 #endif
@@ -177,11 +180,17 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
         const float ex = sc * sqrtf(fmaf(uy, uy, wy * wy)), ey = sc * sqrtf(fmaf(ux, ux, wx * wx));
         const float hu = (fabsf(ux) + fabsf(uy)) * 3.5f + rcs;
         const float hw = (fabsf(wx) + fabsf(wy)) * 3.5f + rcs;
+#if GS_EXACT_CULL
+        const SupportMetric metric = support_metric(ux, wx, uy, wy, rcs);
+#endif
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
           const float ox = (w & 1) ? 4.0f : -4.0f, oy = (w >> 1) ? 4.0f : -4.0f;   // block centre - tile centre
-          bool hit = (fabsf(ox - ddx) - 3.5f <= ex) && (fabsf(oy - ddy) - 3.5f <= ey) &&
-                     (fabsf(fmaf(ux, ox, fmaf(uy, oy, tx0))) <= hu) && (fabsf(fmaf(wx, ox, fmaf(wy, oy, ty0))) <= hw);
+          const float t0x = fmaf(ux, ox, fmaf(uy, oy, tx0)), t0y = fmaf(wx, ox, fmaf(wy, oy, ty0));
+          bool hit = (fabsf(ox - ddx) - 3.5f <= ex) && (fabsf(oy - ddy) - 3.5f <= ey) && (fabsf(t0x) <= hu) && (fabsf(t0y) <= hw);
+#if GS_EXACT_CULL
+          if (hit) hit = block_reaches_support(metric, t0x, t0y, ux, wx, uy, wy);
+#endif
           mask |= hit ? (1u << w) : 0u;
         }
       }

@@ -52,6 +52,50 @@ __device__ __forceinline__ real pdf_plain_grad(real px, real py, const real *g, 
   return p;
 }
 
+// Exact culling of an 8x8 pixel block against a splat's support (tuned kernels).  In t = U d space (U = [u; w]) the
+// support { alpha pdf > threshold } is the disc |t| <= rcs and the block -- pixel centres c + (a, b), |a|, |b| <= 3.5
+// -- is the parallelogram t0 + a e1 + b e2 with e1 = (ux, wx), e2 = (uy, wy).  The block can hold a contributing
+// pixel only if the parallelogram comes within rcs of the origin: minimise the convex quadratic |t0 + a e1 + b e2|^2
+// over the box (zero if the unconstrained minimiser is inside, else the best of the four edges).  Conservative: rcs
+// carries the evaluation-error margin, the continuous box contains the pixel centres, r2 has slack for rounding.
+struct SupportMetric {
+  float G11, G12, G22, i11, i22, idet, r2;
+};
+
+__device__ __forceinline__ SupportMetric support_metric(float ux, float wx, float uy, float wy, float rcs) {
+  SupportMetric m;
+  m.G11 = fmaf(ux, ux, wx * wx); m.G22 = fmaf(uy, uy, wy * wy); m.G12 = fmaf(ux, uy, wx * wy);
+  const float det_u = ux * wy - uy * wx;
+  m.idet = 1.0f / fmaxf(det_u * det_u, 1e-30f);
+  m.i11 = 1.0f / fmaxf(m.G11, 1e-30f); m.i22 = 1.0f / fmaxf(m.G22, 1e-30f);
+  m.r2 = rcs * rcs * 1.0002f + 1e-5f;
+  return m;
+}
+
+__device__ __forceinline__ bool block_reaches_support(const SupportMetric &m, float t0x, float t0y, float ux, float wx,
+                                                      float uy, float wy) {
+  const float h = 3.5f;
+  const float g1 = fmaf(t0x, ux, t0y * wx), g2 = fmaf(t0x, uy, t0y * wy), q0 = fmaf(t0x, t0x, t0y * t0y);
+  const float a0 = (g2 * m.G12 - g1 * m.G22) * m.idet, b0 = (g1 * m.G12 - g2 * m.G11) * m.idet;
+  if (fabsf(a0) <= h && fabsf(b0) <= h) return true;      // the origin of t-space lies inside the parallelogram
+  float qmin = 3.0e38f;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const float sh = s ? h : -h;
+    {   // edge a = sh, free b
+      const float c0 = fmaf(h * h, m.G11, fmaf(2.0f * sh, g1, q0)), c1 = fmaf(sh, m.G12, g2);
+      const float b = fminf(fmaxf(-c1 * m.i22, -h), h);
+      qmin = fminf(qmin, fmaf(b, fmaf(b, m.G22, 2.0f * c1), c0));
+    }
+    {   // edge b = sh, free a
+      const float c0 = fmaf(h * h, m.G22, fmaf(2.0f * sh, g2, q0)), c1 = fmaf(sh, m.G12, g1);
+      const float a = fminf(fmaxf(-c1 * m.i11, -h), h);
+      qmin = fminf(qmin, fmaf(a, fmaf(a, m.G11, 2.0f * c1), c0));
+    }
+  }
+  return qmin <= m.r2;
+}
+
 template <typename real>
 __device__ __forceinline__ real s_sig(real x, real sigma) {
   real z = x / sigma;
