@@ -235,6 +235,8 @@ class _RenderFunction(torch.autograd.Function):
     _lib.call("gs_render_forward_f32", args, cap, ptr(tiles), ptr(o2p), ws_sort.data_ptr() if cap > 0 else None,
               ws_sort.numel() if cap > 0 else 0, v_out, k_out, max_out, done, stream)
     v, k = int(v_out.value), int(k_out.value)
+    if done.value and _lib.profiler is not None:
+      _lib.profiler.launches += _lib.OWN_KERNELS["gs_render_stage_b_f32"]   # stage B ran inside the forward driver
     if not done.value:
       cap = k
       tiles, o2p = empty((2, k), i32), empty((2, k), i32)
