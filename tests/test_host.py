@@ -126,3 +126,27 @@ def test_ctypes_structs_match_the_header(tmp_path):
     assert int(out[cname]) == ctypes.sizeof(cls), (cname, out[cname], ctypes.sizeof(cls))
     for field, _ in cls._fields_:
       assert int(out[f"{cname}.{field}"]) == getattr(cls, field).offset, (cname, field)
+
+
+def test_bench_line_contract():
+  """The committed bench line of the final build carries every key the bench contract names, and the algorithmic
+  byte model reproduces SURVEY 8d's worked figure for the bench workload (2.22 GB per frame)."""
+  import importlib.util
+  import json
+  line = json.loads(open(os.path.join(ROOT, "profiles", "r01v_bench.json")).read())
+  for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+    assert key in line, key
+  assert line["config"]["workload"] and line["gpu_launches"] > 0 and line["higher_is_better"] is True
+  for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+    assert key in line["e2e"], key
+  for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+    assert key in line["roofline"], key
+  for key in ("value", "unit", "cores", "kind", "sample"):
+    assert key in line["cpu_baseline"], key
+  assert abs(line["value"] - line["n_gpus"] * line["config"]["n_gaussians"] / (line["ms_per_step"] * 1e-3)) < 1e-3 * line["value"]
+  spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+  bench = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(bench)
+  _, total = bench.algorithmic_bytes(1_000_000, 1_000_000, 3_838_201, 2048 * 2048, 16384, 3, 16)
+  assert abs(total / 1e9 - 2.22) < 0.02, total
