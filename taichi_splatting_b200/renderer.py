@@ -244,6 +244,8 @@ class _RenderFunction(torch.autograd.Function):
       ws_sort = _lib.workspace(nbytes.value, device)
       _lib.call("gs_render_stage_b_f32", args, v, k, int(max_out.value), k, ptr(tiles), ptr(o2p), ws_sort.data_ptr(),
                 ws_sort.numel(), stream)
+    if o2p is None:   # first frame on this device and nothing to rasterise (K = 0): stage B ran with empty buffers
+      tiles, o2p = empty((2, 0), i32), empty((2, 0), i32)
     _k_capacity[dev_key] = max(int(k * 1.25), 1024)
 
     g2d, depths, indexes, features, digest = g2d_n[:v], depths_n[:v], idx_n[:v], feat_n[:v], digest_n[:v]
