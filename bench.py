@@ -145,7 +145,7 @@ def run_ours(args):
     dist.init_process_group("nccl", device_id=dev)
 
   n, (w, h), deg = WORKLOAD["n_gaussians"], WORKLOAD["image_size"], WORKLOAD["sh_degree"]
-  config = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True)
+  config = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True, forward_saturate_eps=args.fwd_eps)
   cam_host = scenes.benchmark_camera((w, h), yaw_deg=0.0)
   cloud_host = scenes.random_3d_gaussians(n, cam_host, scale_factor=1.0, sh_degree=deg, seed=0)
   # rank r looks at the same cloud from its own view (small yaw steps keep the cloud in the frustum)
@@ -338,7 +338,7 @@ def run_ours(args):
       "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
       "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": dict(WORKLOAD, V=V, K=K, tiles=T, overlaps_per_tile=round(K / T, 1),
+      "config": dict(WORKLOAD, forward_saturate_eps=args.fwd_eps, V=V, K=K, tiles=T, overlaps_per_tile=round(K / T, 1),
                      parallelism=(f"view-parallel x{world}: replicated cloud, one view per rank; gradients summed over ranks by an NCCL "
                                   "all-reduce (geometry, 44 B/Gaussian) + all-gather of the rank-1 SH-gradient factors "
                                   "(12 B/Gaussian/view)") if world > 1 else "single GPU"),
@@ -424,6 +424,8 @@ def main():
   ap.add_argument("--steps", type=int, default=50)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--fwd-eps", type=float, default=0.0,
+                  help="RasterConfig.forward_saturate_eps (0 = the reference's semantics: the forward never stops early)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

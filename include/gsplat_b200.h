@@ -370,7 +370,18 @@ typedef struct gs_render_bwd_args {
   float *d_feature;                /* same shape as feature */
   void *ev_raster_start, *ev_raster_end;
   int64_t d_image_strides[3];      /* element strides (y, x, channel) of d_image when d_image_strided */
+  /* use_sh: gradient of the loss w.r.t. the camera centre (3) through the SH view directions, or NULL.  The reference
+   * gets it from autograd through camera_params.camera_position = inverse(T_camera_world)[:3,3]
+   * (perspective/params.py:78-80); the caller chains it into d_T_camera_world (zero-filled here). */
+  float *d_camera_pos;
+  /* which parts of the backward to enqueue (0 = all).  A view-parallel caller runs GS_BWD_RASTER (zero fills + raster
+   * backward), launches its exchange of the colour gradients, then GS_BWD_PROJECT, and replaces GS_BWD_FEATURE (SH
+   * backward / feature scatter) by the exchange's own kernel. */
+  int32_t phases;
 } gs_render_bwd_args;
+#define GS_BWD_RASTER 1
+#define GS_BWD_FEATURE 2
+#define GS_BWD_PROJECT 4
 
 int gs_render_backward_f32(const gs_render_bwd_args *args, void *stream);
 

@@ -39,7 +39,7 @@ def render_forward_backward(g, camera, config, use_sh=False, grad_image=None, ra
       camera.image_size, camera.depth_range, blur_cov=config.blur_cov, clamp_margin=config.clamp_margin,
       alpha_threshold=config.alpha_threshold)
   if use_sh:
-    cam_pos = torch.inverse(Tcw.detach())[0:3, 3]
+    cam_pos = torch.inverse(Tcw)[0:3, 3]   # differentiable, as camera_params.camera_position is (perspective/params.py:78-80)
     features = sh_fn(leaves["feature"], leaves["position"].detach(), indexes, cam_pos)
   else:
     features = leaves["feature"][indexes]

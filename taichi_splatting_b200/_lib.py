@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import POINTER, c_double, c_int32, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
@@ -68,6 +69,7 @@ class RenderBwdArgsC(ctypes.Structure):
       ("d_T_camera_world", P), ("d_projection", P), ("d_feature", P),
       ("ev_raster_start", P), ("ev_raster_end", P),
       ("d_image_strides", I64 * 3),
+      ("d_camera_pos", P), ("phases", I32),
   ]
 
 
@@ -189,9 +191,26 @@ class Profiler:
 profiler = None   # set to a Profiler() to enable
 
 
+_tls = threading.local()   # .device: index of the device whose stream the calling thread last asked for (stream_ptr)
+
+
 def call(name: str, *args, on=None) -> None:
   """Calls a C-ABI entry point.  `on`: the torch stream the call was enqueued on when it is not the current one
-  (only used to place the profiler's events)."""
+  (only used to place the profiler's events).
+
+  The library launches on the CUDA *current* device (kernel attributes, scratch and auxiliary streams are per
+  device), so when the tensors of this call live on another device than the thread's current one -- a single
+  process driving several GPUs -- the call runs inside `torch.cuda.device(that device)`.  The device is the one the
+  caller last passed to `stream_ptr`, which every operator evaluates for the call's stream argument."""
+  dev = getattr(_tls, "device", None)
+  if dev is not None and dev != torch.cuda.current_device():
+    with torch.cuda.device(dev):
+      _call(name, args, on)
+    return
+  _call(name, args, on)
+
+
+def _call(name: str, args, on) -> None:
   fn = getattr(load(), name)
   prof = profiler
   if prof is None:
@@ -233,6 +252,9 @@ def ptr(t) -> int | None:
 
 
 def stream_ptr(device) -> int:
+  """Handle of the caller's current torch stream on `device`; also tells `call` which device the call belongs to."""
+  device = torch.device(device)
+  _tls.device = device.index if device.index is not None else torch.cuda.current_device()
   return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -21,6 +21,8 @@
 //
 // Per splat iteration the data pipe is charged 3 x 2.69 (records) + 0.7 (list) + 2 x 4.04 (panel stores) + 2 x 4.04
 // (panel loads) + ~2 (shuffles, atomics) = ~27 cycles; the kernel runs at 81 % of that pipe.
+#include <atomic>
+
 #include "packed_f32.cuh"
 #include "raster_common.cuh"
 
@@ -433,13 +435,17 @@ int launch_bwd_transpose(const float4 *digest, const int32_t *ranges, const int3
 #define GS_BWDT_EXTRA_SMEM 0   // profiling aid: extra dynamic shared memory per CTA lowers the residency
 #endif
   const size_t smem = sizeof(bwdt::Smem) + GS_BWDT_EXTRA_SMEM;
+  int dev = 0;
+  GS_CUDA(cudaGetDevice(&dev));
 #define GS_BWDT(GP_, GF_, HE_)                                                                                  \
   do {                                                                                                          \
     auto kern = bwdt::raster_bwd_t_kernel<F, GP_, GF_, HE_>;                                                    \
-    static bool configured = false;                                                                             \
-    if (!configured) {                                                                                          \
+    /* the attribute is per device (and per kernel instantiation): one bit per device, set once each */         \
+    static std::atomic<uint64_t> configured{0};                                                                 \
+    const uint64_t dev_bit = 1ull << (dev & 63);                                                                \
+    if (!(configured.load(std::memory_order_acquire) & dev_bit)) {                                              \
       GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-      configured = true;                                                                                        \
+      configured.fetch_or(dev_bit, std::memory_order_release);                                                  \
     }                                                                                                           \
     kern<<<tiles, bwdt::kThreads, smem, stream>>>(digest, ranges, o2p, image, grad_image, P,                    \
                                                 grad_points, grad_features, heuristic);                         \

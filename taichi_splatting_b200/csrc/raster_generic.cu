@@ -19,8 +19,10 @@ __device__ __forceinline__ real warp_sum(real v) {
   return v;
 }
 
+// __launch_bounds__(1024): tile_size 32 launches 1024-thread blocks; without the bound the fp64 backward took 72
+// registers per thread (72 x 1024 > the 64 K-register block limit) and failed at launch.
 template <typename real>
-__global__ void raster_fwd_generic_kernel(const real *__restrict__ points, const real *__restrict__ features,
+__global__ void __launch_bounds__(1024) raster_fwd_generic_kernel(const real *__restrict__ points, const real *__restrict__ features,
                                           const int32_t *__restrict__ ranges,
                                           const int32_t *__restrict__ overlap_to_point, RasterParams<real> P,
                                           real *__restrict__ image, real *__restrict__ image_alpha,
@@ -74,7 +76,7 @@ __global__ void raster_fwd_generic_kernel(const real *__restrict__ points, const
 }
 
 template <typename real>
-__global__ void raster_bwd_generic_kernel(const real *__restrict__ points, const real *__restrict__ features,
+__global__ void __launch_bounds__(1024) raster_bwd_generic_kernel(const real *__restrict__ points, const real *__restrict__ features,
                                           const int32_t *__restrict__ ranges,
                                           const int32_t *__restrict__ overlap_to_point,
                                           const real *__restrict__ image, const real *__restrict__ grad_image,

@@ -20,15 +20,33 @@ struct DeviceAux {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t fence = nullptr, side_done = nullptr, raster_done = nullptr, fills_done = nullptr, bwd_join = nullptr;
   int32_t *host_words = nullptr;   // pinned: [0] V, [1] K, [2] largest tile population (binned ordering), [4] K (fallback)
+  // The events, the side stream and the pinned words are shared by every frame on this device, so the whole-frame
+  // drivers serialise on this lock: two host threads (or two streams) rendering on one device take turns instead of
+  // overwriting each other's V / K read-backs or re-recording an event the other frame still waits on.
+  std::recursive_mutex frame_mu;
 };
 
-static DeviceAux *device_aux() {
+// Joins the auxiliary stream back into the caller's stream when a driver returns -- on the error paths too, so that
+// torch-owned buffers already handed to work on the auxiliary stream are never freed / reused while it still runs.
+struct SideJoin {
+  cudaStream_t stream, side;
+  cudaEvent_t ev;
+  SideJoin(cudaStream_t stream_, cudaStream_t side_, cudaEvent_t ev_) : stream(stream_), side(side_), ev(ev_) {}
+  ~SideJoin() {
+    if (side == stream) return;
+    if (cudaEventRecord(ev, side) == cudaSuccess) cudaStreamWaitEvent(stream, ev, 0);
+  }
+};
+
+// One auxiliary state per (device, caller stream): frames enqueued on different streams of a device do not share
+// events, side stream or read-back words.
+static DeviceAux *device_aux(cudaStream_t stream) {
   static std::mutex mu;
-  static std::map<int, DeviceAux> table;
+  static std::map<std::pair<int, cudaStream_t>, DeviceAux> table;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
-  DeviceAux &a = table[dev];
+  DeviceAux &a = table[{dev, stream}];
   if (a.side_stream == nullptr) {
     if (cudaStreamCreateWithFlags(&a.side_stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&a.fence, cudaEventDisableTiming);
@@ -85,6 +103,14 @@ static inline int tile_bits(int64_t num_tiles) {
 
 }  // namespace gs
 
+namespace gs {
+static int stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_out, int64_t *max_per_tile_out,
+                        cudaStream_t stream, DeviceAux *aux, cudaStream_t side);
+static int stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64_t max_per_tile, int64_t k_stride,
+                        uint32_t *tiles, int32_t *o2p, void *ws_sort, size_t ws_sort_bytes, cudaStream_t stream,
+                        DeviceAux *aux);
+}  // namespace gs
+
 extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, int64_t *k_out,
                                      int64_t *max_per_tile_out, void *stream_) {
   using namespace gs;
@@ -92,9 +118,17 @@ extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, in
                "render_stage_a: NULL argument");
   GS_CHECK_ARG(render_supported(a->config, a->channels), "render_stage_a: needs tile_size 16, no antialias, alpha blending, 1..4 features");
   cudaStream_t stream = (cudaStream_t)stream_;
-  DeviceAux *aux = device_aux();
+  DeviceAux *aux = device_aux(stream);
   if (aux == nullptr) { set_error("render_stage_a: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
+  std::lock_guard<std::recursive_mutex> frame_lock(aux->frame_mu);
   cudaStream_t side = use_side_stream() ? aux->side_stream : stream;
+  const int rc = stage_a_impl(a, v_out, k_out, max_per_tile_out, stream, aux, side);
+  if (rc != GS_OK) SideJoin(stream, side, aux->bwd_join);   // error after auxiliary work was enqueued: join before returning
+  return rc;
+}
+
+static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_out, int64_t *max_per_tile_out,
+                            cudaStream_t stream, DeviceAux *aux, cudaStream_t side) {
   const gs_raster_config &c = a->config;
   const int64_t n = a->n;
   *v_out = 0; *k_out = 0; *max_per_tile_out = 0;
@@ -160,8 +194,17 @@ extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t
   GS_CHECK_ARG(render_supported(a->config, a->channels), "render_stage_b: unsupported raster configuration");
   GS_CHECK_ARG(k_stride >= k, "render_stage_b: k_stride %lld < k %lld", (long long)k_stride, (long long)k);
   cudaStream_t stream = (cudaStream_t)stream_;
-  DeviceAux *aux = device_aux();
+  DeviceAux *aux = device_aux(stream);
   if (aux == nullptr) { set_error("render_stage_b: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
+  std::lock_guard<std::recursive_mutex> frame_lock(aux->frame_mu);
+  const int rc = stage_b_impl(a, v, k, max_per_tile, k_stride, tiles, o2p, ws_sort, ws_sort_bytes, stream, aux);
+  if (rc != GS_OK) GS_CUDA(cudaStreamWaitEvent(stream, aux->side_done, 0));   // stage A's auxiliary work still holds caller buffers
+  return rc;
+}
+
+static int gs::stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64_t max_per_tile, int64_t k_stride,
+                            uint32_t *tiles, int32_t *o2p, void *ws_sort, size_t ws_sort_bytes, cudaStream_t stream,
+                            DeviceAux *aux) {
   const gs_raster_config &c = a->config;
   const int ts = c.tile_size;
   const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
@@ -223,53 +266,63 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
   GS_CHECK_ARG(a != nullptr, "render_backward: NULL argument");
   GS_CHECK_ARG(render_supported(a->config, a->channels), "render_backward: unsupported raster configuration");
   cudaStream_t stream = (cudaStream_t)stream_;
-  DeviceAux *aux = device_aux();
+  DeviceAux *aux = device_aux(stream);
   if (aux == nullptr) { set_error("render_backward: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
+  std::lock_guard<std::recursive_mutex> frame_lock(aux->frame_mu);   // one frame at a time per device: events / side stream are shared
   cudaStream_t side = use_side_stream() ? aux->side_stream : stream;
   const int64_t n = a->n, v = a->v;
   const int F = a->channels;
   const int D = a->use_sh ? (a->sh_degree + 1) * (a->sh_degree + 1) : 1;
+  const int phases = a->phases == 0 ? (GS_BWD_RASTER | GS_BWD_FEATURE | GS_BWD_PROJECT) : a->phases;
   const bool need_geom = a->d_position || a->d_log_scaling || a->d_rotation || a->d_alpha_logit ||
                          a->d_T_camera_world || a->d_projection;
+  SideJoin join(stream, side, aux->bwd_join);   // every exit path (errors included) joins the auxiliary stream
 
-  // ---- auxiliary stream: zero fills of the dense parameter gradients, beside the raster backward ----
-  GS_CUDA(cudaEventRecord(aux->fence, stream));
-  GS_CUDA(cudaStreamWaitEvent(side, aux->fence, 0));
-  if (a->d_position) GS_CUDA(cudaMemsetAsync(a->d_position, 0, sizeof(float) * 3 * n, side));
-  if (a->d_log_scaling) GS_CUDA(cudaMemsetAsync(a->d_log_scaling, 0, sizeof(float) * 3 * n, side));
-  if (a->d_rotation) GS_CUDA(cudaMemsetAsync(a->d_rotation, 0, sizeof(float) * 4 * n, side));
-  if (a->d_alpha_logit) GS_CUDA(cudaMemsetAsync(a->d_alpha_logit, 0, sizeof(float) * n, side));
-  if (a->d_T_camera_world) GS_CUDA(cudaMemsetAsync(a->d_T_camera_world, 0, sizeof(float) * 16, side));
-  if (a->d_projection) GS_CUDA(cudaMemsetAsync(a->d_projection, 0, sizeof(float) * 4, side));
-  // the SH backward stores whole coefficient rows of every visible Gaussian: nothing to clear when all are visible
-  if (a->d_feature && !(a->use_sh && v == n))
-    GS_CUDA(cudaMemsetAsync(a->d_feature, 0, sizeof(float) * n * F * D, side));
-  GS_CUDA(cudaEventRecord(aux->fills_done, side));
+  if (phases & GS_BWD_RASTER) {
+    // ---- auxiliary stream: zero fills of the dense parameter gradients, beside the raster backward ----
+    GS_CUDA(cudaEventRecord(aux->fence, stream));
+    GS_CUDA(cudaStreamWaitEvent(side, aux->fence, 0));
+    if (a->d_position) GS_CUDA(cudaMemsetAsync(a->d_position, 0, sizeof(float) * 3 * n, side));
+    if (a->d_log_scaling) GS_CUDA(cudaMemsetAsync(a->d_log_scaling, 0, sizeof(float) * 3 * n, side));
+    if (a->d_rotation) GS_CUDA(cudaMemsetAsync(a->d_rotation, 0, sizeof(float) * 4 * n, side));
+    if (a->d_alpha_logit) GS_CUDA(cudaMemsetAsync(a->d_alpha_logit, 0, sizeof(float) * n, side));
+    if (a->d_T_camera_world) GS_CUDA(cudaMemsetAsync(a->d_T_camera_world, 0, sizeof(float) * 16, side));
+    if (a->d_projection) GS_CUDA(cudaMemsetAsync(a->d_projection, 0, sizeof(float) * 4, side));
+    if (a->d_camera_pos) GS_CUDA(cudaMemsetAsync(a->d_camera_pos, 0, sizeof(float) * 3, side));
+    // the SH backward stores whole coefficient rows of every visible Gaussian: nothing to clear when all are visible
+    if (a->d_feature && !(a->use_sh && v == n))
+      GS_CUDA(cudaMemsetAsync(a->d_feature, 0, sizeof(float) * n * F * D, side));
+    GS_CUDA(cudaEventRecord(aux->fills_done, side));
 
-  // ---- raster backward ----
-  if (v > 0) {
-    if (a->grad_points && !a->grad_points_preset) GS_CUDA(cudaMemsetAsync(a->grad_points, 0, sizeof(float) * 7 * v, stream));
-    if (a->grad_features && !a->grad_features_preset) GS_CUDA(cudaMemsetAsync(a->grad_features, 0, sizeof(float) * F * v, stream));
-    if (a->d_image != nullptr) {
-      if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
-      float *gp = need_geom ? a->grad_points : nullptr, *gf = a->d_feature ? a->grad_features : nullptr;
-      if (a->d_image_strided)
-        GS_TRY(gs_raster_bwd_digest_strided_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image,
-                                                a->d_image_strides, v, a->k, a->width, a->height, F, &a->config, gp, gf,
-                                                a->heuristic, stream));
-      else
-        GS_TRY(gs_raster_bwd_digest_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image, v, a->k,
-                                        a->width, a->height, F, &a->config, gp, gf, a->heuristic, stream));
-      if (a->ev_raster_end != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_end, stream));
+    // ---- raster backward ----
+    if (v > 0) {
+      if (a->grad_points && !a->grad_points_preset) GS_CUDA(cudaMemsetAsync(a->grad_points, 0, sizeof(float) * 7 * v, stream));
+      if (a->grad_features && !a->grad_features_preset) GS_CUDA(cudaMemsetAsync(a->grad_features, 0, sizeof(float) * F * v, stream));
+      if (a->d_image != nullptr) {
+        if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
+        float *gp = need_geom ? a->grad_points : nullptr, *gf = a->grad_features;
+        if (a->d_image_strided)
+          GS_TRY(gs_raster_bwd_digest_strided_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image,
+                                                  a->d_image_strides, v, a->k, a->width, a->height, F, &a->config, gp, gf,
+                                                  a->heuristic, stream));
+        else
+          GS_TRY(gs_raster_bwd_digest_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image, v, a->k,
+                                          a->width, a->height, F, &a->config, gp, gf, a->heuristic, stream));
+        if (a->ev_raster_end != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_end, stream));
+      }
     }
-    GS_CUDA(cudaEventRecord(aux->raster_done, stream));
+    // the fills must have landed before anything later on `stream` (this call or the next phase) accumulates
+    GS_CUDA(cudaStreamWaitEvent(stream, aux->fills_done, 0));
+  }
 
+  if (v > 0) {
     // ---- auxiliary stream: feature gradient (SH backward / row scatter) ----
-    if (a->d_feature) {
+    if ((phases & GS_BWD_FEATURE) && a->d_feature) {
+      GS_CUDA(cudaEventRecord(aux->raster_done, stream));
       GS_CUDA(cudaStreamWaitEvent(side, aux->raster_done, 0));
       if (a->use_sh) {
         GS_TRY(gs_sh_bwd_f32(a->feature, a->position, a->indexes, a->camera_pos, a->grad_features, a->features, v, F,
-                             a->sh_degree, 1, a->d_feature, nullptr, nullptr, side));
+                             a->sh_degree, 1, a->d_feature, nullptr, a->d_camera_pos, side));
       } else {
         const int64_t total = v * F;
         scatter_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, side>>>(a->grad_features, a->indexes, v, F,
@@ -279,8 +332,7 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
     }
 
     // ---- caller's stream: projection backward ----
-    GS_CUDA(cudaStreamWaitEvent(stream, aux->fills_done, 0));
-    if (need_geom) {
+    if ((phases & GS_BWD_PROJECT) && need_geom) {
       const float *dd = a->d_depths;
       if (dd == nullptr) {   // no incoming depth gradient: a zeroed column from library scratch
         float *z = (float *)stream_workspace(stream, sizeof(float) * v);
@@ -294,8 +346,5 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
                                 a->d_T_camera_world, a->d_projection, stream));
     }
   }
-  // ---- join ----
-  GS_CUDA(cudaEventRecord(aux->bwd_join, side));
-  GS_CUDA(cudaStreamWaitEvent(stream, aux->bwd_join, 0));
-  return GS_OK;
+  return GS_OK;   // ~SideJoin: the caller's stream waits for the auxiliary stream
 }

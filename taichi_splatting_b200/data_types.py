@@ -28,10 +28,11 @@ class RasterConfig:
   compute_point_heuristic: bool = False
   compute_visibility: bool = False
   median_threshold: float = 0.25
-  # Not in the reference (its forward never stops early): the forward pass stops compositing a
-  # pixel once its remaining transmittance is <= this value, bounding the image error by eps * max|feature|.
-  # 0 reproduces the reference exactly.
-  forward_saturate_eps: float = 1e-6
+  # Not in the reference (its forward never stops early): opt-in early-out -- the forward pass stops
+  # compositing a pixel once its remaining transmittance is <= this value, bounding the image error by
+  # eps * max|feature| (and truncating per-point visibility by the same weights).  The default 0 reproduces the
+  # reference exactly (drop-in parity).
+  forward_saturate_eps: float = 0.0
 
   def __post_init__(self):
     assert self.tile_size in (8, 16, 32), f"tile_size {self.tile_size} not supported (8, 16, 32)"

@@ -89,14 +89,44 @@ def apply_with_ndc(position, log_scaling, rotation, alpha_logit, T_camera_world,
                                 image_size, depth_range, blur_cov, clamp_margin, alpha_threshold, True)
 
 
+def camera_position_vjp(T_camera_world: torch.Tensor, camera_pos: torch.Tensor, d_camera_pos: torch.Tensor) -> torch.Tensor:
+  """Gradient of the loss w.r.t. the (4,4) view matrix through camera_pos = inverse(T)[:3,3] (the reference gets it
+  from autograd through torch.inverse, perspective/params.py:78-80).  With T = [A t; r s] evaluated at r = 0, s = 1:
+  c = -A^-1 t, so dL/dt = u = -A^-T g, dL/dA = u c^T, dL/dr = -(g.c) c^T, dL/ds = -(g.c).  Tiny 3x3 work on the device,
+  no host synchronisation (inv_ex skips the error read-back)."""
+  T = T_camera_world.detach()
+  g, c = d_camera_pos.to(T.dtype), camera_pos.detach().to(T.dtype)
+  inv_A, _ = torch.linalg.inv_ex(T[:3, :3])
+  u = -(inv_A.t() @ g)
+  gc = torch.dot(g, c)
+  d_T = torch.zeros_like(T)
+  d_T[:3, :3] = torch.outer(u, c)
+  d_T[:3, 3] = u
+  d_T[3, :3] = -gc * c
+  d_T[3, 3] = -gc
+  return d_T
+
+
+class _CameraPosition(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, T_camera_world):
+    _lib.require_cuda(T_camera_world=T_camera_world)
+    T = T_camera_world.detach().contiguous()
+    out = torch.empty((3,), dtype=T.dtype, device=T.device)
+    _lib.call(f"gs_camera_position_{_lib.suffix(T.dtype)}", _lib.ptr(T), _lib.ptr(out), _lib.stream_ptr(T.device))
+    ctx.save_for_backward(T, out)
+    return out
+
+  @staticmethod
+  def backward(ctx, d_out):
+    T, out = ctx.saved_tensors
+    return camera_position_vjp(T, out, d_out)
+
+
 def camera_position(T_camera_world: torch.Tensor) -> torch.Tensor:
-  """World-space camera centre of a (4,4) view matrix, computed on the device in one tiny kernel (no gradient).
-  Same value as CameraParams.camera_position (torch.inverse) without the LU kernels and their host sync."""
-  _lib.require_cuda(T_camera_world=T_camera_world)
-  T = T_camera_world.detach().contiguous()
-  out = torch.empty((3,), dtype=T.dtype, device=T.device)
-  _lib.call(f"gs_camera_position_{_lib.suffix(T.dtype)}", _lib.ptr(T), _lib.ptr(out), _lib.stream_ptr(T.device))
-  return out
+  """World-space camera centre of a (4,4) view matrix, computed on the device in one tiny kernel.  Same value and
+  same gradient as CameraParams.camera_position (torch.inverse(T)[:3,3]) without the LU kernels and their host sync."""
+  return _CameraPosition.apply(T_camera_world)
 
 
 @beartype

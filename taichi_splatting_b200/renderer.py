@@ -10,7 +10,7 @@ from . import _lib
 from .data_types import Gaussians3D, RasterConfig
 from .mapper.tile_mapper import ORDERING, bin_and_sort, bin_and_sort_binned, map_to_tiles
 from .perspective import CameraParams
-from .perspective.projection import apply_with_ndc, camera_position
+from .perspective.projection import apply_with_ndc, camera_position, camera_position_vjp
 from .rasterizer.function import (fused_median_supported, rasterize_with_tiles,
                                   rasterize_with_tiles_and_median, tuned_supported)
 from .rendering import RenderedPoints, Rendering, ndc_depth
@@ -273,7 +273,10 @@ class _RenderFunction(torch.autograd.Function):
              for t, i in ((position, 0), (log_scaling, 1), (rotation, 2), (alpha_logit, 3), (T_camera_world, 5), (projection, 6))]
     d_feature = torch.empty_like(feature) if need[4] else None
     grad_g = d_g2d.clone() if d_g2d is not None else torch.empty_like(g2d)
-    grad_f = d_features.clone() if d_features is not None else torch.empty_like(features)
+    grad_f = (d_features.clone() if d_features is not None else torch.empty_like(features)) if need[4] else None
+    # the SH view directions depend on the camera centre inverse(T)[:3,3]: when the pose is trained, its gradient
+    # through them is chained into d_T_camera_world below (reference: autograd through camera_params.camera_position)
+    d_cam = torch.empty((3,), dtype=torch.float32, device=device) if (use_sh and need[4] and need[5]) else None
     ev_bwd = _next_event_pair("bwd")
     # dL/dimage goes to the kernel with whatever strides autograd gave it (an expanded scalar after image.sum(), a
     # permuted CHW tensor, ...): no .contiguous() copy of a full image
@@ -286,11 +289,14 @@ class _RenderFunction(torch.autograd.Function):
         ptr(indexes), ptr(features), ptr(image), ptr(cam_pos), ptr(digest), ptr(overlap_to_point), ptr(ranges),
         (d_image.data_ptr() if strided else ptr(d_image)) if d_image is not None else None,
         ptr(d_depths.contiguous()) if d_depths is not None else None,
-        ptr(grad_g), ptr(grad_f), int(d_g2d is not None), int(d_features is not None),
+        ptr(grad_g), ptr(grad_f), int(d_g2d is not None), int(d_features is not None and grad_f is not None),
         ptr(heuristic) if config.compute_point_heuristic else None,
         *[ptr(g) for g in grads], ptr(d_feature),
-        _event_handle(ev_bwd[0] if ev_bwd else None), _event_handle(ev_bwd[1] if ev_bwd else None), d_image_strides)
+        _event_handle(ev_bwd[0] if ev_bwd else None), _event_handle(ev_bwd[1] if ev_bwd else None), d_image_strides,
+        ptr(d_cam), 0)
     _lib.call("gs_render_backward_f32", args, _lib.stream_ptr(device))
+    if d_cam is not None:
+      grads[4] += camera_position_vjp(T_camera_world, cam_pos, d_cam)
     return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)
 
   @staticmethod
@@ -343,10 +349,12 @@ class _RenderFunction(torch.autograd.Function):
     # ---- features: SH backward; view-parallel runs launch the exchange of the SH-gradient factors instead, so that
     # the all-gather overlaps the projection backward ----
     pending = exchange.start(feature, indexes, features, grad_f, cam_pos) if exchange is not None else None
+    d_cam = None
     if sh_direct and v > 0:
       if use_sh:
+        d_cam = torch.zeros((3,), dtype=dtype, device=device) if need[5] else None
         call(f"gs_sh_bwd_{sfx}", ptr(feature), ptr(position), ptr(indexes), ptr(cam_pos), ptr(grad_f), ptr(features), v,
-             feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, None, stream)
+             feature.shape[1], check_sh_degree(feature), 1, ptr(d_feature), None, ptr(d_cam), stream)
       else:
         d_feature.index_copy_(0, indexes, grad_f)
 
@@ -356,6 +364,8 @@ class _RenderFunction(torch.autograd.Function):
       call(f"gs_project_bwd_{sfx}", ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(T_camera_world),
            ptr(projection), ptr(indexes), v, w, h, blur, margin, ptr(grad_g), ptr(dd), *[ptr(g) for g in grads], stream)
 
+    if d_cam is not None:   # SH view directions -> camera centre -> view matrix (reference: autograd through torch.inverse)
+      grads[4] += camera_position_vjp(T_camera_world, cam_pos, d_cam)
     if exchange is not None:
       d_feature = exchange.finish(pending, feature, position, check_sh_degree(feature))
     return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)

@@ -102,3 +102,25 @@ def test_two_gpu_sharding_matches_single_gpu():
     p.join(timeout=600)
     assert p.exitcode == 0
   assert dict(results) == {0: "ok", 1: "ok"}
+
+
+def test_second_device_in_one_process():
+  """A single process driving two GPUs: tensors on cuda:1 while cuda:0 is the current device.  Kernel attributes
+  (the backward's > 48 KB dynamic shared memory), library scratch and the auxiliary streams are per device, so the
+  call must run on the tensors' device (_lib.call switches to it) -- this failed with 'invalid argument' before."""
+  if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+    pytest.skip("needs >= 2 CUDA devices")
+  import taichi_splatting_b200 as ts
+  torch.cuda.set_device(0)
+  cfg = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True)
+  R = torch.rand((208, 320, 3), generator=torch.Generator().manual_seed(0))
+  grads, images = [], []
+  for dev in ("cuda:0", "cuda:1", "cuda:0"):
+    cloud, cam, _ = _scene(ts, torch.device(dev))
+    out = ts.render_gaussians(cloud, cam, cfg, use_sh=True, render_median_depth=True)
+    (out.image * R.to(dev)).sum().backward()
+    assert torch.cuda.current_device() == 0
+    grads.append(cloud.position.grad.cpu())
+    images.append(out.image.detach().cpu())
+  assert torch.equal(images[0], images[1]) and torch.equal(images[0], images[2])
+  assert _rel(grads[1], grads[0]) < 1e-5 and _rel(grads[2], grads[0]) < 1e-5
