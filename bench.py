@@ -206,7 +206,7 @@ def run_ours(args):
     return pairs
   bwd_pairs = event_pairs(args.steps)
   renderer.raster_events["bwd"] = list(bwd_pairs)
-  prof = _lib.Profiler(only={"gs_raster_bwd_digest_f32"})
+  prof = _lib.Profiler(only={"gs_raster_bwd_packed_f32"})
   _lib.profiler = prof
   with ClockSampler(local_rank) as clocks:
     total_ms = timed(lambda: step(gaussians, camera), args.steps)
@@ -214,8 +214,8 @@ def run_ours(args):
   renderer.raster_events["bwd"] = None
   torch.cuda.synchronize()
   stage_hot = {k: sum(v) / len(v) for k, v in prof.stage_ms().items()}
-  if "gs_raster_bwd_digest_f32" not in stage_hot:
-    stage_hot["gs_raster_bwd_digest_f32"] = sum(a_.elapsed_time(b_) for a_, b_ in bwd_pairs) / len(bwd_pairs)
+  if "gs_raster_bwd_packed_f32" not in stage_hot:
+    stage_hot["gs_raster_bwd_packed_f32"] = sum(a_.elapsed_time(b_) for a_, b_ in bwd_pairs) / len(bwd_pairs)
   launches = prof.launches
   ms_per_step = total_ms / args.steps
   value = world * n / (ms_per_step * 1e-3)
@@ -306,7 +306,7 @@ def run_ours(args):
   P = w * h
   stage_bytes, total_bytes = algorithmic_bytes(n, V, K, P, T, 3, (deg + 1)**2)
   hbm_peak, peak_kind = peaks()
-  bwd_ms = stage_hot.get("gs_raster_bwd_digest_f32")
+  bwd_ms = stage_hot.get("gs_raster_bwd_packed_f32")
   traffic, limiter = None, None
   try:
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:

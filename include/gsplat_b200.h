@@ -274,6 +274,32 @@ int gs_raster_bwd_digest_strided_f32(const void *digest, const int32_t *tile_ran
                                      int32_t height, int32_t num_features, const gs_raster_config *config,
                                      float *grad_points, float *grad_features, float *point_heuristic, void *stream);
 
+/* ---- Packed per-overlap records + bulk-copy staged raster kernels -----------------------------------------------
+ * Replaces the synchronous cooperative gather in front of every batch of the reference's raster kernels
+ * (rasterizer/forward.py:67-83, rasterizer/backward.py:100-118).  gs_raster_pack_f32 runs once per frame after the
+ * sort: for every sorted overlap k it resolves overlap_to_point[k], recentres the splat on its tile and classifies it
+ * against the tile's four 8x8 pixel blocks (exact test), writing
+ *   records[k]        48 bytes (1..3 features) | 64 bytes (4 features): {tx0,ty0,ux,wx | uy,wy,alpha,depth | f.., mask}
+ *   flush_records[k]  16 bytes (backward only; may be NULL): {mean - tile centre, 1/sigma.x, 1/sigma.y}
+ * so that a tile's batch is one contiguous range, which gs_raster_fwd_packed_f32 / gs_raster_bwd_packed_f32 fetch with
+ * cp.async.bulk (TMA engine) + mbarrier into double-buffered shared memory while the previous batch is swept.
+ * Results are those of gs_raster_fwd_digest_f32 / gs_raster_bwd_digest_f32 (which pack into library scratch and call
+ * these).  Alpha blending, tile_size 16, no antialias, 1..4 features; buffers 16-byte aligned. */
+int gs_raster_pack_bytes(int64_t k, int32_t num_features, size_t *record_bytes, size_t *flush_bytes);
+int gs_raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t k,
+                       int32_t width, int32_t height, int32_t num_features, void *records, void *flush_records,
+                       void *stream);
+int gs_raster_fwd_packed_f32(const void *records, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t v,
+                             int64_t k, int32_t width, int32_t height, int32_t num_features,
+                             const gs_raster_config *config, double median_threshold, float *image, float *image_alpha,
+                             float *visibility, float *median_image /* or NULL */, void *stream);
+int gs_raster_bwd_packed_f32(const void *records, const void *flush_records, const int32_t *tile_ranges,
+                             const int32_t *overlap_to_point, const float *image, const float *grad_image,
+                             const int64_t *grad_image_strides_host /* (y, x, channel) element strides, or NULL */,
+                             int64_t v, int64_t k, int32_t width, int32_t height, int32_t num_features,
+                             const gs_raster_config *config, float *grad_points, float *grad_features,
+                             float *point_heuristic, void *stream);
+
 /* ---- Whole-frame host drivers (renderer.py:22-108 in one call per phase) --------------------------------------
  * The per-stage entry points above mirror the reference's operators one to one, and a Python caller that chains
  * them spends 20-30 us of interpreter time per launch: at the bench workload the front end (13 short kernels,
@@ -288,7 +314,8 @@ int gs_raster_bwd_digest_strided_f32(const void *digest, const int32_t *tile_ran
  *   stage A : project+cull -> [host read V] -> compacted write (+ndc) -> depth order -> tile counts -> scan ->
  *             [host read K];  on the library's auxiliary stream, beside the mapper chain: SH evaluation (or the
  *             feature gather), zero fills of visibility / heuristic, the raster digest.
- *   stage B : ordered key emit -> stable tile sort -> tile ranges -> join the auxiliary stream -> raster forward.
+ *   stage B : ordered key emit -> stable tile sort -> tile ranges -> join the auxiliary stream -> raster pack ->
+ *             raster forward (bulk-copy staged).
  *             (ordering = GS_ORDERING_BINNED: per-tile counts / slot emission / per-tile shared-memory sort
  *             instead, falling back to the above when a tile is too crowded for it.)
  *   backward: zero fills (auxiliary stream, beside the raster backward) -> raster backward -> projection backward
@@ -328,6 +355,9 @@ typedef struct gs_render_args {
   void *ev_raster_start, *ev_raster_end;
   int32_t *tile_counts, *tile_cursor;   /* (tiles) each: binned ordering */
   int32_t *tile_totals;                 /* (2) */
+  /* K-sized like tiles / overlap_to_point (same capacity), set before stage B: packed per-overlap raster records
+   * (gs_raster_pack_bytes) written by stage B and kept for the backward.  NULL: stage B packs into library scratch. */
+  void *records, *flush_records;
 } gs_render_args;
 
 int gs_render_stage_a_f32(const gs_render_args *args, int64_t *v_out, int64_t *k_out, int64_t *max_per_tile_out,
@@ -357,6 +387,7 @@ typedef struct gs_render_bwd_args {
   const float *features, *image, *camera_pos;
   const void *digest;
   const int32_t *overlap_to_point, *tile_ranges;
+  const void *records, *flush_records;   /* stage B's packed records, or NULL (re-packed from the digest) */
   /* incoming gradients */
   const float *d_image;            /* (H,W,channels): contiguous, or any element strides with d_image_strided */
   const float *d_depths;           /* (v,1) or NULL (zero) */

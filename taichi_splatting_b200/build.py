@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 VARIANT = os.environ.get("GS_BUILD_VARIANT", "")          # experiments: alternate .so + extra -D flags
 OBJ = PKG / "csrc" / ("build" + VARIANT)
 LIB = PKG / f"libgsplat_b200{VARIANT}.so"
-SOURCES = ["api.cu", "projection.cu", "sh.cu", "mapper.cu", "raster_generic.cu", "raster_digest.cu", "raster_fwd.cu", "raster_bwd.cu", "raster_bwd_t.cu", "render.cu", "optim.cu"]
+SOURCES = ["api.cu", "projection.cu", "sh.cu", "mapper.cu", "raster_generic.cu", "raster_digest.cu", "raster_pack.cu", "raster_fwd.cu", "raster_fwd_bulk.cu", "raster_bwd.cu", "raster_bwd_t.cu", "render.cu", "optim.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr",

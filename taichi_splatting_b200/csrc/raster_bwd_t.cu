@@ -21,8 +21,14 @@
 //
 // Per splat iteration the data pipe is charged 3 x 2.69 (records) + 0.7 (list) + 2 x 4.04 (panel stores) + 2 x 4.04
 // (panel loads) + ~2 (shuffles, atomics) = ~27 cycles; the kernel runs at 81 % of that pipe.
+//
+// Staging: the tile's records come from raster_pack.cu (sorted order, tile-centred, block mask included), one
+// `cp.async.bulk` per batch of 128 into one of two shared-memory buffers, signalled on an mbarrier (bulk_copy.cuh);
+// batch b+1 is in flight while batch b is swept.  The reference stages with a synchronous cooperative gather
+// (backward.py:100-118); the first version of this kernel gathered 64-byte digests and classified the blocks itself.
 #include <atomic>
 
+#include "bulk_copy.cuh"
 #include "packed_f32.cuh"
 #include "raster_common.cuh"
 
@@ -68,29 +74,32 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+template <int RECW>
 struct Smem {
-  float4 a[kBatch + 1];            // tx0, ty0, ux, wx                 (+1: null record that pads the hit lists)
-  float4 b[kBatch + 1];            // uy, wy, alpha, unused
-  float4 f[kBatch + 1];
-  float4 c[kBatch];                // mean - tile centre, 1/sigma.x, 1/sigma.y  (read by the flush only)
+  // two landing buffers of raster_pack records {tx0, ty0, ux, wx | uy, wy, alpha, depth | features (, mask)}
+  // (+1: null record that pads the hit lists)
+  float4 rec[2][(kBatch + 1) * RECW];
   float acc[kBatch * kAcc];
   float4 panel0[kWarps][kChunk * kRow];  // per-warp [splat][lane] scratch: {S, D, sum G^2, sum |G dpdf/dmean|}
   float4 panel1[kWarps][kChunk * kRow];  //                                 {sum weight dL/dimage[c]}
-  // byte offsets (16 j) of the staged records a warp must visit; entry k lives at index k + 3, so that the eight
+  // byte offsets (16 RECW j) of the records a warp must visit; entry k lives at index k + 3, so that the eight
   // "next" entries of a chunk (k = h0 + 1 .. h0 + 8) are two aligned 16-byte loads
   alignas(16) unsigned list[kWarps][kBatch + kChunk + 4];
-  unsigned char mask[kBatch];
+  alignas(8) uint64_t full[2];           // mbarriers: "buffer b holds its batch"
   int warp_done[kWarps];
 };
 
-template <int F, bool GP, bool GF, bool HEUR>
+template <int F, bool GP, bool GF, bool HEUR, int RECW>
 __global__ void __launch_bounds__(kThreads, GS_BWDT_MIN_BLOCKS)
-raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
+raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict__ flush_records,
+                    const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
                     const float *__restrict__ image, const float *__restrict__ grad_image, RasterParams<float> P,
                     float *__restrict__ grad_points, float *__restrict__ grad_features,
                     float *__restrict__ heuristic) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+  Smem<RECW> &sm = *reinterpret_cast<Smem<RECW> *>(smem_raw);
+  constexpr unsigned kRecBytes = 16u * RECW;
+  constexpr int kMaskWord = RECW == 3 ? 11 : 12;
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
@@ -137,9 +146,6 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
   const int slot_base = kChunk == 8 ? ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0)
                                     : ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0);
   float4 *panel0 = sm.panel0[warp], *panel1 = sm.panel1[warp];
-  const unsigned char *rec_a = reinterpret_cast<const unsigned char *>(sm.a);
-  const unsigned char *rec_b = reinterpret_cast<const unsigned char *>(sm.b);
-  const unsigned char *rec_f = reinterpret_cast<const unsigned char *>(sm.f);
   float g_scalar[2][4];               // dL/dimage of the two pixels as scalars (same registers as gpix2)
 #pragma unroll
   for (int c = 0; c < 4; ++c) { g_scalar[0][c] = 0.f; g_scalar[1][c] = 0.f; }
@@ -147,74 +153,61 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
   for (int c = 0; c < F; ++c) upk(gpix2[c], g_scalar[0][c], g_scalar[1][c]);
 
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
-  if (lane == 0) sm.warp_done[warp] = 0;
-  if (tid == 0) {
-    sm.a[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
-    sm.b[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
-    sm.f[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  const int nbatches = (end - start + kBatch - 1) / kBatch;
 
-  for (int base = start; base < end; base += kBatch) {
-    const int nb = min(kBatch, end - base);
-    __syncthreads();
+  auto issue = [&](int b) {   // thread 0 only: arm the barrier with the byte count, hand the range to the copy engine
+    const int base = start + b * kBatch;
+    const uint32_t bytes = (uint32_t)min(kBatch, end - base) * kRecBytes;
+    mbar_arrive_expect_tx(&sm.full[b & 1], bytes);
+    bulk_copy_g2s(sm.rec[b & 1], records + (int64_t)RECW * base, bytes, &sm.full[b & 1]);
+  };
+
+  if (tid == 0) {
+    mbar_init(&sm.full[0], 1);
+    mbar_init(&sm.full[1], 1);
+    mbar_fence_init();
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int q = 0; q < RECW; ++q) sm.rec[b][kBatch * RECW + q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nbatches > 0) issue(0);
+    if (nbatches > 1) issue(1);
+  }
+  if (lane == 0) sm.warp_done[warp] = 0;
+#pragma unroll
+  for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
+
+  for (int b = 0; b < nbatches; ++b) {
+    const int buf = b & 1;
+    const int base = start + b * kBatch, nb = min(kBatch, end - base);
+    __syncthreads();   // previous flush finished: its buffer is free, accumulators are zero again, warp_done visible
     {
       int all_done = 1;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) all_done &= sm.warp_done[w];
+      // refill the buffer the previous batch just released (the flush still read its records, so not earlier); the
+      // copy of batch b + 1 then runs beside the sweep of batch b.  Every issued copy is waited for before the CTA
+      // exits: when every pixel is saturated nothing new is issued and batch b is the last one in flight.
+      if (tid == 0 && b >= 1 && b + 1 < nbatches && !all_done) issue(b + 1);
+      mbar_wait(&sm.full[buf], (uint32_t)(b >> 1) & 1u);   // the batch has landed
       if (all_done) break;
     }
-    // ---- stage (thread j owns splat j of the batch, and flushes it at the end) ----
-    int my_id = -1;
-    if (tid < nb) {
-      my_id = overlap_to_point[base + tid];
-      const float4 *rec = digest + 4 * (int64_t)my_id;
-      const float4 R0 = __ldg(rec), R1 = __ldg(rec + 1), R2 = __ldg(rec + 2), R3 = __ldg(rec + 3);
-      const float ux = R0.z, wx = R0.w, uy = R1.x, wy = R1.y, rcs = R3.x;
-      const float ddx = R0.x - ((float)tile_x0 + 8.0f), ddy = R0.y - ((float)tile_y0 + 8.0f);
-      const float tx0 = -fmaf(ux, ddx, uy * ddy), ty0 = -fmaf(wx, ddx, wy * ddy);
-      sm.a[tid] = make_float4(tx0, ty0, ux, wx);
-      sm.b[tid] = R1;
-      sm.f[tid] = R2;
-      sm.c[tid] = make_float4(ddx, ddy, R3.y, R3.z);
-      unsigned mask = 0;
-      if (rcs > 0.f) {   // same block test as the forward kernel (raster_fwd.cu: stage_splat)
-        const float sc = rcs * rcp_approx(fabsf(ux * wy - uy * wx)) * 1.0001f;
-        const float ex = sc * sqrtf(fmaf(uy, uy, wy * wy)), ey = sc * sqrtf(fmaf(ux, ux, wx * wx));
-        const float hu = (fabsf(ux) + fabsf(uy)) * 3.5f + rcs;
-        const float hw = (fabsf(wx) + fabsf(wy)) * 3.5f + rcs;
-#if GS_EXACT_CULL
-        const SupportMetric metric = support_metric(ux, wx, uy, wy, rcs);
-#endif
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          const float ox = (w & 1) ? 4.0f : -4.0f, oy = (w >> 1) ? 4.0f : -4.0f;   // block centre - tile centre
-          const float t0x = fmaf(ux, ox, fmaf(uy, oy, tx0)), t0y = fmaf(wx, ox, fmaf(wy, oy, ty0));
-          bool hit = (fabsf(ox - ddx) - 3.5f <= ex) && (fabsf(oy - ddy) - 3.5f <= ey) && (fabsf(t0x) <= hu) && (fabsf(t0y) <= hw);
-#if GS_EXACT_CULL
-          if (hit) hit = block_reaches_support(metric, t0x, t0y, ux, wx, uy, wy);
-#endif
-          mask |= hit ? (1u << w) : 0u;
-        }
-      }
-      sm.mask[tid] = (unsigned char)mask;
-#pragma unroll
-      for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
-    }
-    __syncthreads();
+    const unsigned char *rec = reinterpret_cast<const unsigned char *>(sm.rec[buf]);
+    const unsigned *words = reinterpret_cast<const unsigned *>(sm.rec[buf]);
 
     // ---- per-warp ordered hit list, padded to a multiple of the chunk with the null record ----
     int nhit = 0;
     if (!__all_sync(full, trans[0] <= t_min && trans[1] <= t_min)) {
       for (int c = 0; c < nb; c += 32) {
         int j = c + lane;
-        bool hit = j < nb && ((sm.mask[j] >> warp) & 1);
+        bool hit = j < nb && ((words[j * (4 * RECW) + kMaskWord] >> warp) & 1u);
         unsigned bal = __ballot_sync(full, hit);
-        if (hit) sm.list[warp][3 + nhit + __popc(bal & ((1u << lane) - 1))] = 16u * (unsigned)j;
+        if (hit) sm.list[warp][3 + nhit + __popc(bal & ((1u << lane) - 1))] = kRecBytes * (unsigned)j;
         nhit += __popc(bal);
       }
     }
     // pad with the null record (also when the list is empty: the sweep prefetches entry 0 unconditionally)
-    if (lane <= kChunk) sm.list[warp][3 + nhit + lane] = 16u * (unsigned)kBatch;
+    if (lane <= kChunk) sm.list[warp][3 + nhit + lane] = kRecBytes * (unsigned)kBatch;
     __syncwarp();
 #ifdef GS_COUNT
     if (lane == 0) { atomicAdd(&g_count[1], (unsigned long long)nhit); if (warp == 0) atomicAdd(&g_count[3], 1ull); }
@@ -225,9 +218,9 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
     float4 A, B, fv;
     {
       const unsigned off = sm.list[warp][3];
-      A = *reinterpret_cast<const float4 *>(rec_a + off);
-      B = *reinterpret_cast<const float4 *>(rec_b + off);
-      fv = *reinterpret_cast<const float4 *>(rec_f + off);
+      A = *reinterpret_cast<const float4 *>(rec + off);
+      B = *reinterpret_cast<const float4 *>(rec + off + 16);
+      fv = *reinterpret_cast<const float4 *>(rec + off + 32);
     }
     for (int h0 = 0; h0 < nhit; h0 += kChunk) {
       // ---- phase 1: lane = two pixels; 8 splats in depth order ----
@@ -238,9 +231,9 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
 #pragma unroll kUnroll1
       for (int u = 0; u < kChunk; ++u) {
         const unsigned off_next = next_off[u];
-        const float4 An = *reinterpret_cast<const float4 *>(rec_a + off_next);
-        const float4 Bn = *reinterpret_cast<const float4 *>(rec_b + off_next);
-        const float4 fn = *reinterpret_cast<const float4 *>(rec_f + off_next);
+        const float4 An = *reinterpret_cast<const float4 *>(rec + off_next);
+        const float4 Bn = *reinterpret_cast<const float4 *>(rec + off_next + 16);
+        const float4 fn = *reinterpret_cast<const float4 *>(rec + off_next + 32);
         const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
         const f32x2 uw_x = pk(A.z, A.w), uw_y = pk(B.x, B.y);
         const f32x2 tbase = fma2(lx2, uw_x, pk(A.x, A.y));
@@ -369,7 +362,7 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
         for (int i = 0; i < 3; ++i) v[i] += __shfl_xor_sync(full, v[i], 4);
       }
       if (h0 + s < nhit && (kChunk == 8 || (lane & 4) == 0)) {
-        float *dst = sm.acc + (sm.list[warp][3 + h0 + s] >> 4) * kAcc + slot_base;
+        float *dst = sm.acc + (sm.list[warp][3 + h0 + s] / kRecBytes) * kAcc + slot_base;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
           if (v[i] != 0.f) atomicAdd(dst + i, v[i]);
@@ -379,7 +372,7 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
     }
     if (__all_sync(full, trans[0] <= t_min && trans[1] <= t_min) && lane == 0) sm.warp_done[warp] = 1;
 
-    // ---- flush: one thread per staged splat ----
+    // ---- flush: one thread per splat of the batch ----
     __syncthreads();
     if (tid < nb) {
       float S[12];
@@ -387,9 +380,13 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
 #pragma unroll
       for (int c = 0; c < 12; ++c) { S[c] = sm.acc[tid * kAcc + c]; any |= (S[c] != 0.f); }
       if (any) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
+        const int my_id = __ldg(overlap_to_point + base + tid);
         if (GP) {
           // shift the tile-centred moments to the splat mean: d = l + c
-          const float4 RA = sm.a[tid], RB = sm.b[tid], RC = sm.c[tid];
+          const float4 RA = sm.rec[buf][tid * RECW], RB = sm.rec[buf][tid * RECW + 1];
+          const float4 RC = __ldg(flush_records + base + tid);   // mean - tile centre, 1/sigma.x, 1/sigma.y
           const float inv_k = 1.0f / kExpScale;
           const float cx = -RC.x, cy = -RC.y, s_isx = RC.z, s_isy = RC.w, s_alpha = RB.z;
           const float M0 = S[0], Lx = S[1], Ly = S[2], Lxx = S[3], Lxy = S[4], Lyy = S[5];
@@ -427,19 +424,20 @@ raster_bwd_t_kernel(const float4 *__restrict__ digest, const int32_t *__restrict
 }  // namespace bwdt
 
 template <int F>
-int launch_bwd_transpose(const float4 *digest, const int32_t *ranges, const int32_t *o2p,
+int launch_bwd_transpose(const float4 *records, const float4 *flush_records, const int32_t *ranges, const int32_t *o2p,
                          const float *image, const float *grad_image, const RasterParams<float> &P, int tiles,
                          float *grad_points, float *grad_features, float *heuristic, cudaStream_t stream) {
+  constexpr int RECW = F <= 3 ? 3 : 4;
   const bool gp = grad_points != nullptr, gf = grad_features != nullptr, he = P.heur && heuristic != nullptr;
 #ifndef GS_BWDT_EXTRA_SMEM
 #define GS_BWDT_EXTRA_SMEM 0   // profiling aid: extra dynamic shared memory per CTA lowers the residency
 #endif
-  const size_t smem = sizeof(bwdt::Smem) + GS_BWDT_EXTRA_SMEM;
+  const size_t smem = sizeof(bwdt::Smem<RECW>) + GS_BWDT_EXTRA_SMEM;
   int dev = 0;
   GS_CUDA(cudaGetDevice(&dev));
 #define GS_BWDT(GP_, GF_, HE_)                                                                                  \
   do {                                                                                                          \
-    auto kern = bwdt::raster_bwd_t_kernel<F, GP_, GF_, HE_>;                                                    \
+    auto kern = bwdt::raster_bwd_t_kernel<F, GP_, GF_, HE_, RECW>;                                              \
     /* the attribute is per device (and per kernel instantiation): one bit per device, set once each */         \
     static std::atomic<uint64_t> configured{0};                                                                 \
     const uint64_t dev_bit = 1ull << (dev & 63);                                                                \
@@ -447,7 +445,7 @@ int launch_bwd_transpose(const float4 *digest, const int32_t *ranges, const int3
       GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
       configured.fetch_or(dev_bit, std::memory_order_release);                                                  \
     }                                                                                                           \
-    kern<<<tiles, bwdt::kThreads, smem, stream>>>(digest, ranges, o2p, image, grad_image, P,                    \
+    kern<<<tiles, bwdt::kThreads, smem, stream>>>(records, flush_records, ranges, o2p, image, grad_image, P,    \
                                                 grad_points, grad_features, heuristic);                         \
   } while (0)
   if (gp && gf && he) GS_BWDT(true, true, true);
@@ -463,13 +461,13 @@ int launch_bwd_transpose(const float4 *digest, const int32_t *ranges, const int3
   return GS_OK;
 }
 
-template int launch_bwd_transpose<1>(const float4 *, const int32_t *, const int32_t *, const float *, const float *,
+template int launch_bwd_transpose<1>(const float4 *, const float4 *, const int32_t *, const int32_t *, const float *, const float *,
                                      const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
-template int launch_bwd_transpose<2>(const float4 *, const int32_t *, const int32_t *, const float *, const float *,
+template int launch_bwd_transpose<2>(const float4 *, const float4 *, const int32_t *, const int32_t *, const float *, const float *,
                                      const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
-template int launch_bwd_transpose<3>(const float4 *, const int32_t *, const int32_t *, const float *, const float *,
+template int launch_bwd_transpose<3>(const float4 *, const float4 *, const int32_t *, const int32_t *, const float *, const float *,
                                      const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
-template int launch_bwd_transpose<4>(const float4 *, const int32_t *, const int32_t *, const float *, const float *,
+template int launch_bwd_transpose<4>(const float4 *, const float4 *, const int32_t *, const int32_t *, const float *, const float *,
                                      const RasterParams<float> &, int, float *, float *, float *, cudaStream_t);
 
 }  // namespace gs

@@ -22,6 +22,8 @@
 //     once every pixel of the warp has crossed the median limit; per-splat visibility (sum of blend weights over
 //     pixels) is reduced 16 splats at a time with one transposed butterfly (16 shuffles per 16 splats instead of 5
 //     per splat) and one shared-memory atomic instruction per 16 splats.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "packed_f32.cuh"
@@ -324,6 +326,19 @@ static int launch_fwd(const float4 *digest, const int32_t *ranges, const int32_t
 
 int raster_digest_f32(const float *points, const float *features, const float *depths, int64_t v, int F,
                       double alpha_threshold, void *digest, cudaStream_t stream);   // raster_digest.cu
+int raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t k,
+                    int32_t width, int32_t height, int32_t F, void *records, void *flush, cudaStream_t stream);   // raster_pack.cu
+
+// GS_RASTER_STAGING=gather keeps the in-kernel digest gather of this file for alpha blending too (A/B switch);
+// default: packed records + bulk-copy staging (raster_pack.cu, raster_fwd_bulk.cu).
+static bool use_bulk_staging() {
+  static int choice = -1;
+  if (choice < 0) {
+    const char *e = getenv("GS_RASTER_STAGING");
+    choice = (e != nullptr && e[0] == 'g') ? 0 : 1;
+  }
+  return choice == 1;
+}
 
 static bool fwd_tuned(const gs_raster_config *cfg, int F) {
   return cfg->tile_size == kTile && !cfg->antialias && F >= 1 && F <= 4;
@@ -331,9 +346,10 @@ static bool fwd_tuned(const gs_raster_config *cfg, int F) {
 
 // Tuned kernel on a ready digest.
 static int raster_fwd_digest_impl(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point,
-                                  int64_t v, int32_t width, int32_t height, int32_t F, const gs_raster_config *cfg,
-                                  double median_threshold, float *image, float *image_alpha, float *visibility,
-                                  float *median_image, cudaStream_t stream) {
+                                  int64_t v, int64_t k, int32_t width, int32_t height, int32_t F,
+                                  const gs_raster_config *cfg, double median_threshold, float *image,
+                                  float *image_alpha, float *visibility, float *median_image, cudaStream_t stream,
+                                  size_t prefix_bytes = 0) {
   GS_CHECK_ARG(cfg != nullptr, "raster_fwd: config is NULL");
   GS_CHECK_ARG(width > 0 && height > 0, "raster_fwd: bad image size %dx%d", width, height);
   GS_CHECK_ARG(!cfg->compute_visibility || visibility != nullptr || v == 0, "raster_fwd: compute_visibility needs a visibility buffer");
@@ -342,6 +358,19 @@ static int raster_fwd_digest_impl(const void *digest, const int32_t *tile_ranges
     set_error("raster_fwd (digest): needs tile_size 16, no antialias, 1..4 features%s",
               median_image != nullptr ? ", alpha blending for the fused median" : "");
     return GS_ERR_UNSUPPORTED;
+  }
+  if (cfg->use_alpha_blending && use_bulk_staging()) {
+    // packed per-overlap records into library scratch (after `prefix_bytes` the caller already uses), bulk-copy kernel
+    void *records = nullptr;
+    if (k > 0) {
+      unsigned char *ws = (unsigned char *)stream_workspace(stream, prefix_bytes + (size_t)k * (F <= 3 ? 48 : 64));
+      if (ws == nullptr) return GS_ERR_CUDA;
+      records = ws + prefix_bytes;
+      int rc = raster_pack_f32(digest, tile_ranges, overlap_to_point, k, width, height, F, records, nullptr, stream);
+      if (rc != GS_OK) return rc;
+    }
+    return gs_raster_fwd_packed_f32(records, tile_ranges, overlap_to_point, v, k, width, height, F, cfg,
+                                    median_threshold, image, image_alpha, visibility, median_image, stream);
   }
   RasterParams<float> P = make_params<float>(cfg, width, height, F);
   const int tiles = P.tiles_wide * ((height + kTile - 1) / kTile);
@@ -358,7 +387,7 @@ static int raster_fwd_digest_impl(const void *digest, const int32_t *tile_ranges
 // Reference-shaped entry (raw (V,7) points + features): digest into library scratch, then the tuned kernel;
 // other configurations go to the generic kernel.
 static int raster_fwd_f32_impl(const float *points, const float *features, const float *depths,
-                               const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t v, int32_t width,
+                               const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t v, int64_t k, int32_t width,
                                int32_t height, int32_t F, const gs_raster_config *cfg, double median_threshold,
                                float *image, float *image_alpha, float *visibility, float *median_image,
                                cudaStream_t stream) {
@@ -372,14 +401,16 @@ static int raster_fwd_f32_impl(const float *points, const float *features, const
   }
   if (fast) {
     void *digest = nullptr;
+    const size_t digest_bytes = align_up((size_t)v * 64, 256);
     if (v > 0) {
-      digest = stream_workspace(stream, (size_t)v * 64);
+      // digest first, the packed records follow it in the same scratch
+      digest = stream_workspace(stream, digest_bytes + (size_t)k * (F <= 3 ? 48 : 64));
       if (digest == nullptr) return GS_ERR_CUDA;
       int rc = raster_digest_f32(points, features, depths, v, F, cfg->alpha_threshold, digest, stream);
       if (rc != GS_OK) return rc;
     }
-    return raster_fwd_digest_impl(digest, tile_ranges, overlap_to_point, v, width, height, F, cfg, median_threshold,
-                                  image, image_alpha, visibility, median_image, stream);
+    return raster_fwd_digest_impl(digest, tile_ranges, overlap_to_point, v, k, width, height, F, cfg, median_threshold,
+                                  image, image_alpha, visibility, median_image, stream, digest_bytes);
   }
   return raster_fwd_generic<float>(points, features, tile_ranges, overlap_to_point, width, height, F, cfg, image,
                                    image_alpha, visibility, stream);
@@ -391,8 +422,7 @@ extern "C" int gs_raster_fwd_f32(const float *points, const float *features, con
                                  const int32_t *overlap_to_point, int64_t v, int64_t k, int32_t width,
                                  int32_t height, int32_t F, const gs_raster_config *cfg, float *image,
                                  float *image_alpha, float *visibility, void *stream_) {
-  (void)k;
-  return gs::raster_fwd_f32_impl(points, features, nullptr, tile_ranges, overlap_to_point, v, width, height, F, cfg, 0.0,
+  return gs::raster_fwd_f32_impl(points, features, nullptr, tile_ranges, overlap_to_point, v, k, width, height, F, cfg, 0.0,
                                  image, image_alpha, visibility, nullptr, (cudaStream_t)stream_);
 }
 
@@ -401,9 +431,8 @@ extern "C" int gs_raster_fwd_median_f32(const float *points, const float *featur
                                         int64_t k, int32_t width, int32_t height, int32_t F,
                                         const gs_raster_config *cfg, double median_threshold, float *image,
                                         float *image_alpha, float *visibility, float *median_image, void *stream_) {
-  (void)k;
   GS_CHECK_ARG(median_image != nullptr && (depths != nullptr || v == 0), "raster_fwd_median: depths / median_image is NULL");
-  return gs::raster_fwd_f32_impl(points, features, depths, tile_ranges, overlap_to_point, v, width, height, F, cfg,
+  return gs::raster_fwd_f32_impl(points, features, depths, tile_ranges, overlap_to_point, v, k, width, height, F, cfg,
                                  median_threshold, image, image_alpha, visibility, median_image, (cudaStream_t)stream_);
 }
 
@@ -412,8 +441,7 @@ extern "C" int gs_raster_fwd_digest_f32(const void *digest, const int32_t *tile_
                                         int32_t height, int32_t F, const gs_raster_config *cfg,
                                         double median_threshold, float *image, float *image_alpha, float *visibility,
                                         float *median_image, void *stream_) {
-  (void)k;
-  return gs::raster_fwd_digest_impl(digest, tile_ranges, overlap_to_point, v, width, height, F, cfg, median_threshold,
+  return gs::raster_fwd_digest_impl(digest, tile_ranges, overlap_to_point, v, k, width, height, F, cfg, median_threshold,
                                     image, image_alpha, visibility, median_image, (cudaStream_t)stream_);
 }
 

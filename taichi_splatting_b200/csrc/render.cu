@@ -237,10 +237,20 @@ static int gs::stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64
     GS_TRY(gs_tile_ranges_from_tiles(tiles + k_stride, k, a->tile_ranges, num_tiles, stream));
   }
   GS_CUDA(cudaStreamWaitEvent(stream, aux->side_done, 0));
-  if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
-  GS_TRY(gs_raster_fwd_digest_f32(a->digest, a->tile_ranges, sorted_o2p, v, k, a->width, a->height, a->channels,
-                                  &a->config, a->median_threshold, a->image, a->image_alpha, a->visibility,
-                                  a->want_median ? a->median_image : nullptr, stream));
+  if (a->records != nullptr || k == 0) {
+    // per-overlap records in sorted order (kept for the backward), then the bulk-copy staged forward kernel
+    GS_TRY(gs_raster_pack_f32(a->digest, a->tile_ranges, sorted_o2p, k, a->width, a->height, a->channels, a->records,
+                              a->flush_records, stream));
+    if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
+    GS_TRY(gs_raster_fwd_packed_f32(a->records, a->tile_ranges, sorted_o2p, v, k, a->width, a->height, a->channels,
+                                    &a->config, a->median_threshold, a->image, a->image_alpha, a->visibility,
+                                    a->want_median ? a->median_image : nullptr, stream));
+  } else {
+    if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
+    GS_TRY(gs_raster_fwd_digest_f32(a->digest, a->tile_ranges, sorted_o2p, v, k, a->width, a->height, a->channels,
+                                    &a->config, a->median_threshold, a->image, a->image_alpha, a->visibility,
+                                    a->want_median ? a->median_image : nullptr, stream));
+  }
   if (a->ev_raster_end != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_end, stream));
   return GS_OK;
 }
@@ -301,7 +311,11 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
       if (a->d_image != nullptr) {
         if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
         float *gp = need_geom ? a->grad_points : nullptr, *gf = a->grad_features;
-        if (a->d_image_strided)
+        if (a->records != nullptr && a->flush_records != nullptr)
+          GS_TRY(gs_raster_bwd_packed_f32(a->records, a->flush_records, a->tile_ranges, a->overlap_to_point, a->image,
+                                          a->d_image, a->d_image_strided ? a->d_image_strides : nullptr, v, a->k,
+                                          a->width, a->height, F, &a->config, gp, gf, a->heuristic, stream));
+        else if (a->d_image_strided)
           GS_TRY(gs_raster_bwd_digest_strided_f32(a->digest, a->tile_ranges, a->overlap_to_point, a->image, a->d_image,
                                                   a->d_image_strides, v, a->k, a->width, a->height, F, &a->config, gp, gf,
                                                   a->heuristic, stream));

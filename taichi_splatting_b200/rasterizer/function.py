@@ -42,6 +42,22 @@ def make_digest(gaussians2d: torch.Tensor, features: torch.Tensor, depths: Optio
   return digest
 
 
+def pack_records(digest: torch.Tensor, ranges: torch.Tensor, overlap_to_point: torch.Tensor, image_size,
+                 num_features: int):
+  """Per-overlap raster records in sorted order (gs_raster_pack_f32): (K, 12 | 16) sweep records and (K, 4) flush
+  records.  Written once per frame after the sort; the forward and backward kernels fetch a tile's batch from them
+  with one bulk copy (TMA engine) instead of gathering through overlap_to_point."""
+  k = overlap_to_point.shape[0]
+  device = digest.device
+  records = torch.empty((k, 12 if num_features <= 3 else 16), dtype=torch.float32, device=device)
+  flush_records = torch.empty((k, 4), dtype=torch.float32, device=device)
+  if k > 0:
+    _lib.call("gs_raster_pack_f32", _lib.ptr(digest), _lib.ptr(ranges), _lib.ptr(overlap_to_point), k,
+              int(image_size[0]), int(image_size[1]), num_features, _lib.ptr(records), _lib.ptr(flush_records),
+              _lib.stream_ptr(device))
+  return records, flush_records
+
+
 def rasterize_with_tiles_and_median(gaussians2d, features, depths, overlap_to_point, tile_overlap_ranges, image_size,
                                     config):
   """rasterize_with_tiles plus the reference's median-depth pass (renderer.py:77-82) -> (RasterOut, median (H,W)).
@@ -89,21 +105,29 @@ class _RasterFunction(torch.autograd.Function):
     vis_ptr = _lib.ptr(visibility) if config.compute_visibility else None
     median = None
     digest = torch.empty((0, 16), dtype=torch.float32, device=device)
+    packed = None
     if median_depths is not None:
       assert fused_median_supported(config, F, dtype), "fused median depth: unsupported configuration"
       median = torch.empty((h, w), dtype=dtype, device=device)
     if tuned_supported(config, F, dtype):
       d = median_depths.detach().contiguous().view(-1) if median_depths is not None else None
       digest = make_digest(g, f, d, config)
-      _lib.call("gs_raster_fwd_digest_f32", _lib.ptr(digest), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0], w, h,
-                F, cfg, float(config.median_threshold), _lib.ptr(image), _lib.ptr(alpha), vis_ptr,
-                _lib.ptr(median) if median is not None else None, _lib.stream_ptr(device))
+      if config.use_alpha_blending:
+        packed = pack_records(digest, ranges, o2p, (w, h), F)
+        _lib.call("gs_raster_fwd_packed_f32", _lib.ptr(packed[0]), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0], w,
+                  h, F, cfg, float(config.median_threshold), _lib.ptr(image), _lib.ptr(alpha), vis_ptr,
+                  _lib.ptr(median) if median is not None else None, _lib.stream_ptr(device))
+      else:
+        _lib.call("gs_raster_fwd_digest_f32", _lib.ptr(digest), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0], w, h,
+                  F, cfg, float(config.median_threshold), _lib.ptr(image), _lib.ptr(alpha), vis_ptr,
+                  _lib.ptr(median) if median is not None else None, _lib.stream_ptr(device))
     else:
       _lib.call(f"gs_raster_fwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), v, o2p.shape[0],
                 w, h, F, cfg, _lib.ptr(image), _lib.ptr(alpha), vis_ptr, _lib.stream_ptr(device))
 
     ctx.config, ctx.image_size = config, (w, h)
     ctx.heuristic = heuristic
+    ctx.packed = packed
     ctx.save_for_backward(g, f, image, o2p, ranges, digest)
     ctx.mark_non_differentiable(alpha, heuristic, visibility)
     if median is not None:
@@ -122,7 +146,11 @@ class _RasterFunction(torch.autograd.Function):
     if need_g or need_f or config.compute_point_heuristic:
       cfg = _lib.raster_config_c(config)
       heur_ptr = _lib.ptr(ctx.heuristic) if config.compute_point_heuristic else None
-      if tuned_supported(config, f.shape[1], g.dtype):
+      if ctx.packed is not None:
+        _lib.call("gs_raster_bwd_packed_f32", _lib.ptr(ctx.packed[0]), _lib.ptr(ctx.packed[1]), _lib.ptr(ranges),
+                  _lib.ptr(o2p), _lib.ptr(image), _lib.ptr(grad_image.contiguous()), None, g.shape[0], o2p.shape[0], w,
+                  h, f.shape[1], cfg, _lib.ptr(grad_g), _lib.ptr(grad_f), heur_ptr, _lib.stream_ptr(g.device))
+      elif tuned_supported(config, f.shape[1], g.dtype):
         _lib.call("gs_raster_bwd_digest_f32", _lib.ptr(digest), _lib.ptr(ranges), _lib.ptr(o2p), _lib.ptr(image),
                   _lib.ptr(grad_image.contiguous()), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
                   _lib.ptr(grad_g), _lib.ptr(grad_f), heur_ptr, _lib.stream_ptr(g.device))

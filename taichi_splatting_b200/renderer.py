@@ -11,7 +11,7 @@ from .data_types import Gaussians3D, RasterConfig
 from .mapper.tile_mapper import ORDERING, bin_and_sort, bin_and_sort_binned, map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import apply_with_ndc, camera_position, camera_position_vjp
-from .rasterizer.function import (fused_median_supported, rasterize_with_tiles,
+from .rasterizer.function import (fused_median_supported, pack_records, rasterize_with_tiles,
                                   rasterize_with_tiles_and_median, tuned_supported)
 from .rendering import RenderedPoints, Rendering, ndc_depth
 from .spherical_harmonics import check_sh_degree, evaluate_sh_at
@@ -146,12 +146,19 @@ class _RenderFunction(torch.autograd.Function):
     # ---- rasteriser (+ fused median depth) ----
     vis_ptr = ptr(visibility) if config.compute_visibility else None
     cfg = _lib.raster_config_c(config)
+    packed = None
     if use_digest:
       if fused_median:
         median = torch.empty((h, w), dtype=dtype, device=device)
-      call("gs_raster_fwd_digest_f32", ptr(digest), ptr(ranges), ptr(overlap_to_point), v, k, w, h, F, cfg,
-           float(config.median_threshold), ptr(image), ptr(alpha), vis_ptr, ptr(median) if fused_median else None,
-           stream)
+      if config.use_alpha_blending:   # per-overlap records in sorted order, then the bulk-copy staged kernel
+        packed = pack_records(digest, ranges, overlap_to_point, (w, h), F)
+        call("gs_raster_fwd_packed_f32", ptr(packed[0]), ptr(ranges), ptr(overlap_to_point), v, k, w, h, F, cfg,
+             float(config.median_threshold), ptr(image), ptr(alpha), vis_ptr, ptr(median) if fused_median else None,
+             stream)
+      else:
+        call("gs_raster_fwd_digest_f32", ptr(digest), ptr(ranges), ptr(overlap_to_point), v, k, w, h, F, cfg,
+             float(config.median_threshold), ptr(image), ptr(alpha), vis_ptr, ptr(median) if fused_median else None,
+             stream)
     else:
       call(f"gs_raster_fwd_{sfx}", ptr(g2d), ptr(features), ptr(ranges), ptr(overlap_to_point), v, k, w, h, F, cfg,
            ptr(image), ptr(alpha), vis_ptr, stream)
@@ -165,6 +172,7 @@ class _RenderFunction(torch.autograd.Function):
 
     ctx.save_for_backward(*tensors, feature_c, indexes, g2d, features, image, overlap_to_point, ranges,
                           cam_pos if cam_pos is not None else torch.empty(0, device=device), digest)
+    ctx.packed = packed
     ctx.meta = (config, (w, h), blur, margin, bool(use_sh), heuristic)
     ctx.sh_exchange = sh_exchange
     ctx.set_materialize_grads(False)
@@ -220,16 +228,19 @@ class _RenderFunction(torch.autograd.Function):
         ws[0].data_ptr(), ws[0].numel(), ws[1].data_ptr(), ws[1].numel(), ws[2].data_ptr(), ws[2].numel(),
         ptr(image), ptr(alpha), ptr(median) if render_median_depth else None, ptr(tile_ranges),
         _event_handle(ev_fwd[0] if ev_fwd else None), _event_handle(ev_fwd[1] if ev_fwd else None),
-        ptr(tile_counts), ptr(tile_cursor), ptr(tile_totals))
+        ptr(tile_counts), ptr(tile_cursor), ptr(tile_totals), None, None)
+    rec_cols = 12 if F <= 3 else 16   # floats per packed raster record (gs_raster_pack_bytes)
     # K-sized buffers: sized from the previous frame on this device (+25 %), so that the driver can go from the
     # host read of K straight into key emission; if K outgrew them, allocate exactly and run stage B from here
     v_out, k_out, max_out, done = _lib.c_int64(), _lib.c_int64(), _lib.c_int64(), _lib.c_int32()
     nbytes = _lib.c_size_t()
     dev_key = device.index if device.index is not None else torch.cuda.current_device()
     cap = _k_capacity.get(dev_key, 0)
-    tiles = o2p = ws_sort = None
+    tiles = o2p = ws_sort = records = flush_records = None
     if cap > 0:
       tiles, o2p = empty((2, cap), i32), empty((2, cap), i32)
+      records, flush_records = empty((cap, rec_cols)), empty((cap, 4))
+      args.records, args.flush_records = ptr(records), ptr(flush_records)
       _lib.call("gs_sort_pairs_workspace_bytes", cap, 4, nbytes)
       ws_sort = _lib.workspace(nbytes.value, device)
     _lib.call("gs_render_forward_f32", args, cap, ptr(tiles), ptr(o2p), ws_sort.data_ptr() if cap > 0 else None,
@@ -240,12 +251,15 @@ class _RenderFunction(torch.autograd.Function):
     if not done.value:
       cap = k
       tiles, o2p = empty((2, k), i32), empty((2, k), i32)
+      records, flush_records = empty((k, rec_cols)), empty((k, 4))
+      args.records, args.flush_records = ptr(records), ptr(flush_records)
       _lib.call("gs_sort_pairs_workspace_bytes", k, 4, nbytes)
       ws_sort = _lib.workspace(nbytes.value, device)
       _lib.call("gs_render_stage_b_f32", args, v, k, int(max_out.value), k, ptr(tiles), ptr(o2p), ws_sort.data_ptr(),
                 ws_sort.numel(), stream)
     if o2p is None:   # first frame on this device and nothing to rasterise (K = 0): stage B ran with empty buffers
       tiles, o2p = empty((2, 0), i32), empty((2, 0), i32)
+      records, flush_records = empty((0, rec_cols)), empty((0, 4))
     _k_capacity[dev_key] = max(int(k * 1.25), 1024)
 
     g2d, depths, indexes, features, digest = g2d_n[:v], depths_n[:v], idx_n[:v], feat_n[:v], digest_n[:v]
@@ -253,6 +267,7 @@ class _RenderFunction(torch.autograd.Function):
     heuristic = heur_n[:v] if heur_n is not None else empty((0, 2))
     overlap_to_point, ranges = o2p[1, :k], tile_ranges.view(-1, 2)
     ctx.save_for_backward(*tensors, feature_c, indexes, g2d, features, image, overlap_to_point, ranges, cam_pos, digest)
+    ctx.packed = (records[:k], flush_records[:k])   # per-overlap raster records of this frame: the backward sweeps them again
     ctx.meta = (config, (w, h), float(config.blur_cov), float(config.clamp_margin), bool(use_sh), heuristic)
     ctx.sh_exchange = sh_exchange
     ctx.set_materialize_grads(False)
@@ -287,6 +302,7 @@ class _RenderFunction(torch.autograd.Function):
         n, v, k, w, h, blur, margin, int(use_sh), check_sh_degree(feature) if use_sh else 0, F, int(strided),
         _lib.raster_config_c(config),
         ptr(indexes), ptr(features), ptr(image), ptr(cam_pos), ptr(digest), ptr(overlap_to_point), ptr(ranges),
+        ptr(ctx.packed[0]), ptr(ctx.packed[1]),
         (d_image.data_ptr() if strided else ptr(d_image)) if d_image is not None else None,
         ptr(d_depths.contiguous()) if d_depths is not None else None,
         ptr(grad_g), ptr(grad_f), int(d_g2d is not None), int(d_features is not None and grad_f is not None),
@@ -337,7 +353,11 @@ class _RenderFunction(torch.autograd.Function):
     if d_image is not None and v > 0:
       out_ptrs = (ptr(grad_g) if need_geom else None, ptr(grad_f) if need[4] else None,
                   ptr(heuristic) if config.compute_point_heuristic else None)
-      if digest.shape[0] == v:
+      if getattr(ctx, "packed", None) is not None:
+        call("gs_raster_bwd_packed_f32", ptr(ctx.packed[0]), ptr(ctx.packed[1]), ptr(ranges), ptr(overlap_to_point),
+             ptr(image), ptr(d_image.contiguous()), None, v, overlap_to_point.shape[0], w, h, F,
+             _lib.raster_config_c(config), *out_ptrs, stream)
+      elif digest.shape[0] == v:
         call("gs_raster_bwd_digest_f32", ptr(digest), ptr(ranges), ptr(overlap_to_point), ptr(image),
              ptr(d_image.contiguous()), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
              *out_ptrs, stream)
