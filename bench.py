@@ -165,13 +165,13 @@ def run_ours(args):
     if world == 1:
       out = ts.render_gaussians(gauss, cam, config, use_sh=True, render_median_depth=True)
     else:
-      out = parallel.render_view_parallel(gauss, cam, config, use_sh=True, render_median_depth=True)
+      # view-parallel exchange, all of it inside the backward: the SH gradient is summed over ranks through its
+      # rank-1 factors (all-gather of 12 B / Gaussian / view, beside the projection backward), the geometry
+      # gradients by one NCCL all-reduce of a flat 44 B / Gaussian buffer (beside the SH rebuild kernel)
+      out = parallel.render_view_parallel(gauss, cam, config, use_sh=True, render_median_depth=True,
+                                          reduce_in_backward=True)
     loss = out.image.sum()
     loss.backward()
-    if world > 1:
-      # view-parallel exchange: the SH gradient was summed over ranks inside the backward through its rank-1
-      # factors (all-gather of 12 B / Gaussian / view); here the NCCL all-reduce of the geometry gradients
-      parallel.finish_view_parallel_backward(gauss, use_sh=True)
     return out, loss
 
   def barrier():
@@ -194,6 +194,28 @@ def run_ours(args):
 
   # ---- device-resident arm ----
   for _ in range(max(args.warmup, 3)):
+    out, _ = step(gaussians, camera)
+  # N > 1: the exchanged gradients of the warm-up step against the sum of single-GPU gradients of all N views,
+  # rendered one after the other on this rank (every rank checks; rank 0 reports)
+  multi_gpu_check = None
+  if world > 1:
+    got = {k: params[k].grad.detach().clone() for k in names}
+    want = {k: torch.zeros_like(params[k]) for k in names}
+    for r in range(world):
+      for t in params.values():
+        t.grad = None
+      o = ts.render_gaussians(gaussians, scenes.benchmark_camera((w, h), yaw_deg=2.0 * r).to(device=dev), config,
+                              use_sh=True, render_median_depth=True)
+      o.image.sum().backward()
+      for k in names:
+        want[k] += params[k].grad
+    errs = {k: float((got[k] - want[k]).abs().max() / want[k].abs().max().clamp_min(1e-30)) for k in names}
+    worst = torch.tensor([max(errs.values())], device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    multi_gpu_check = {"what": "exchanged gradients vs sum over the N views of single-GPU gradients, max relative error per tensor "
+                               "(this rank), worst over ranks", "per_tensor": {k: float(f"{v:.3g}") for k, v in errs.items()},
+                       "worst_over_ranks": float(f"{float(worst.item()):.3g}"), "tolerance": 2e-5}
+    assert float(worst.item()) < 2e-5, f"multi-GPU gradient mismatch: {errs}"
     out, _ = step(gaussians, camera)
   # The dominant kernel (raster backward) is timed live with CUDA events on its own stream: the whole-frame
   # driver records one (start, end) pair per step around that launch (N = 1); the staged view-parallel backward
@@ -339,15 +361,17 @@ def run_ours(args):
       "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
       "config": dict(WORKLOAD, forward_saturate_eps=args.fwd_eps, V=V, K=K, tiles=T, overlaps_per_tile=round(K / T, 1),
-                     parallelism=(f"view-parallel x{world}: replicated cloud, one view per rank; gradients summed over ranks by an NCCL "
-                                  "all-reduce (geometry, 44 B/Gaussian) + all-gather of the rank-1 SH-gradient factors "
-                                  "(12 B/Gaussian/view)") if world > 1 else "single GPU"),
+                     parallelism=(f"view-parallel x{world}: replicated cloud, one view per rank; gradients summed over ranks inside the "
+                                  "backward by an NCCL all-reduce (geometry, one flat 44 B/Gaussian buffer) + all-gather of the rank-1 "
+                                  "SH-gradient factors (12 B/Gaussian/view)") if world > 1 else "single GPU"),
       "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
               "note": ("per rank: 1/N row shard of the cloud + camera over PCIe, shards all-gathered over NVLink"
                        if world > 1 else "whole cloud + camera over PCIe") + "; double-buffered against compute"},
       "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "stages_ms": stages_ms,
   }
+  if multi_gpu_check is not None:
+    line["multi_gpu_check"] = multi_gpu_check
   if rank == 0 and world == 1:
     line["cpu_baseline"] = cpu_baseline(steps=2, warmup=1)   # warm: the first CPU step pays thread-pool start-up
   if rank == 0:

@@ -140,6 +140,11 @@ int gs_sh_bwd_f64(const double *params, const double *positions, const int64_t *
 int gs_sh_bwd_views_f32(const float *positions, const float *cam_positions, const float *g_all, int64_t n,
                         int32_t views, int32_t channels, int64_t view_stride, int32_t degree, float *d_params,
                         void *stream);
+/* This rank's contribution to that exchange in one launch: out (n * channels + 3) = dense (n, channels) colour
+ * gradients, zero where the colour is clamped (colour <= 0 or >= 1) or the Gaussian was culled, followed by the camera
+ * centre.  d_colours / colours (v, channels), indexes (v). */
+int gs_sh_pack_factors_f32(const float *colours, const float *d_colours, const int64_t *indexes,
+                           const float *camera_pos, int64_t v, int32_t channels, int64_t n, float *out, void *stream);
 
 /* ---- R3-R7: tile mapper -------------------------------------------------------------------------
  * gs_tile_count      replaces tile_overlaps_kernel (mapper/tile_mapper.py:75-86, grid_query.py:46-93)

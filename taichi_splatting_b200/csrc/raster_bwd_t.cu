@@ -230,6 +230,9 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
       constexpr int kUnroll1 = GS_BWDT_UNROLL;
 #pragma unroll kUnroll1
       for (int u = 0; u < kChunk; ++u) {
+#ifdef GS_BWDT_SKIP_PAD
+        if (u > 0 && h0 + u >= nhit) break;   // padded tail of the list: phase 2 ignores those rows anyway
+#endif
         const unsigned off_next = next_off[u];
         const float4 An = *reinterpret_cast<const float4 *>(rec + off_next);
         const float4 Bn = *reinterpret_cast<const float4 *>(rec + off_next + 16);

@@ -308,6 +308,36 @@ int sh_bwd(const real *params, const real *positions, const int64_t *indexes, co
                             unique_indexes, d_params, d_positions, d_camera_pos, (cudaStream_t)stream);         \
   }
 
+namespace gs {
+// This rank's factors for the view-parallel exchange, in one launch: out[idx * channels + c] = dL/dcolour[i, c] where
+// the colour is inside the clamp (0 < colour < 1; 0 otherwise, like the SH backward), rows of culled Gaussians zero,
+// camera centre in the last three words.  Replaces zeros + where + index_copy_ + slice assignment (four torch kernels).
+__global__ void __launch_bounds__(256)
+sh_pack_factors_kernel(const float *__restrict__ colours, const float *__restrict__ d_colours,
+                       const int64_t *__restrict__ indexes, const float *__restrict__ camera_pos, int64_t v,
+                       int channels, int64_t n, float *__restrict__ out) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < 3) out[n * channels + t] = camera_pos[t];
+  if (t >= v * channels) return;
+  const int64_t i = t / channels;
+  const float col = colours[t];
+  out[indexes[i] * channels + (t - i * channels)] = (col > 0.f && col < 1.f) ? d_colours[t] : 0.f;
+}
+}  // namespace gs
+
+extern "C" int gs_sh_pack_factors_f32(const float *colours, const float *d_colours, const int64_t *indexes,
+                                      const float *camera_pos, int64_t v, int32_t channels, int64_t n, float *out,
+                                      void *stream_) {
+  GS_CHECK_ARG(out != nullptr && camera_pos != nullptr && channels >= 1 && v >= 0 && v <= n, "sh_pack_factors: bad arguments");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (v < n) GS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n * channels, stream));   // rows of culled Gaussians
+  const int64_t total = v * channels > 3 ? v * channels : 3;
+  gs::sh_pack_factors_kernel<<<(unsigned)gs::ceil_div(total, 256), 256, 0, stream>>>(colours, d_colours, indexes, camera_pos,
+                                                                                      v, channels, n, out);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
 extern "C" int gs_sh_bwd_views_f32(const float *positions, const float *cam_positions, const float *g_all, int64_t n,
                                    int32_t views, int32_t channels, int64_t view_stride, int32_t degree,
                                    float *d_params, void *stream) {

@@ -52,6 +52,16 @@ def allreduce_gradients(tensors: Sequence[torch.Tensor], group=None, bucket: boo
     for w in works:
       w.wait()
     return
+  # gradients that already sit back to back in one allocation (the view-parallel backward writes the geometry
+  # gradients into one flat buffer): reduce that range in place, no concatenation and no copy back
+  adjacent = all(g.is_contiguous() and g.dtype == grads[0].dtype for g in grads) and all(
+      b.untyped_storage().data_ptr() == a.untyped_storage().data_ptr()
+      and b.data_ptr() == a.data_ptr() + a.numel() * a.element_size() for a, b in zip(grads, grads[1:]))
+  if adjacent:
+    total = sum(g.numel() for g in grads)
+    flat = grads[0].new_empty(0).set_(grads[0].untyped_storage(), grads[0].storage_offset(), (total,), (1,))
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return
   flat = torch.cat([g.reshape(-1) for g in grads])
   dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
   offset = 0
@@ -71,19 +81,24 @@ class ShGradientExchange:
   sum_w Y_w * g_w locally with one kernel (gs_sh_bwd_views_f32).  The result equals the all-reduced gradient up to
   fp32 summation order.  Used through `render_view_parallel`; the renderer's backward calls `sum_sh_gradient`."""
 
-  def __init__(self, group=None):
+  def __init__(self, group=None, reduce_geometry=False):
     self.group = group
     self.rank, self.world = world_info(group)
+    # reduce_geometry: the backward also all-reduces the geometry gradients (position, log_scaling, rotation,
+    # alpha_logit), written by the projection backward into ONE flat buffer, while the SH gradient is rebuilt -- the
+    # caller then needs no collective of its own after loss.backward()
+    self.reduce_geometry = reduce_geometry
 
   def start(self, sh_params, indexes, colours, d_colours, camera_pos):
-    """Launch the all-gather of this rank's factors (asynchronously: the caller overlaps the projection backward)."""
+    """Launch the all-gather of this rank's factors (asynchronously: the caller overlaps the projection backward).
+    One kernel packs them (gs_sh_pack_factors_f32: clamp mask, scatter to dense rows, camera centre)."""
+    from . import _lib
     n, channels = sh_params.shape[0], sh_params.shape[1]
     device = sh_params.device
     stride = n * channels + 3
-    local = torch.zeros((stride,), dtype=torch.float32, device=device)
-    masked = torch.where((colours > 0) & (colours < 1), d_colours, torch.zeros_like(d_colours))
-    local[:n * channels].view(n, channels).index_copy_(0, indexes, masked)
-    local[n * channels:] = camera_pos
+    local = torch.empty((stride,), dtype=torch.float32, device=device)
+    _lib.call("gs_sh_pack_factors_f32", _lib.ptr(colours), _lib.ptr(d_colours), _lib.ptr(indexes), _lib.ptr(camera_pos),
+              indexes.shape[0], channels, n, _lib.ptr(local), _lib.stream_ptr(device))
     gathered = torch.empty((self.world, stride), dtype=torch.float32, device=device)
     work = dist.all_gather_into_tensor(gathered, local, group=self.group, async_op=True)
     return (work, gathered, local, stride)
@@ -105,12 +120,19 @@ class ShGradientExchange:
 
 
 def render_view_parallel(gaussians, camera_params, config, use_sh: bool = False, use_depth16: bool = False,
-                         render_median_depth: bool = False, group=None):
-  """render_gaussians for this rank's view of a replicated cloud.  After `loss.backward()` call
-  `finish_view_parallel_backward(gaussians, use_sh, group)`: with SH the feature gradient has already been
-  summed over ranks inside the backward (ShGradientExchange); everything else is all-reduced there."""
+                         render_median_depth: bool = False, group=None, reduce_in_backward: bool = False):
+  """render_gaussians for this rank's view of a replicated cloud.
+
+  reduce_in_backward=False: after `loss.backward()` call `finish_view_parallel_backward(gaussians, use_sh, group)`:
+  with SH the feature gradient has already been summed over ranks inside the backward (ShGradientExchange);
+  everything else is all-reduced there.
+  reduce_in_backward=True (SH, fp32): the backward itself leaves every per-Gaussian gradient summed over ranks -- the
+  all-gather of the SH factors runs beside the projection backward, the all-reduce of the flat geometry-gradient
+  buffer beside the kernel that rebuilds the SH gradient -- and nothing remains to be called afterwards (gradients of
+  the camera, which differs per rank, stay local)."""
   from .renderer import _RenderFunction, _wrap_rendering
-  exchange = ShGradientExchange(group) if use_sh else None
+  exchange = ShGradientExchange(group, reduce_geometry=reduce_in_backward) if use_sh else None
+  assert exchange is not None or not reduce_in_backward, "reduce_in_backward needs use_sh=True"
   outs = _RenderFunction.apply(*gaussians.shape_tensors(), gaussians.feature, camera_params.T_camera_world,
                                camera_params.projection, camera_params, config, use_sh, use_depth16,
                                render_median_depth, exchange)

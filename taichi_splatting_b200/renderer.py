@@ -316,11 +316,64 @@ class _RenderFunction(torch.autograd.Function):
     return (grads[0], grads[1], grads[2], grads[3], d_feature, grads[4], grads[5], None, None, None, None, None, None)
 
   @staticmethod
+  def _backward_fused_view_parallel(ctx, d_image, d_g2d, d_depths, d_features):
+    """View-parallel backward through gs_render_backward_f32 in two phases with the exchange between them:
+       raster backward (C) -> pack + all-gather of the SH factors (NCCL, async) -> projection backward (C) into ONE
+       flat geometry buffer -> all-reduce of that buffer (NCCL, async) -> rebuild the SH gradient from the gathered
+       factors (overlaps the all-reduce) -> wait."""
+    import torch.distributed as dist
+    (position, log_scaling, rotation, alpha_logit, T_camera_world, projection, feature, indexes, g2d, features, image,
+     overlap_to_point, ranges, cam_pos, digest) = ctx.saved_tensors
+    config, (w, h), blur, margin, use_sh, heuristic = ctx.meta
+    exchange = ctx.sh_exchange
+    device = position.device
+    ptr = _lib.ptr
+    n, v, k, F = position.shape[0], g2d.shape[0], overlap_to_point.shape[0], features.shape[1]
+    need = ctx.needs_input_grad
+    # position | log_scaling | rotation | alpha_logit as consecutive blocks of one buffer: one collective, no
+    # concatenation and no copy back
+    flat = torch.empty((11 * n,), dtype=torch.float32, device=device)
+    geom = [flat[0:3 * n].view(n, 3), flat[3 * n:6 * n].view(n, 3), flat[6 * n:10 * n].view(n, 4), flat[10 * n:].view(n, 1)]
+    d_T = torch.empty_like(T_camera_world) if need[5] else None
+    d_proj = torch.empty_like(projection) if need[6] else None
+    grad_g = d_g2d.clone() if d_g2d is not None else torch.empty_like(g2d)
+    grad_f = d_features.clone() if d_features is not None else torch.empty_like(features)
+    ev_bwd = _next_event_pair("bwd")
+    strided = d_image is not None and not d_image.is_contiguous()
+    d_image_strides = (_lib.c_int64 * 3)(*(d_image.stride() if strided else (0, 0, 0)))
+    args = _lib.RenderBwdArgsC(
+        ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(feature), ptr(T_camera_world), ptr(projection),
+        n, v, k, w, h, blur, margin, int(use_sh), check_sh_degree(feature), F, int(strided),
+        _lib.raster_config_c(config),
+        ptr(indexes), ptr(features), ptr(image), ptr(cam_pos), ptr(digest), ptr(overlap_to_point), ptr(ranges),
+        ptr(ctx.packed[0]), ptr(ctx.packed[1]),
+        (d_image.data_ptr() if strided else ptr(d_image)) if d_image is not None else None,
+        ptr(d_depths.contiguous()) if d_depths is not None else None,
+        ptr(grad_g), ptr(grad_f), int(d_g2d is not None), int(d_features is not None),
+        ptr(heuristic) if config.compute_point_heuristic else None,
+        *[ptr(g) for g in geom], ptr(d_T), ptr(d_proj), None,
+        _event_handle(ev_bwd[0] if ev_bwd else None), _event_handle(ev_bwd[1] if ev_bwd else None), d_image_strides,
+        None, _lib.GS_BWD_RASTER)
+    stream = _lib.stream_ptr(device)
+    _lib.call("gs_render_backward_f32", args, stream)
+    pending = exchange.start(feature, indexes, features, grad_f, cam_pos)
+    args.phases = _lib.GS_BWD_PROJECT
+    _lib.call("gs_render_backward_f32", args, stream)
+    reduce = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=exchange.group, async_op=True) if exchange.reduce_geometry else None
+    d_feature = exchange.finish(pending, feature, position, check_sh_degree(feature))
+    if reduce is not None:
+      reduce.wait()
+    grads = [g if need[i] else None for i, g in enumerate(geom)]
+    return (grads[0], grads[1], grads[2], grads[3], d_feature, d_T, d_proj, None, None, None, None, None, None)
+
+  @staticmethod
   def backward(ctx, d_image, d_alpha, d_g2d, d_depths, d_indexes, d_features, *unused):
     if ctx.fused_host:
       exchange = ctx.sh_exchange
       if exchange is None or exchange.world <= 1 or not (ctx.needs_input_grad[4] and ctx.meta[4]):
         return _RenderFunction._backward_fused_host(ctx, d_image, d_g2d, d_depths, d_features)
+      if os.environ.get("GS_VIEW_PARALLEL_STAGED", "0") != "1":
+        return _RenderFunction._backward_fused_view_parallel(ctx, d_image, d_g2d, d_depths, d_features)
     (position, log_scaling, rotation, alpha_logit, T_camera_world, projection, feature, indexes, g2d, features, image,
      overlap_to_point, ranges, cam_pos, digest) = ctx.saved_tensors
     config, (w, h), blur, margin, use_sh, heuristic = ctx.meta
