@@ -188,6 +188,15 @@ int gs_tile_count_ordered(const float *gaussians, const int32_t *order, int64_t 
 int gs_tile_emit_ordered(const float *gaussians, const int32_t *order, const int32_t *cum, int64_t v,
                          int32_t width_padded, int32_t height_padded, int32_t tile_size, double alpha_threshold,
                          uint32_t *tile_keys, int32_t *overlap_to_point, void *stream);
+/* Same two kernels sharing ONE grid query: the count kernel also leaves a 16-byte hit record per Gaussian (tile span
+ * as 4 x u16 + a 64-bit mask of the accepted tiles in enumeration order; spans over 64 tiles are marked and
+ * re-queried), and the emit kernel walks the set bits instead of repeating the query.  hits: (v) x 16 bytes. */
+int gs_tile_count_ordered_hits(const float *gaussians, const int32_t *order, int64_t v, int32_t width_padded,
+                               int32_t height_padded, int32_t tile_size, double alpha_threshold, int32_t *counts,
+                               void *hits, void *stream);
+int gs_tile_emit_hits(const float *gaussians, const int32_t *order, const int32_t *cum, const void *hits, int64_t v,
+                      int32_t width_padded, int32_t height_padded, int32_t tile_size, double alpha_threshold,
+                      uint32_t *tile_keys, int32_t *overlap_to_point, void *stream);
 int gs_tile_ranges_from_tiles(const uint32_t *sorted_tiles, int64_t k, int32_t *tile_ranges, int64_t num_tiles,
                               void *stream);
 
@@ -294,6 +303,11 @@ int gs_raster_pack_bytes(int64_t k, int32_t num_features, size_t *record_bytes, 
 int gs_raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t k,
                        int32_t width, int32_t height, int32_t num_features, void *records, void *flush_records,
                        void *stream);
+/* Same records from the sorted tile-id array (one thread per overlap instead of one CTA per tile; the whole-frame
+ * driver has the array from its tile sort). */
+int gs_raster_pack_sorted_f32(const void *digest, const uint32_t *sorted_tiles, const int32_t *overlap_to_point,
+                              int64_t k, int32_t width, int32_t height, int32_t num_features, void *records,
+                              void *flush_records, void *stream);
 int gs_raster_fwd_packed_f32(const void *records, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t v,
                              int64_t k, int32_t width, int32_t height, int32_t num_features,
                              const gs_raster_config *config, double median_threshold, float *image, float *image_alpha,
@@ -363,6 +377,7 @@ typedef struct gs_render_args {
   /* K-sized like tiles / overlap_to_point (same capacity), set before stage B: packed per-overlap raster records
    * (gs_raster_pack_bytes) written by stage B and kept for the backward.  NULL: stage B packs into library scratch. */
   void *records, *flush_records;
+  void *hits;                           /* (n) x 16 bytes: hit records shared by tile count and emit, or NULL */
 } gs_render_args;
 
 int gs_render_stage_a_f32(const gs_render_args *args, int64_t *v_out, int64_t *k_out, int64_t *max_per_tile_out,

@@ -48,7 +48,7 @@ class RenderArgsC(ctypes.Structure):
       ("image", P), ("image_alpha", P), ("median_image", P), ("tile_ranges", P),
       ("ev_raster_start", P), ("ev_raster_end", P),
       ("tile_counts", P), ("tile_cursor", P), ("tile_totals", P),
-      ("records", P), ("flush_records", P),
+      ("records", P), ("flush_records", P), ("hits", P),
   ]
 
 
@@ -106,6 +106,8 @@ SIGNATURES = {
     "gs_tile_count_ordered": ([P, P, I64, I32, I32, I32, D, P, P], c_int32),
     "gs_tile_emit_ordered": ([P, P, P, I64, I32, I32, I32, D, P, P, P], c_int32),
     "gs_tile_ranges_from_tiles": ([P, I64, P, I64, P], c_int32),
+    "gs_tile_count_ordered_hits": ([P, P, I64, I32, I32, I32, D, P, P, P], c_int32),
+    "gs_tile_emit_hits": ([P, P, P, P, I64, I32, I32, I32, D, P, P, P], c_int32),
     "gs_tile_bin_count": ([P, I64, I32, I32, I32, D, P, P], c_int32),
     "gs_tile_bin_offsets": ([P, I64, P, P, P, P, P], c_int32),
     "gs_tile_bin_emit": ([P, P, I64, I32, I32, I32, D, I32, P, P, P], c_int32),
@@ -121,6 +123,7 @@ SIGNATURES = {
     "gs_raster_bwd_digest_strided_f32": ([P, P, P, P, P, POINTER(I64), I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
     "gs_raster_pack_bytes": ([I64, I32, POINTER(SZ), POINTER(SZ)], c_int32),
     "gs_raster_pack_f32": ([P, P, P, I64, I32, I32, I32, P, P, P], c_int32),
+    "gs_raster_pack_sorted_f32": ([P, P, P, I64, I32, I32, I32, P, P, P], c_int32),
     "gs_raster_fwd_packed_f32": ([P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_packed_f32": ([P, P, P, P, P, P, POINTER(I64), I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
     "gs_render_stage_a_f32": ([POINTER(RenderArgsC), POINTER(I64), POINTER(I64), POINTER(I64), P], c_int32),
@@ -170,11 +173,11 @@ OWN_KERNELS = {
     "gs_project_cull_f32": 1, "gs_project_cull_f64": 1, "gs_project_write_f32": 1, "gs_project_write_f64": 1,
     "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_camera_position_f32": 1, "gs_camera_position_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
     "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_sh_bwd_views_f32": 1, "gs_sh_pack_factors_f32": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
-    "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1,
+    "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1, "gs_tile_count_ordered_hits": 1, "gs_tile_emit_hits": 1,
     "gs_tile_ranges_from_tiles": 1, "gs_tile_bin_count": 1, "gs_tile_bin_offsets": 1, "gs_tile_bin_emit": 1,
     "gs_tile_bin_sort": 1, "gs_raster_fwd_f32": 3, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 3, "gs_raster_bwd_f32": 3,
     "gs_raster_bwd_f64": 1, "gs_raster_digest_f32": 1, "gs_raster_fwd_digest_f32": 2, "gs_raster_bwd_digest_f32": 2, "gs_raster_bwd_digest_strided_f32": 2,
-    "gs_raster_pack_f32": 1, "gs_raster_fwd_packed_f32": 1, "gs_raster_bwd_packed_f32": 1,
+    "gs_raster_pack_f32": 1, "gs_raster_pack_sorted_f32": 1, "gs_raster_fwd_packed_f32": 1, "gs_raster_bwd_packed_f32": 1,
     # whole-frame drivers: cull, camera position, write, SH, digest, depth key, count, scan tail | emit, ranges, raster |
     # raster backward, projection backward, SH backward
     "gs_render_stage_a_f32": 8, "gs_render_stage_b_f32": 4, "gs_render_backward_f32": 3, "gs_render_forward_f32": 8,

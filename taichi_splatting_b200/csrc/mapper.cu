@@ -154,6 +154,70 @@ tile_emit_ordered_kernel(const float *__restrict__ gaussians, const int32_t *__r
       }
 }
 
+// ---- count and emit sharing ONE grid query ----------------------------------------------------------------------
+// The count kernel already runs the OBB-vs-tile test for every tile of the Gaussian's span; instead of repeating the
+// whole query (7 scattered loads, an fp64 log, 4 divisions, up to 16 separating-axis tests) in the emit kernel, it
+// leaves a 16-byte "hit record" per Gaussian -- {minx, miny, spanx, spany} as 4 x u16 and a 64-bit mask of the accepted
+// tiles in enumeration order (x outer, y inner) -- and the emit kernel only walks the set bits.  Spans of more than 64
+// tiles (huge splats) are marked and re-queried.
+__global__ void __launch_bounds__(128)
+tile_count_hits_kernel(const float *__restrict__ gaussians, const int32_t *__restrict__ order, int64_t v, int w_pad,
+                       int h_pad, int ts, float thr, int32_t *__restrict__ counts, ulonglong2 *__restrict__ hits) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= v) return;
+  ObbQuery q = obb_grid_query(gaussians + 7 * (int64_t)order[r], w_pad, h_pad, ts, thr);
+  int c = 0;
+  unsigned long long mask = 0ull;
+  const bool small = q.spanx * q.spany <= 64;
+  int bit = 0;
+  for (int u = 0; u < q.spanx; ++u)
+    for (int w = 0; w < q.spany; ++w, ++bit)
+      if (test_tile(q, u, w, ts)) {
+        ++c;
+        if (small) mask |= 1ull << bit;
+      }
+  counts[r] = c;
+  const unsigned long long box = (unsigned long long)(unsigned)q.minx | ((unsigned long long)(unsigned)q.miny << 16) |
+                                 ((unsigned long long)(unsigned)(small ? q.spanx : 0xffff) << 32) |
+                                 ((unsigned long long)(unsigned)q.spany << 48);
+  hits[r] = make_ulonglong2(box, mask);
+}
+
+__global__ void __launch_bounds__(128)
+tile_emit_hits_kernel(const float *__restrict__ gaussians, const int32_t *__restrict__ order,
+                      const int32_t *__restrict__ cum, const ulonglong2 *__restrict__ hits, int64_t v, int w_pad,
+                      int h_pad, int ts, float thr, uint32_t *__restrict__ tile_keys,
+                      int32_t *__restrict__ overlap_to_point) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= v) return;
+  const int32_t i = order[r];
+  const ulonglong2 h = hits[r];
+  const int tiles_wide = w_pad / ts;
+  int64_t k = cum[r];
+  const int minx = (int)(h.x & 0xffff), miny = (int)((h.x >> 16) & 0xffff);
+  const int spanx = (int)((h.x >> 32) & 0xffff), spany = (int)((h.x >> 48) & 0xffff);
+  if (spanx == 0xffff) {   // span too large for the mask: run the query again
+    ObbQuery q = obb_grid_query(gaussians + 7 * (int64_t)i, w_pad, h_pad, ts, thr);
+    for (int u = 0; u < q.spanx; ++u)
+      for (int w = 0; w < q.spany; ++w)
+        if (test_tile(q, u, w, ts)) {
+          tile_keys[k] = (uint32_t)((q.minx + u) + (q.miny + w) * tiles_wide);
+          overlap_to_point[k] = i;
+          ++k;
+        }
+    return;
+  }
+  unsigned long long mask = h.y;
+  while (mask) {
+    const int bit = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    const int u = bit / spany, w = bit - u * spany;
+    tile_keys[k] = (uint32_t)((minx + u) + (miny + w) * tiles_wide);
+    overlap_to_point[k] = i;
+    ++k;
+  }
+}
+
 // ---- binned ordering (same final order again, no global sort at all) --------------------------------------------
 // The final order is: by tile, then by depth bits, ties by ascending Gaussian index.  Count overlaps per TILE
 // (atomics), turn the counts into tile offsets (= the tile ranges), let every overlap grab a slot inside its
@@ -461,6 +525,32 @@ extern "C" int gs_tile_emit_ordered(const float *gaussians, const int32_t *order
   if (v == 0) return GS_OK;
   gs::tile_emit_ordered_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
       gaussians, order, cum, v, w_pad, h_pad, ts, (float)alpha_threshold, tile_keys, overlap_to_point);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_tile_count_ordered_hits(const float *gaussians, const int32_t *order, int64_t v, int32_t w_pad,
+                                          int32_t h_pad, int32_t ts, double alpha_threshold, int32_t *counts,
+                                          void *hits, void *stream) {
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_count: image %dx%d not padded to tile %d", w_pad, h_pad, ts);
+  GS_CHECK_ARG((int64_t)(w_pad / ts) * (h_pad / ts) < 65535, "tile dimensions (%d, %d) exceed maximum tile count (16 bit id), try increasing tile_size", h_pad / ts, w_pad / ts);
+  GS_CHECK_ARG(hits != nullptr || v == 0, "tile_count_hits: hits is NULL");
+  GS_CHECK_ARG((reinterpret_cast<uintptr_t>(hits) & 15) == 0, "tile_count_hits: hits must be 16-byte aligned");
+  if (v == 0) return GS_OK;
+  gs::tile_count_hits_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
+      gaussians, order, v, w_pad, h_pad, ts, (float)alpha_threshold, counts, reinterpret_cast<ulonglong2 *>(hits));
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+extern "C" int gs_tile_emit_hits(const float *gaussians, const int32_t *order, const int32_t *cum, const void *hits,
+                                 int64_t v, int32_t w_pad, int32_t h_pad, int32_t ts, double alpha_threshold,
+                                 uint32_t *tile_keys, int32_t *overlap_to_point, void *stream) {
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_emit: image not padded to tile size");
+  if (v == 0) return GS_OK;
+  gs::tile_emit_hits_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
+      gaussians, order, cum, reinterpret_cast<const ulonglong2 *>(hits), v, w_pad, h_pad, ts, (float)alpha_threshold,
+      tile_keys, overlap_to_point);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

@@ -23,7 +23,8 @@ int launch_bwd_transpose(const float4 *records, const float4 *flush_records, con
 int raster_digest_f32(const float *points, const float *features, const float *depths, int64_t v, int F,
                       double alpha_threshold, void *digest, cudaStream_t stream);   // raster_digest.cu
 int raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t k,
-                    int32_t width, int32_t height, int32_t F, void *records, void *flush, cudaStream_t stream);   // raster_pack.cu
+                    int32_t width, int32_t height, int32_t F, void *records, void *flush, cudaStream_t stream,
+                    const uint32_t *sorted_tiles = nullptr);   // raster_pack.cu
 
 constexpr int kTileB = 16;
 

@@ -66,8 +66,10 @@ __device__ __forceinline__ SupportMetric support_metric(float ux, float wx, floa
   SupportMetric m;
   m.G11 = fmaf(ux, ux, wx * wx); m.G22 = fmaf(uy, uy, wy * wy); m.G12 = fmaf(ux, uy, wx * wy);
   const float det_u = ux * wy - uy * wx;
-  m.idet = 1.0f / fmaxf(det_u * det_u, 1e-30f);
-  m.i11 = 1.0f / fmaxf(m.G11, 1e-30f); m.i22 = 1.0f / fmaxf(m.G22, 1e-30f);
+  // approximate reciprocals (1 ulp-level error): they only place the minimiser, and r2 carries a 2e-4 relative margin
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(m.idet) : "f"(fmaxf(det_u * det_u, 1e-30f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(m.i11) : "f"(fmaxf(m.G11, 1e-30f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(m.i22) : "f"(fmaxf(m.G22, 1e-30f)));
   m.r2 = rcs * rcs * 1.0002f + 1e-5f;
   return m;
 }

@@ -327,7 +327,8 @@ static int launch_fwd(const float4 *digest, const int32_t *ranges, const int32_t
 int raster_digest_f32(const float *points, const float *features, const float *depths, int64_t v, int F,
                       double alpha_threshold, void *digest, cudaStream_t stream);   // raster_digest.cu
 int raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t k,
-                    int32_t width, int32_t height, int32_t F, void *records, void *flush, cudaStream_t stream);   // raster_pack.cu
+                    int32_t width, int32_t height, int32_t F, void *records, void *flush, cudaStream_t stream,
+                    const uint32_t *sorted_tiles = nullptr);   // raster_pack.cu
 
 // GS_RASTER_STAGING=gather keeps the in-kernel digest gather of this file for alpha blending too (A/B switch);
 // default: packed records + bulk-copy staging (raster_pack.cu, raster_fwd_bulk.cu).

@@ -179,7 +179,10 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
   }
   // ---- tile mapper, first half (two-level ordering): depth order -> counts -> scan -> K ----
   GS_TRY(gs_depth_order(a->ndc, v, a->use_depth16, a->order, a->ws_order, a->ws_order_bytes, stream));
-  GS_TRY(gs_tile_count_ordered(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, stream));
+  if (a->hits != nullptr)   // count and emit share one grid query through per-Gaussian hit records
+    GS_TRY(gs_tile_count_ordered_hits(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, a->hits, stream));
+  else
+    GS_TRY(gs_tile_count_ordered(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, stream));
   GS_TRY(gs_tile_scan(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[1], stream));
   GS_CUDA(cudaStreamSynchronize(stream));
   *k_out = v > 0 ? (int64_t)aux->host_words[1] : 0;
@@ -229,8 +232,11 @@ static int gs::stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64
       GS_TRY(gs_tile_scan(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[4], stream));
     }
     if (k > 0) {
-      GS_TRY(gs_tile_emit_ordered(a->points, a->order, a->cum, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p,
-                                  stream));
+      if (a->hits != nullptr && !binned)
+        GS_TRY(gs_tile_emit_hits(a->points, a->order, a->cum, a->hits, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p, stream));
+      else
+        GS_TRY(gs_tile_emit_ordered(a->points, a->order, a->cum, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p,
+                                    stream));
       GS_TRY(gs_sort_pairs(tiles, o2p, tiles + k_stride, o2p + k_stride, k, 4, 0, tile_bits(num_tiles), ws_sort,
                            ws_sort_bytes, stream));
     }
@@ -239,8 +245,12 @@ static int gs::stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64
   GS_CUDA(cudaStreamWaitEvent(stream, aux->side_done, 0));
   if (a->records != nullptr || k == 0) {
     // per-overlap records in sorted order (kept for the backward), then the bulk-copy staged forward kernel
-    GS_TRY(gs_raster_pack_f32(a->digest, a->tile_ranges, sorted_o2p, k, a->width, a->height, a->channels, a->records,
-                              a->flush_records, stream));
+    if (binned && max_per_tile <= gs_tile_bin_max_per_tile())   // binned ordering: no sorted tile-id array
+      GS_TRY(gs_raster_pack_f32(a->digest, a->tile_ranges, sorted_o2p, k, a->width, a->height, a->channels, a->records,
+                                a->flush_records, stream));
+    else
+      GS_TRY(gs_raster_pack_sorted_f32(a->digest, tiles + k_stride, sorted_o2p, k, a->width, a->height, a->channels,
+                                       a->records, a->flush_records, stream));
     if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
     GS_TRY(gs_raster_fwd_packed_f32(a->records, a->tile_ranges, sorted_o2p, v, k, a->width, a->height, a->channels,
                                     &a->config, a->median_threshold, a->image, a->image_alpha, a->visibility,

@@ -122,7 +122,9 @@ def bin_and_sort(g: torch.Tensor, d: torch.Tensor, image_size, config, use_depth
   call("gs_depth_order", ptr(d), v, int(use_depth16), ptr(order), ws.data_ptr(), ws.numel(), stream)
   counts = torch.empty((v,), dtype=torch.int32, device=device)
   cum = torch.empty((v + 1,), dtype=torch.int32, device=device)
-  call("gs_tile_count_ordered", ptr(g), ptr(order), v, w_pad, h_pad, ts, thr, ptr(counts), stream)
+  # count and emit share ONE grid query: the count kernel leaves a 16-byte hit record per Gaussian for the emit kernel
+  hits = torch.empty((v, 2), dtype=torch.int64, device=device)
+  call("gs_tile_count_ordered_hits", ptr(g), ptr(order), v, w_pad, h_pad, ts, thr, ptr(counts), ptr(hits), stream)
   call("gs_tile_scan_workspace_bytes", v, nbytes)
   ws2 = _lib.workspace(nbytes.value, device)
   word = _lib.host_word(device)
@@ -133,7 +135,8 @@ def bin_and_sort(g: torch.Tensor, d: torch.Tensor, image_size, config, use_depth
   tiles = torch.empty((2, k), dtype=torch.int32, device=device)
   o2p = torch.empty((2, k), dtype=torch.int32, device=device)
   if k > 0:
-    call("gs_tile_emit_ordered", ptr(g), ptr(order), ptr(cum), v, w_pad, h_pad, ts, thr, ptr(tiles[0]), ptr(o2p[0]), stream)
+    call("gs_tile_emit_hits", ptr(g), ptr(order), ptr(cum), ptr(hits), v, w_pad, h_pad, ts, thr, ptr(tiles[0]), ptr(o2p[0]),
+         stream)
     call("gs_sort_pairs_workspace_bytes", k, 4, nbytes)
     ws3 = _lib.workspace(nbytes.value, device)
     call("gs_sort_pairs", ptr(tiles[0]), ptr(o2p[0]), ptr(tiles[1]), ptr(o2p[1]), k, 4, 0, tile_bits(num_tiles),

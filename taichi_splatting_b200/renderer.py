@@ -208,6 +208,7 @@ class _RenderFunction(torch.autograd.Function):
     heur_n = empty((n, 2)) if config.compute_point_heuristic else None
     cam_pos = empty((3,))
     order, counts, cum = empty((n,), i32), empty((n,), i32), empty((n + 1,), i32)
+    hits = empty((n, 2), torch.int64)   # per-Gaussian hit records shared by tile count and emit
     ws_bytes = _workspace_sizes(n)
     ws = [_lib.workspace(b, device) for b in ws_bytes]
     image, alpha = empty((h, w, F)), empty((h, w))
@@ -228,7 +229,7 @@ class _RenderFunction(torch.autograd.Function):
         ws[0].data_ptr(), ws[0].numel(), ws[1].data_ptr(), ws[1].numel(), ws[2].data_ptr(), ws[2].numel(),
         ptr(image), ptr(alpha), ptr(median) if render_median_depth else None, ptr(tile_ranges),
         _event_handle(ev_fwd[0] if ev_fwd else None), _event_handle(ev_fwd[1] if ev_fwd else None),
-        ptr(tile_counts), ptr(tile_cursor), ptr(tile_totals), None, None)
+        ptr(tile_counts), ptr(tile_cursor), ptr(tile_totals), None, None, ptr(hits))
     rec_cols = 12 if F <= 3 else 16   # floats per packed raster record (gs_raster_pack_bytes)
     # K-sized buffers: sized from the previous frame on this device (+25 %), so that the driver can go from the
     # host read of K straight into key emission; if K outgrew them, allocate exactly and run stage B from here
