@@ -35,7 +35,7 @@ UNIT = "Gaussians/s"
 WORKLOAD = dict(workload="cfg3", n_gaussians=1_000_000, image_size=[2048, 2048], sh_degree=3, tile_size=16,
                 visibility=True, point_heuristic=True, median_depth=True, loss="image.sum()",
                 l2="inputs (236 MB cloud + per-frame K-sized buffers) exceed the 126 MB L2; no explicit flush")
-CPU_SAMPLE_N = 100_000   # bounded CPU sample: a 100 k-Gaussian cloud of the same generator on the same 2048^2 image
+CPU_SAMPLE_N = WORKLOAD["n_gaussians"]   # the CPU arm runs the SAME cloud (1 M Gaussians at 2048^2): a few seconds per step
 
 
 def peaks():
@@ -113,14 +113,16 @@ class ClockSampler:
             "power_w_max": round(max(s[2] for s in self.samples), 1), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def algorithmic_bytes(N, V, K, P, T, F, D):
-  """SURVEY 8d per-stage algorithmic bytes (fp32, i32 ids, u64 keys; each tensor read once / written once)."""
+def algorithmic_bytes(N, V, K, P, T, F, D, dense_grad_image=False):
+  """SURVEY 8d per-stage algorithmic bytes (fp32, i32 ids, u64 keys; each tensor read once / written once).
+  dense_grad_image: dL/dimage is a materialised (H,W,F) tensor (4PF more bytes read by the backward); the bench's
+  image.sum() loss hands over an expanded scalar, which the backward reads through its strides."""
   Pr = -(-(32 + max(1, (T - 1).bit_length())) // 8)
   stages = {
       "project": 44 * N + 40 * V, "sh": V * (12 * D + 20) + 12 * V, "tile_count_scan": 40 * V,
       "emit_keys": 36 * V + 12 * K, "sort": Pr * 24 * K + 8 * K, "ranges": 8 * K + 8 * T,
       "raster_fwd": 8 * T + K * (32 + 4 * F) + 4 * P * (F + 1) + 4 * V,
-      "raster_bwd": 8 * T + K * (32 + 4 * F) + 8 * P * F + 2 * V * (28 + 4 * F) + 16 * V,
+      "raster_bwd": 8 * T + K * (32 + 4 * F) + (8 if dense_grad_image else 4) * P * F + 2 * V * (28 + 4 * F) + 16 * V,
       "sh_bwd": V * (12 * D + 36) + 12 * D * N, "project_bwd": 108 * V + 44 * N,
   }
   return stages, sum(stages.values())
@@ -259,6 +261,9 @@ def run_ours(args):
 
   # ---- end-to-end arm: host buffers in, loss out ----
   loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+  image_host = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()   # an end-to-end render hands the image back
+  d2h_stream = torch.cuda.Stream(device=dev)
+  d2h_done = torch.cuda.Event()
 
   # Double-buffered: step i+1's host->device copies run on a copy stream while step i computes; every step
   # still moves its full input set (cloud + camera) from pinned memory and reads its loss back to the host.
@@ -311,17 +316,41 @@ def run_ours(args):
     torch.cuda.current_stream().wait_event(cur["ready"])
     cam = ts.perspective.CameraParams(projection=cur["proj"], T_camera_world=cur["Tcw"], near_plane=cam_rank.near_plane,
                                       far_plane=cam_rank.far_plane, image_size=(w, h))
-    _, loss = step(ts.Gaussians3D(**cur["params"], batch_size=(n,)), cam)
+    out_, loss = step(ts.Gaussians3D(**cur["params"], batch_size=(n,)), cam)
     cur["free"].record()
-    loss_host.copy_(loss.detach(), non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    # device -> host: the rendered image (50 MB) and the loss, on their own stream so that the read-back of step i
+    # overlaps the compute of step i + 1 (PCIe is full duplex); the host waits for step i's read-back before it
+    # launches step i + 1's
+    d2h_stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(d2h_stream):
+      image_host.copy_(out_.image.detach(), non_blocking=True)
+      loss_host.copy_(loss.detach(), non_blocking=True)
+      out_.image.record_stream(d2h_stream)
+      d2h_done.record(d2h_stream)
+    e2e_state["pending"] = True
     e2e_state["i"] = i + 1
+
+  def e2e_wait():
+    if e2e_state.get("pending"):
+      d2h_done.synchronize()
+      e2e_state["pending"] = False
+
+  def e2e_step_synced():
+    e2e_wait()      # the previous step's image and loss are on the host
+    e2e_step()
 
   for s_ in slots:
     s_["free"].record()
   for _ in range(3):
-    e2e_step()
-  e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_step_synced()
+  e2e_wait()
+
+  def e2e_run():
+    e2e_step_synced()
+  e2e_total = timed(lambda: e2e_run(), args.steps)   # timed() ends with a device synchronise: the last read-back is inside
+  e2e_wait()
+  e2e_ms = e2e_total / args.steps
+  d2h_bytes = image_host.numel() * 4 + 4
   e2e_value = world * n / (e2e_ms * 1e-3)
 
   # ---- roofline of the dominant kernel (raster backward) ----
@@ -341,7 +370,8 @@ def run_ours(args):
   except Exception:
     pass
   roofline = {
-      "bound": "hbm", "kernel": "bwdt::raster_bwd_t_kernel<3,GP,GF,HEUR>", "unit": "GB/s",
+      "bound": "hbm", "actual_bound": "L1/shared-memory data pipe + issue slots (see limiter); `frac` is HBM-relative as the contract asks",
+      "kernel": "bwdt::raster_bwd_t_kernel<3,GP,GF,HEUR,3>", "unit": "GB/s",
       "achieved": round(stage_bytes["raster_bwd"] / (bwd_ms * 1e-3) / 1e9, 2) if bwd_ms else None,
       "peak": hbm_peak, "peak_source": peak_kind,
       "frac": round(stage_bytes["raster_bwd"] / (bwd_ms * 1e-3) / 1e9 / hbm_peak, 5) if bwd_ms else None,
@@ -365,15 +395,15 @@ def run_ours(args):
                                   "backward by an NCCL all-reduce (geometry, one flat 44 B/Gaussian buffer) + all-gather of the rank-1 "
                                   "SH-gradient factors (12 B/Gaussian/view)") if world > 1 else "single GPU"),
       "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
-              "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+              "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
               "note": ("per rank: 1/N row shard of the cloud + camera over PCIe, shards all-gathered over NVLink"
-                       if world > 1 else "whole cloud + camera over PCIe") + "; double-buffered against compute"},
+                       if world > 1 else "whole cloud + camera over PCIe") + "; image (H,W,3) + loss read back every step; copies double-buffered against compute"},
       "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "stages_ms": stages_ms,
   }
   if multi_gpu_check is not None:
     line["multi_gpu_check"] = multi_gpu_check
   if rank == 0 and world == 1:
-    line["cpu_baseline"] = cpu_baseline(steps=2, warmup=1)   # warm: the first CPU step pays thread-pool start-up
+    line["cpu_baseline"] = cpu_baseline(steps=1, warmup=1)   # warm: the first CPU step pays thread-pool start-up (~10-20 s in all)
   if rank == 0:
     print(json.dumps(line), flush=True)
   if world > 1:
@@ -382,11 +412,15 @@ def run_ours(args):
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def _cpu_scene():
+  """The GPU arm's own cloud and camera (same generator, same seed), as CPU tensors for the oracle pipeline."""
+  from types import SimpleNamespace
   from oracle import random_data
-  torch.manual_seed(0)
+  from taichi_splatting_b200.benchmarks import scenes
   w, h = WORKLOAD["image_size"]
-  cam = random_data.fixed_camera((w, h))
-  g = random_data.random_3d_gaussians(CPU_SAMPLE_N, cam, scale_factor=1.0, sh_degree=WORKLOAD["sh_degree"])
+  cam_pkg = scenes.benchmark_camera((w, h), yaw_deg=0.0)
+  cloud = scenes.random_3d_gaussians(CPU_SAMPLE_N, cam_pkg, scale_factor=1.0, sh_degree=WORKLOAD["sh_degree"], seed=0)
+  g = SimpleNamespace(**{k: getattr(cloud, k) for k in ("position", "log_scaling", "rotation", "alpha_logit", "feature")})
+  cam = random_data.make_camera(cam_pkg.T_camera_world, cam_pkg.projection, (w, h), cam_pkg.near_plane, cam_pkg.far_plane)
   return g, cam
 
 
@@ -414,9 +448,9 @@ def cpu_baseline(steps=1, warmup=0):
     out = _cpu_step(g, cam, use_ref)
   dt = (time.perf_counter() - t0) / steps
   return {"value": round(CPU_SAMPLE_N / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
-          "ms_per_step": round(dt * 1e3, 2),
-          "sample": f"{CPU_SAMPLE_N} Gaussians of the same generator at {WORKLOAD['image_size']}, SH deg 3, vis+heuristics, "
-                    f"fwd+bwd (K={len(out.overlap_to_point)}); projection+SH = "
+          "ms_per_step": round(dt * 1e3, 2), "steps": steps,
+          "sample": f"the whole workload: {CPU_SAMPLE_N} Gaussians of the same generator and seed at {WORKLOAD['image_size']}, SH deg 3, "
+                    f"vis+heuristics, fwd+bwd (K={len(out.overlap_to_point)}), {steps} step(s); projection+SH = "
                     f"{'reference torch_lib' if use_ref else 'oracle restatement of reference torch_lib'}, "
                     "mapper+raster = C restatement of the Taichi kernels (no CPU implementation upstream), OpenMP"}
 
@@ -433,7 +467,7 @@ def run_reference(args):
       "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
       "steps": budget_steps, "warmup": min(warmup, 1), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": dict(WORKLOAD, cpu_sample_n=CPU_SAMPLE_N),
+      "config": dict(WORKLOAD, forward_saturate_eps=0.0),
       "cpu_baseline": res,
       "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "note": "Taichi is not installable in this image, so the reference's Taichi-CUDA path cannot run; this arm is the "

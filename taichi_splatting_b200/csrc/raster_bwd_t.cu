@@ -53,10 +53,7 @@ __device__ unsigned long long g_count[4];   // warp iterations (padded), hit-lis
 constexpr int kTile = 16;
 constexpr int kWarps = 4;          // one warp per 8x8 pixel block; every lane owns two pixels (rows r and r + 4)
 constexpr int kThreads = kWarps * 32;
-#ifndef GS_BWDT_BATCH
-#define GS_BWDT_BATCH 96
-#endif
-constexpr int kBatch = GS_BWDT_BATCH;   // records per bulk copy (96: two record buffers + two accumulator sets fit 4 CTAs / SM)
+constexpr int kBatch = kThreads;   // splats staged per round: thread j stages and finally flushes splat j
 #ifndef GS_BWDT_CHUNK
 #define GS_BWDT_CHUNK 8
 #endif
@@ -82,16 +79,14 @@ struct Smem {
   // two landing buffers of raster_pack records {tx0, ty0, ux, wx | uy, wy, alpha, depth | features (, mask)}
   // (+1: null record that pads the hit lists)
   float4 rec[2][(kBatch + 1) * RECW];
-  float acc[2][kBatch * kAcc];           // per-splat sums of the batch, double-buffered like the records
+  float acc[kBatch * kAcc];
   float4 panel0[kWarps][kChunk * kRow];  // per-warp [splat][lane] scratch: {S, D, sum G^2, sum |G dpdf/dmean|}
   float4 panel1[kWarps][kChunk * kRow];  //                                 {sum weight dL/dimage[c]}
   // byte offsets (16 RECW j) of the records a warp must visit; entry k lives at index k + 3, so that the eight
   // "next" entries of a chunk (k = h0 + 1 .. h0 + 8) are two aligned 16-byte loads
   alignas(16) unsigned list[kWarps][kBatch + kChunk + 4];
   alignas(8) uint64_t full[2];           // mbarriers: "buffer b holds its batch"
-  int arrived[2];                        // warps that have finished with buffer b (the last one flushes and refills it)
-  int warp_done[kWarps];                 // every pixel of the warp's block is saturated
-  int n_total;                           // batches that are (going to be) issued: shrinks when the whole tile is saturated
+  int warp_done[kWarps];
 };
 
 template <int F, bool GP, bool GF, bool HEUR, int RECW>
@@ -175,27 +170,28 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
     for (int b = 0; b < 2; ++b)
 #pragma unroll
       for (int q = 0; q < RECW; ++q) sm.rec[b][kBatch * RECW + q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    sm.n_total = nbatches;
-    sm.arrived[0] = sm.arrived[1] = 0;
     if (nbatches > 0) issue(0);
     if (nbatches > 1) issue(1);
   }
   if (lane == 0) sm.warp_done[warp] = 0;
-  for (int c = tid; c < 2 * kBatch * kAcc; c += kThreads) (&sm.acc[0][0])[c] = 0.f;
-  __syncthreads();   // the only block barrier of the kernel: the batch loop synchronises through mbarriers / counters
-  volatile int *n_total = &sm.n_total;
+#pragma unroll
+  for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
 
-  for (int b = 0; b < *n_total; ++b) {
+  for (int b = 0; b < nbatches; ++b) {
     const int buf = b & 1;
     const int base = start + b * kBatch, nb = min(kBatch, end - base);
-    // wait for the batch to land -- or learn that the tile was stopped (every pixel saturated) before it was issued
+    __syncthreads();   // previous flush finished: its buffer is free, accumulators are zero again, warp_done visible
     {
-      bool landed = true;
-      while (!mbar_try_wait(&sm.full[buf], (uint32_t)(b >> 1) & 1u))
-        if (*n_total <= b) { landed = false; break; }
-      if (!landed) break;
+      int all_done = 1;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) all_done &= sm.warp_done[w];
+      // refill the buffer the previous batch just released (the flush still read its records, so not earlier); the
+      // copy of batch b + 1 then runs beside the sweep of batch b.  Every issued copy is waited for before the CTA
+      // exits: when every pixel is saturated nothing new is issued and batch b is the last one in flight.
+      if (tid == 0 && b >= 1 && b + 1 < nbatches && !all_done) issue(b + 1);
+      mbar_wait(&sm.full[buf], (uint32_t)(b >> 1) & 1u);   // the batch has landed
+      if (all_done) break;
     }
-    float *acc = sm.acc[buf];
     const unsigned char *rec = reinterpret_cast<const unsigned char *>(sm.rec[buf]);
     const unsigned *words = reinterpret_cast<const unsigned *>(sm.rec[buf]);
 
@@ -234,9 +230,6 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
       constexpr int kUnroll1 = GS_BWDT_UNROLL;
 #pragma unroll kUnroll1
       for (int u = 0; u < kChunk; ++u) {
-#ifdef GS_BWDT_SKIP_PAD
-        if (u > 0 && h0 + u >= nhit) break;   // padded tail of the list: phase 2 ignores those rows anyway
-#endif
         const unsigned off_next = next_off[u];
         const float4 An = *reinterpret_cast<const float4 *>(rec + off_next);
         const float4 Bn = *reinterpret_cast<const float4 *>(rec + off_next + 16);
@@ -369,7 +362,7 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
         for (int i = 0; i < 3; ++i) v[i] += __shfl_xor_sync(full, v[i], 4);
       }
       if (h0 + s < nhit && (kChunk == 8 || (lane & 4) == 0)) {
-        float *dst = acc + (sm.list[warp][3 + h0 + s] / kRecBytes) * kAcc + slot_base;
+        float *dst = sm.acc + (sm.list[warp][3 + h0 + s] / kRecBytes) * kAcc + slot_base;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
           if (v[i] != 0.f) atomicAdd(dst + i, v[i]);
@@ -379,78 +372,50 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
     }
     if (__all_sync(full, trans[0] <= t_min && trans[1] <= t_min) && lane == 0) sm.warp_done[warp] = 1;
 
-    // ---- release the buffer.  No block barrier: every warp counts itself out of buffer `buf` and goes on to the next
-    // batch (its copy is already in flight); the LAST warp to leave flushes the batch's per-splat sums to global
-    // memory, clears them, and hands the buffer back to the copy engine for batch b + 2.  The four warps of a tile
-    // (whose pixel blocks hold different numbers of splats) therefore never wait for each other inside a tile -- the
-    // block barriers of the previous version cost ~12 % of this kernel's stall samples.  acc[buf] / rec[buf] are next
-    // touched by batch b + 2, which cannot start before its records have landed, i.e. after this flush. ----
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) {
-      __threadfence_block();   // this warp's shared-memory atomics before its arrival
-      last = atomicAdd(&sm.arrived[buf], 1) == kWarps - 1;
-    }
-    last = __shfl_sync(full, last, 0);
-    if (!last) continue;
-    __threadfence_block();
-    for (int j = lane; j < nb; j += 32) {
+    // ---- flush: one thread per splat of the batch ----
+    __syncthreads();
+    if (tid < nb) {
       float S[12];
       bool any = false;
 #pragma unroll
-      for (int c = 0; c < 12; ++c) { S[c] = acc[j * kAcc + c]; any |= (S[c] != 0.f); }
-      if (!any) continue;
+      for (int c = 0; c < 12; ++c) { S[c] = sm.acc[tid * kAcc + c]; any |= (S[c] != 0.f); }
+      if (any) {
 #pragma unroll
-      for (int c = 0; c < 12; ++c) acc[j * kAcc + c] = 0.f;
-      const int my_id = __ldg(overlap_to_point + base + j);
-      if (GP) {
-        // shift the tile-centred moments to the splat mean: d = l + c
-        const float4 RA = sm.rec[buf][j * RECW], RB = sm.rec[buf][j * RECW + 1];
-        const float4 RC = __ldg(flush_records + base + j);   // mean - tile centre, 1/sigma.x, 1/sigma.y
-        const float inv_k = 1.0f / kExpScale;
-        const float cx = -RC.x, cy = -RC.y, s_isx = RC.z, s_isy = RC.w, s_alpha = RB.z;
-        const float M0 = S[0], Lx = S[1], Ly = S[2], Lxx = S[3], Lxy = S[4], Lyy = S[5];
-        const float Mx = fmaf(cx, M0, Lx), My = fmaf(cy, M0, Ly);
-        const float Mxx = Lxx + cx * (2.0f * Lx + cx * M0);
-        const float Myy = Lyy + cy * (2.0f * Ly + cy * M0);
-        const float Mxy = Lxy + cx * Ly + cy * Lx + cx * cy * M0;
-        const float ux = RA.z * inv_k, uy = RB.x * inv_k, wx = RA.w * inv_k, wy = RB.y * inv_k;   // axis / sigma
-        const float S1 = ux * Mx + uy * My, S2 = wx * Mx + wy * My;
-        const float S3 = ux * Mxx + uy * Mxy, S4 = ux * Mxy + uy * Myy;
-        const float S5 = wx * Mxx + wy * Mxy, S6 = wx * Mxy + wy * Myy;
-        float *gp = grad_points + 7 * (int64_t)my_id;
-        atomicAdd(gp + 0, S1 * ux + S2 * wx);
-        atomicAdd(gp + 1, S1 * uy + S2 * wy);
-        atomicAdd(gp + 2, -s_isx * S3 - s_isy * S6);
-        atomicAdd(gp + 3, -s_isx * S4 + s_isy * S5);
-        atomicAdd(gp + 4, s_isx * (ux * S3 + uy * S4));
-        atomicAdd(gp + 5, s_isy * (wx * S5 + wy * S6));
-        atomicAdd(gp + 6, M0 / s_alpha);
-      }
-      if (GF) {
-        float *gf = grad_features + (int64_t)F * my_id;
+        for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
+        const int my_id = __ldg(overlap_to_point + base + tid);
+        if (GP) {
+          // shift the tile-centred moments to the splat mean: d = l + c
+          const float4 RA = sm.rec[buf][tid * RECW], RB = sm.rec[buf][tid * RECW + 1];
+          const float4 RC = __ldg(flush_records + base + tid);   // mean - tile centre, 1/sigma.x, 1/sigma.y
+          const float inv_k = 1.0f / kExpScale;
+          const float cx = -RC.x, cy = -RC.y, s_isx = RC.z, s_isy = RC.w, s_alpha = RB.z;
+          const float M0 = S[0], Lx = S[1], Ly = S[2], Lxx = S[3], Lxy = S[4], Lyy = S[5];
+          const float Mx = fmaf(cx, M0, Lx), My = fmaf(cy, M0, Ly);
+          const float Mxx = Lxx + cx * (2.0f * Lx + cx * M0);
+          const float Myy = Lyy + cy * (2.0f * Ly + cy * M0);
+          const float Mxy = Lxy + cx * Ly + cy * Lx + cx * cy * M0;
+          const float ux = RA.z * inv_k, uy = RB.x * inv_k, wx = RA.w * inv_k, wy = RB.y * inv_k;   // axis / sigma
+          const float S1 = ux * Mx + uy * My, S2 = wx * Mx + wy * My;
+          const float S3 = ux * Mxx + uy * Mxy, S4 = ux * Mxy + uy * Myy;
+          const float S5 = wx * Mxx + wy * Mxy, S6 = wx * Mxy + wy * Myy;
+          float *gp = grad_points + 7 * (int64_t)my_id;
+          atomicAdd(gp + 0, S1 * ux + S2 * wx);
+          atomicAdd(gp + 1, S1 * uy + S2 * wy);
+          atomicAdd(gp + 2, -s_isx * S3 - s_isy * S6);
+          atomicAdd(gp + 3, -s_isx * S4 + s_isy * S5);
+          atomicAdd(gp + 4, s_isx * (ux * S3 + uy * S4));
+          atomicAdd(gp + 5, s_isy * (wx * S5 + wy * S6));
+          atomicAdd(gp + 6, M0 / s_alpha);
+        }
+        if (GF) {
+          float *gf = grad_features + (int64_t)F * my_id;
 #pragma unroll
-        for (int c = 0; c < F; ++c) atomicAdd(gf + c, S[6 + c]);
-      }
-      if (HEUR) {
-        atomicAdd(heuristic + 2 * (int64_t)my_id, S[10]);
-        atomicAdd(heuristic + 2 * (int64_t)my_id + 1, S[11]);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) {
-      sm.arrived[buf] = 0;
-      int all_done = 1;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) all_done &= *(volatile int *)&sm.warp_done[w];
-      if (all_done) {
-        // every pixel of the tile is saturated: nothing further is issued.  Batch b + 1 (in flight) is still waited
-        // for by every warp; a warp already waiting for batch b + 2 sees n_total shrink and leaves.
-        if (*n_total > b + 2) *n_total = b + 2;
-        __threadfence_block();
-      } else if (b + 2 < nbatches) {
-        fence_proxy_async();   // this warp's reads of rec[buf] (flush) before the copy engine overwrites it
-        issue(b + 2);
+          for (int c = 0; c < F; ++c) atomicAdd(gf + c, S[6 + c]);
+        }
+        if (HEUR) {
+          atomicAdd(heuristic + 2 * (int64_t)my_id, S[10]);
+          atomicAdd(heuristic + 2 * (int64_t)my_id + 1, S[11]);
+        }
       }
     }
   }

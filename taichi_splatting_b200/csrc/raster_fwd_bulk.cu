@@ -11,9 +11,15 @@
 //                    range: thread 0 issues `cp.async.bulk` (TMA engine, SASS UBLKCP) into one of two shared-memory
 //                    buffers and arms an mbarrier with the byte count; the copy of batch b+1 is in flight while batch
 //                    b is swept, and batch b+2 is issued the moment batch b's buffer is free.  No staging arithmetic,
-//                    no index indirection, no LSU traffic for staging, and NO block barrier in the batch loop: warps
-//                    count themselves out of a buffer and the last one refills it, so the four warps of a tile (whose
-//                    pixel blocks hold different numbers of splats) never wait for each other.
+//                    no index indirection, no LSU traffic for staging, one block barrier per batch.
+//
+// Measured and rejected (profiles/r02/r02e_barrier_free.md): a batch loop WITHOUT block barriers -- warps count themselves
+// out of a buffer and the last one flushes / refills it, so warps run ahead of each other.  The four warps of a tile
+// carry different loads (their 8x8 blocks hold different numbers of splats); letting the light warps run ahead and exit
+// leaves the heavy warp alone at the end of every tile while the CTA still holds its shared memory, and a lone warp
+// hides none of its own latency: resident warps fell from 24.5 % to 17.8 % of peak and the backward went from 1.02 to
+// 1.65 ms (forward 0.39 -> 0.43 ms).  The barrier keeps the light warps' work spread over the tile's lifetime, where
+// it overlaps the heavy warp's stalls.
 #include <type_traits>
 
 #include "bulk_copy.cuh"
@@ -52,9 +58,7 @@ struct Smem {
   float vis[2][kBatch];                 // per-splat visibility of the batch (double-buffered like the records)
   alignas(16) unsigned list[kWarps][kBatch + kUnroll];   // byte offsets of the records a warp must visit
   alignas(8) uint64_t full[2];          // mbarriers: "buffer b holds its batch"
-  int arrived[2];                       // warps that have finished with buffer b (the last one flushes and refills it)
-  int warp_done[kWarps];                // every pixel of the warp's block is below forward_saturate_eps
-  int n_total;                          // batches that are (going to be) issued: shrinks when the whole tile is done
+  int warp_done[kWarps];
 };
 
 // N values per lane -> every lane of group g = lane / (32 / N) ends with the warp-wide sum of value g in v[0]
@@ -122,29 +126,29 @@ raster_fwd_bulk_kernel(const float4 *__restrict__ records, const int32_t *__rest
     for (int b = 0; b < 2; ++b)   // null record: alpha = 0 never passes the threshold
 #pragma unroll
       for (int q = 0; q < RECW; ++q) sm.rec[b][kBatch * RECW + q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    sm.n_total = nbatches;
     if (nbatches > 0) issue(0);
     if (nbatches > 1) issue(1);
   }
-  if (tid < 2) sm.arrived[tid] = 0;
   if (lane == 0) sm.warp_done[warp] = 0;
   if (VIS) {
 #pragma unroll
     for (int j = tid; j < kBatch; j += kThreads) { sm.vis[0][j] = 0.f; sm.vis[1][j] = 0.f; }
   }
-  __syncthreads();   // the only block barrier of the kernel: the batch loop below synchronises through mbarriers / counters
+  __syncthreads();
 
-  volatile int *n_total = &sm.n_total;
-  for (int b = 0; b < *n_total; ++b) {
+  for (int b = 0; b < nbatches; ++b) {
     const int buf = b & 1;
     const int base = start + b * kBatch, nb = min(kBatch, end - base);
-    // wait for the batch to land -- or learn that the tile was stopped (every pixel done) before it was issued
-    {
-      bool landed = true;
-      while (!mbar_try_wait(&sm.full[buf], (uint32_t)(b >> 1) & 1u))
-        if (*n_total <= b) { landed = false; break; }
-      if (!landed) break;
+    // ids of the splats this thread flushes after the sweep: loaded now, used then
+    int my_id[kBatch / kThreads];
+    if (VIS) {
+#pragma unroll
+      for (int s = 0; s < kBatch / kThreads; ++s) {
+        const int j = tid + s * kThreads;
+        my_id[s] = j < nb ? overlap_to_point[base + j] : 0;
+      }
     }
+    mbar_wait(&sm.full[buf], (uint32_t)(b >> 1) & 1u);   // the batch has landed
     const unsigned char *rb = reinterpret_cast<const unsigned char *>(sm.rec[buf]);
     const unsigned *words = reinterpret_cast<const unsigned *>(sm.rec[buf]);
 
@@ -220,45 +224,27 @@ raster_fwd_bulk_kernel(const float4 *__restrict__ records, const int32_t *__rest
       }
       if (__all_sync(full, trans[0] <= eps && trans[1] <= eps)) break;
     }
-
-    // ---- release the buffer.  No block barrier: every warp counts itself out of buffer `buf` and moves on to the next
-    // batch (whose copy was issued earlier); the LAST warp to leave flushes the batch's visibility sums and hands the
-    // buffer back to the copy engine for batch b + 2.  Warps of a tile whose pixel blocks hold different numbers of
-    // splats therefore never wait for each other inside a tile.  The visibility slots of `buf` are reused by batch
-    // b + 2, which cannot start before its records have landed, i.e. after this flush. ----
     if (__all_sync(full, trans[0] <= eps && trans[1] <= eps) && lane == 0) sm.warp_done[warp] = 1;
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) {
-      __threadfence_block();   // this warp's shared-memory atomics (visibility) before its arrival
-      last = atomicAdd(&sm.arrived[buf], 1) == kWarps - 1;
-    }
-    last = __shfl_sync(full, last, 0);
-    if (last) {
-      __threadfence_block();
-      if (VIS) {
-        for (int j = lane; j < nb; j += 32) {
-          const float vsum = sm.vis[buf][j];
-          if (vsum != 0.f) { atomicAdd(visibility + overlap_to_point[base + j], vsum); sm.vis[buf][j] = 0.f; }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        sm.arrived[buf] = 0;
-        int all_done = 1;
+
+    __syncthreads();   // every warp is through with this buffer (records and visibility sums)
+    int all_done = 1;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) all_done &= *(volatile int *)&sm.warp_done[w];
-        if (all_done) {
-          // nothing can change any more: no further batch is issued.  Batch b + 1 (in flight) is still waited for by
-          // every warp, so no copy is outstanding when the CTA exits; a warp already waiting for batch b + 2 sees
-          // n_total shrink and leaves.
-          if (*n_total > b + 2) *n_total = b + 2;
-          __threadfence_block();
-        } else if (b + 2 < nbatches) {
-          fence_proxy_async();
-          issue(b + 2);
+    for (int w = 0; w < kWarps; ++w) all_done &= sm.warp_done[w];
+    if (tid == 0 && b + 2 < nbatches && !all_done) issue(b + 2);   // refill the buffer just released
+    if (VIS) {
+#pragma unroll
+      for (int s = 0; s < kBatch / kThreads; ++s) {
+        const int j = tid + s * kThreads;
+        if (j < nb) {
+          const float vsum = sm.vis[buf][j];
+          if (vsum != 0.f) { atomicAdd(visibility + my_id[s], vsum); sm.vis[buf][j] = 0.f; }
         }
       }
+    }
+    if (all_done) {
+      // batch b + 1 was handed to the copy engine earlier: it must land before this CTA's shared memory is released
+      if (b + 1 < nbatches) mbar_wait(&sm.full[buf ^ 1], (uint32_t)((b + 1) >> 1) & 1u);
+      break;
     }
   }
 
