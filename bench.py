@@ -32,9 +32,18 @@ import torch  # noqa: E402
 
 METRIC = "gaussians_per_sec_fwd_bwd"
 UNIT = "Gaussians/s"
-WORKLOAD = dict(workload="cfg3", n_gaussians=1_000_000, image_size=[2048, 2048], sh_degree=3, tile_size=16,
-                visibility=True, point_heuristic=True, median_depth=True, loss="image.sum()",
-                l2="inputs (236 MB cloud + per-frame K-sized buffers) exceed the 126 MB L2; no explicit flush")
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on (default)
+    "cfg3": dict(workload="cfg3", n_gaussians=1_000_000, image_size=[2048, 2048], sh_degree=3, tile_size=16,
+                 visibility=True, point_heuristic=True, median_depth=True, loss="image.sum()",
+                 l2="inputs (236 MB cloud + per-frame K-sized buffers) exceed the 126 MB L2; no explicit flush"),
+    # BASELINE.json configs[3]: ONE view of 6 M Gaussians at 4096x2160, the tile grid sharded over the ranks (strong
+    # scaling: the same frame at every N; value = n_gaussians / step time)
+    "cfg4": dict(workload="cfg4", n_gaussians=6_000_000, image_size=[4096, 2160], sh_degree=3, tile_size=16,
+                 visibility=True, point_heuristic=True, median_depth=True, loss="image.sum()",
+                 l2="inputs (1.4 GB cloud + per-frame K-sized buffers) exceed the 126 MB L2; no explicit flush"),
+}
+WORKLOAD = WORKLOADS["cfg3"]
 CPU_SAMPLE_N = WORKLOAD["n_gaussians"]   # the CPU arm runs the SAME cloud (1 M Gaussians at 2048^2): a few seconds per step
 
 
@@ -147,11 +156,13 @@ def run_ours(args):
     dist.init_process_group("nccl", device_id=dev)
 
   n, (w, h), deg = WORKLOAD["n_gaussians"], WORKLOAD["image_size"], WORKLOAD["sh_degree"]
+  tile_sharded = WORKLOAD["workload"] == "cfg4"   # one view, tile grid cut over the ranks; else one view per rank
+  shard = parallel.TileShard() if (tile_sharded and world > 1) else None
   config = ts.RasterConfig(compute_visibility=True, compute_point_heuristic=True, forward_saturate_eps=args.fwd_eps)
   cam_host = scenes.benchmark_camera((w, h), yaw_deg=0.0)
   cloud_host = scenes.random_3d_gaussians(n, cam_host, scale_factor=1.0, sh_degree=deg, seed=0)
   # rank r looks at the same cloud from its own view (small yaw steps keep the cloud in the frustum)
-  cam_rank = scenes.benchmark_camera((w, h), yaw_deg=2.0 * rank)
+  cam_rank = scenes.benchmark_camera((w, h), yaw_deg=0.0 if tile_sharded else 2.0 * rank)
   names = ("position", "log_scaling", "rotation", "alpha_logit", "feature")
   pinned = {k: getattr(cloud_host, k).contiguous().pin_memory() for k in names}
   cam_pinned = (cam_rank.projection.pin_memory(), cam_rank.T_camera_world.pin_memory())
@@ -166,6 +177,10 @@ def run_ours(args):
       t.grad = None
     if world == 1:
       out = ts.render_gaussians(gauss, cam, config, use_sh=True, render_median_depth=True)
+    elif tile_sharded:
+      # this rank bins / sorts / packs / rasterises its own tile range; ONE all-reduce of the packed-2D + colour
+      # gradients (40 B per visible Gaussian) in the backward, then the replicated SH / projection backward
+      out, _ = parallel.render_tile_sharded(gauss, cam, config, use_sh=True, shard=shard, render_median_depth=True)
     else:
       # view-parallel exchange, all of it inside the backward: the SH gradient is summed over ranks through its
       # rank-1 factors (all-gather of 12 B / Gaussian / view, beside the projection backward), the geometry
@@ -195,15 +210,21 @@ def run_ours(args):
     return float(ms.item())
 
   # ---- device-resident arm ----
-  for _ in range(max(args.warmup, 3)):
+  for i_ in range(max(args.warmup, 3)):
     out, _ = step(gaussians, camera)
+    if shard is not None and i_ == 0:   # equal-tile boundaries -> equal-overlap boundaries from the first frame's counts
+      shard.rebalance()
   # N > 1: the exchanged gradients of the warm-up step against the sum of single-GPU gradients of all N views,
   # rendered one after the other on this rank (every rank checks; rank 0 reports)
   multi_gpu_check = None
   if world > 1:
     got = {k: params[k].grad.detach().clone() for k in names}
     want = {k: torch.zeros_like(params[k]) for k in names}
-    for r in range(world):
+    image_union = None
+    if tile_sharded:   # union of the ranks' image strips (disjoint tiles: the sum) against the single-GPU image
+      image_union = out.image.detach().clone()
+      dist.all_reduce(image_union)
+    for r in range(1 if tile_sharded else world):
       for t in params.values():
         t.grad = None
       o = ts.render_gaussians(gaussians, scenes.benchmark_camera((w, h), yaw_deg=2.0 * r).to(device=dev), config,
@@ -212,10 +233,14 @@ def run_ours(args):
       for k in names:
         want[k] += params[k].grad
     errs = {k: float((got[k] - want[k]).abs().max() / want[k].abs().max().clamp_min(1e-30)) for k in names}
+    if image_union is not None:
+      errs["image"] = float((image_union - o.image.detach()).abs().max() / o.image.detach().abs().max().clamp_min(1e-30))
     worst = torch.tensor([max(errs.values())], device=dev)
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-    multi_gpu_check = {"what": "exchanged gradients vs sum over the N views of single-GPU gradients, max relative error per tensor "
-                               "(this rank), worst over ranks", "per_tensor": {k: float(f"{v:.3g}") for k, v in errs.items()},
+    multi_gpu_check = {"what": ("union of the ranks' image strips and reduced gradients vs the single-GPU render of the same view"
+                                if tile_sharded else "exchanged gradients vs sum over the N views of single-GPU gradients") +
+                               ", max relative error per tensor (this rank), worst over ranks",
+                       "per_tensor": {k: float(f"{v:.3g}") for k, v in errs.items()},
                        "worst_over_ranks": float(f"{float(worst.item()):.3g}"), "tolerance": 2e-5}
     assert float(worst.item()) < 2e-5, f"multi-GPU gradient mismatch: {errs}"
     out, _ = step(gaussians, camera)
@@ -242,22 +267,33 @@ def run_ours(args):
     stage_hot["gs_raster_bwd_packed_f32"] = sum(a_.elapsed_time(b_) for a_, b_ in bwd_pairs) / len(bwd_pairs)
   launches = prof.launches
   ms_per_step = total_ms / args.steps
-  value = world * n / (ms_per_step * 1e-3)
+  value = (1 if tile_sharded else world) * n / (ms_per_step * 1e-3)
 
   # ---- one profiled pass for the per-stage breakdown (outside the timed region): the same kernels chained
   # through the per-stage entry points, so that each one can be bracketed ----
-  prof_all = _lib.Profiler()
-  _lib.profiler = prof_all
-  fused_host, renderer._FUSED_HOST = renderer._FUSED_HOST, False
-  out, _ = step(gaussians, camera)
-  renderer._FUSED_HOST = fused_host
-  _lib.profiler = None
-  torch.cuda.synchronize()
-  stages_ms = {k: round(sum(v), 4) for k, v in prof_all.stage_ms().items()}
-  V = int(out.points.idx.shape[0])
-  o2p, ranges = ts.map_to_tiles(out.points.gaussians2d.detach(), ts.rendering.ndc_depth(out.points.depths.detach(), camera.near_plane, camera.far_plane), (w, h), config)
-  K = int(o2p.shape[0])
-  T = int(ranges.shape[0] * ranges.shape[1])
+  if shard is None:
+    prof_all = _lib.Profiler()
+    _lib.profiler = prof_all
+    fused_host, renderer._FUSED_HOST = renderer._FUSED_HOST, False
+    out, _ = step(gaussians, camera)
+    renderer._FUSED_HOST = fused_host
+    _lib.profiler = None
+    torch.cuda.synchronize()
+    stages_ms = {k: round(sum(v), 4) for k, v in prof_all.stage_ms().items()}
+    V = int(out.points.idx.shape[0])
+    o2p, ranges = ts.map_to_tiles(out.points.gaussians2d.detach(), ts.rendering.ndc_depth(out.points.depths.detach(), camera.near_plane, camera.far_plane), (w, h), config)
+    K = int(o2p.shape[0])
+    T = int(ranges.shape[0] * ranges.shape[1])
+    shard_info = None
+  else:   # tile-sharded: the per-stage pass has no sharded form; K is the sum of the ranks' overlap counts
+    stages_ms = {}
+    V = int(out.points.idx.shape[0])
+    k_local = torch.tensor([shard.last_k], device=dev, dtype=torch.int64)
+    k_all = [torch.zeros_like(k_local) for _ in range(world)]
+    dist.all_gather(k_all, k_local)
+    K = int(sum(int(x.item()) for x in k_all))
+    T = int(shard.num_tiles)
+    shard_info = {"tile_bounds": [int(b) for b in shard.bounds], "overlaps_per_rank": [int(x.item()) for x in k_all]}
 
   # ---- end-to-end arm: host buffers in, loss out ----
   loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -351,7 +387,7 @@ def run_ours(args):
   e2e_wait()
   e2e_ms = e2e_total / args.steps
   d2h_bytes = image_host.numel() * 4 + 4
-  e2e_value = world * n / (e2e_ms * 1e-3)
+  e2e_value = (1 if tile_sharded else world) * n / (e2e_ms * 1e-3)
 
   # ---- roofline of the dominant kernel (raster backward) ----
   P = w * h
@@ -389,9 +425,12 @@ def run_ours(args):
   line = {
       "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
       "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "scaling": "strong" if tile_sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
       "config": dict(WORKLOAD, forward_saturate_eps=args.fwd_eps, V=V, K=K, tiles=T, overlaps_per_tile=round(K / T, 1),
-                     parallelism=(f"view-parallel x{world}: replicated cloud, one view per rank; gradients summed over ranks inside the "
+                     parallelism=(f"tile-sharded x{world}: one view, contiguous tile-id ranges with equal overlap counts per rank; every rank "
+                                  "runs the O(N) front end, bins / sorts / packs / rasterises its own tiles; ONE NCCL all-reduce of the "
+                                  "packed-2D + colour gradients (40 B / visible Gaussian) in the backward") if (world > 1 and tile_sharded) else
+                                 (f"view-parallel x{world}: replicated cloud, one view per rank; gradients summed over ranks inside the "
                                   "backward by an NCCL all-reduce (geometry, one flat 44 B/Gaussian buffer) + all-gather of the rank-1 "
                                   "SH-gradient factors (12 B/Gaussian/view)") if world > 1 else "single GPU"),
       "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
@@ -402,7 +441,9 @@ def run_ours(args):
   }
   if multi_gpu_check is not None:
     line["multi_gpu_check"] = multi_gpu_check
-  if rank == 0 and world == 1:
+  if shard_info is not None:
+    line["tile_shards"] = shard_info
+  if rank == 0 and world == 1 and WORKLOAD["workload"] == "cfg3":
     line["cpu_baseline"] = cpu_baseline(steps=1, warmup=1)   # warm: the first CPU step pays thread-pool start-up (~10-20 s in all)
   if rank == 0:
     print(json.dumps(line), flush=True)
@@ -482,9 +523,15 @@ def main():
   ap.add_argument("--steps", type=int, default=50)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS),
+                  help="cfg3 (default; the metric's configuration; N > 1: one view per rank) | cfg4 (6 M Gaussians, "
+                       "4096x2160, one view tile-sharded over the ranks, strong scaling)")
   ap.add_argument("--fwd-eps", type=float, default=0.0,
                   help="RasterConfig.forward_saturate_eps (0 = the reference's semantics: the forward never stops early)")
   args = ap.parse_args()
+  global WORKLOAD, CPU_SAMPLE_N
+  WORKLOAD = WORKLOADS[args.workload]
+  CPU_SAMPLE_N = WORKLOAD["n_gaussians"]
   if args.impl == "reference":
     run_reference(args)
   else:

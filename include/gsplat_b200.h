@@ -190,13 +190,16 @@ int gs_tile_emit_ordered(const float *gaussians, const int32_t *order, const int
                          uint32_t *tile_keys, int32_t *overlap_to_point, void *stream);
 /* Same two kernels sharing ONE grid query: the count kernel also leaves a 16-byte hit record per Gaussian (tile span
  * as 4 x u16 + a 64-bit mask of the accepted tiles in enumeration order; spans over 64 tiles are marked and
- * re-queried), and the emit kernel walks the set bits instead of repeating the query.  hits: (v) x 16 bytes. */
+ * re-queried), and the emit kernel walks the set bits instead of repeating the query.  hits: (v) x 16 bytes.
+ * tile_lo / tile_hi: a tile-sharded multi-GPU rank keeps only the overlaps of its own contiguous tile-id range, so its
+ * sort, pack and raster kernels see K / world overlaps. */
 int gs_tile_count_ordered_hits(const float *gaussians, const int32_t *order, int64_t v, int32_t width_padded,
-                               int32_t height_padded, int32_t tile_size, double alpha_threshold, int32_t *counts,
-                               void *hits, void *stream);
+                               int32_t height_padded, int32_t tile_size, double alpha_threshold,
+                               int32_t tile_lo, int32_t tile_hi /* keep tiles [lo, hi) only; (0, 0): all */,
+                               int32_t *counts, void *hits, void *stream);
 int gs_tile_emit_hits(const float *gaussians, const int32_t *order, const int32_t *cum, const void *hits, int64_t v,
                       int32_t width_padded, int32_t height_padded, int32_t tile_size, double alpha_threshold,
-                      uint32_t *tile_keys, int32_t *overlap_to_point, void *stream);
+                      int32_t tile_lo, int32_t tile_hi, uint32_t *tile_keys, int32_t *overlap_to_point, void *stream);
 int gs_tile_ranges_from_tiles(const uint32_t *sorted_tiles, int64_t k, int32_t *tile_ranges, int64_t num_tiles,
                               void *stream);
 
@@ -378,6 +381,7 @@ typedef struct gs_render_args {
    * (gs_raster_pack_bytes) written by stage B and kept for the backward.  NULL: stage B packs into library scratch. */
   void *records, *flush_records;
   void *hits;                           /* (n) x 16 bytes: hit records shared by tile count and emit, or NULL */
+  int32_t tile_lo, tile_hi;             /* tile-sharded rank: bin / rasterise tiles [lo, hi) only (needs hits); (0, 0): all */
 } gs_render_args;
 
 int gs_render_stage_a_f32(const gs_render_args *args, int64_t *v_out, int64_t *k_out, int64_t *max_per_tile_out,

@@ -48,7 +48,7 @@ class RenderArgsC(ctypes.Structure):
       ("image", P), ("image_alpha", P), ("median_image", P), ("tile_ranges", P),
       ("ev_raster_start", P), ("ev_raster_end", P),
       ("tile_counts", P), ("tile_cursor", P), ("tile_totals", P),
-      ("records", P), ("flush_records", P), ("hits", P),
+      ("records", P), ("flush_records", P), ("hits", P), ("tile_lo", I32), ("tile_hi", I32),
   ]
 
 
@@ -106,8 +106,8 @@ SIGNATURES = {
     "gs_tile_count_ordered": ([P, P, I64, I32, I32, I32, D, P, P], c_int32),
     "gs_tile_emit_ordered": ([P, P, P, I64, I32, I32, I32, D, P, P, P], c_int32),
     "gs_tile_ranges_from_tiles": ([P, I64, P, I64, P], c_int32),
-    "gs_tile_count_ordered_hits": ([P, P, I64, I32, I32, I32, D, P, P, P], c_int32),
-    "gs_tile_emit_hits": ([P, P, P, P, I64, I32, I32, I32, D, P, P, P], c_int32),
+    "gs_tile_count_ordered_hits": ([P, P, I64, I32, I32, I32, D, I32, I32, P, P, P], c_int32),
+    "gs_tile_emit_hits": ([P, P, P, P, I64, I32, I32, I32, D, I32, I32, P, P, P], c_int32),
     "gs_tile_bin_count": ([P, I64, I32, I32, I32, D, P, P], c_int32),
     "gs_tile_bin_offsets": ([P, I64, P, P, P, P, P], c_int32),
     "gs_tile_bin_emit": ([P, P, I64, I32, I32, I32, D, I32, P, P, P], c_int32),

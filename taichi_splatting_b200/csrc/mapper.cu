@@ -162,20 +162,24 @@ tile_emit_ordered_kernel(const float *__restrict__ gaussians, const int32_t *__r
 // tiles (huge splats) are marked and re-queried.
 __global__ void __launch_bounds__(128)
 tile_count_hits_kernel(const float *__restrict__ gaussians, const int32_t *__restrict__ order, int64_t v, int w_pad,
-                       int h_pad, int ts, float thr, int32_t *__restrict__ counts, ulonglong2 *__restrict__ hits) {
+                       int h_pad, int ts, float thr, int tile_lo, int tile_hi, int32_t *__restrict__ counts,
+                       ulonglong2 *__restrict__ hits) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= v) return;
   ObbQuery q = obb_grid_query(gaussians + 7 * (int64_t)order[r], w_pad, h_pad, ts, thr);
   int c = 0;
   unsigned long long mask = 0ull;
   const bool small = q.spanx * q.spany <= 64;
+  const int tiles_wide = w_pad / ts;
   int bit = 0;
   for (int u = 0; u < q.spanx; ++u)
-    for (int w = 0; w < q.spany; ++w, ++bit)
-      if (test_tile(q, u, w, ts)) {
+    for (int w = 0; w < q.spany; ++w, ++bit) {
+      const int tile = (q.minx + u) + (q.miny + w) * tiles_wide;   // tile-sharded runs keep only [tile_lo, tile_hi)
+      if (tile >= tile_lo && tile < tile_hi && test_tile(q, u, w, ts)) {
         ++c;
         if (small) mask |= 1ull << bit;
       }
+    }
   counts[r] = c;
   const unsigned long long box = (unsigned long long)(unsigned)q.minx | ((unsigned long long)(unsigned)q.miny << 16) |
                                  ((unsigned long long)(unsigned)(small ? q.spanx : 0xffff) << 32) |
@@ -186,7 +190,7 @@ tile_count_hits_kernel(const float *__restrict__ gaussians, const int32_t *__res
 __global__ void __launch_bounds__(128)
 tile_emit_hits_kernel(const float *__restrict__ gaussians, const int32_t *__restrict__ order,
                       const int32_t *__restrict__ cum, const ulonglong2 *__restrict__ hits, int64_t v, int w_pad,
-                      int h_pad, int ts, float thr, uint32_t *__restrict__ tile_keys,
+                      int h_pad, int ts, float thr, int tile_lo, int tile_hi, uint32_t *__restrict__ tile_keys,
                       int32_t *__restrict__ overlap_to_point) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= v) return;
@@ -199,12 +203,14 @@ tile_emit_hits_kernel(const float *__restrict__ gaussians, const int32_t *__rest
   if (spanx == 0xffff) {   // span too large for the mask: run the query again
     ObbQuery q = obb_grid_query(gaussians + 7 * (int64_t)i, w_pad, h_pad, ts, thr);
     for (int u = 0; u < q.spanx; ++u)
-      for (int w = 0; w < q.spany; ++w)
-        if (test_tile(q, u, w, ts)) {
-          tile_keys[k] = (uint32_t)((q.minx + u) + (q.miny + w) * tiles_wide);
+      for (int w = 0; w < q.spany; ++w) {
+        const int tile = (q.minx + u) + (q.miny + w) * tiles_wide;
+        if (tile >= tile_lo && tile < tile_hi && test_tile(q, u, w, ts)) {
+          tile_keys[k] = (uint32_t)tile;
           overlap_to_point[k] = i;
           ++k;
         }
+      }
     return;
   }
   unsigned long long mask = h.y;
@@ -530,27 +536,31 @@ extern "C" int gs_tile_emit_ordered(const float *gaussians, const int32_t *order
 }
 
 extern "C" int gs_tile_count_ordered_hits(const float *gaussians, const int32_t *order, int64_t v, int32_t w_pad,
-                                          int32_t h_pad, int32_t ts, double alpha_threshold, int32_t *counts,
-                                          void *hits, void *stream) {
+                                          int32_t h_pad, int32_t ts, double alpha_threshold, int32_t tile_lo,
+                                          int32_t tile_hi, int32_t *counts, void *hits, void *stream) {
+  if (tile_lo == 0 && tile_hi == 0) tile_hi = 0x7fffffff;   // (0, 0): every tile
   GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_count: image %dx%d not padded to tile %d", w_pad, h_pad, ts);
   GS_CHECK_ARG((int64_t)(w_pad / ts) * (h_pad / ts) < 65535, "tile dimensions (%d, %d) exceed maximum tile count (16 bit id), try increasing tile_size", h_pad / ts, w_pad / ts);
   GS_CHECK_ARG(hits != nullptr || v == 0, "tile_count_hits: hits is NULL");
   GS_CHECK_ARG((reinterpret_cast<uintptr_t>(hits) & 15) == 0, "tile_count_hits: hits must be 16-byte aligned");
   if (v == 0) return GS_OK;
   gs::tile_count_hits_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
-      gaussians, order, v, w_pad, h_pad, ts, (float)alpha_threshold, counts, reinterpret_cast<ulonglong2 *>(hits));
+      gaussians, order, v, w_pad, h_pad, ts, (float)alpha_threshold, tile_lo, tile_hi, counts,
+      reinterpret_cast<ulonglong2 *>(hits));
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
 
 extern "C" int gs_tile_emit_hits(const float *gaussians, const int32_t *order, const int32_t *cum, const void *hits,
                                  int64_t v, int32_t w_pad, int32_t h_pad, int32_t ts, double alpha_threshold,
-                                 uint32_t *tile_keys, int32_t *overlap_to_point, void *stream) {
+                                 int32_t tile_lo, int32_t tile_hi, uint32_t *tile_keys, int32_t *overlap_to_point,
+                                 void *stream) {
+  if (tile_lo == 0 && tile_hi == 0) tile_hi = 0x7fffffff;
   GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_emit: image not padded to tile size");
   if (v == 0) return GS_OK;
   gs::tile_emit_hits_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
       gaussians, order, cum, reinterpret_cast<const ulonglong2 *>(hits), v, w_pad, h_pad, ts, (float)alpha_threshold,
-      tile_keys, overlap_to_point);
+      tile_lo, tile_hi, tile_keys, overlap_to_point);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

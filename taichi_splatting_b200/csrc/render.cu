@@ -177,10 +177,12 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
     *max_per_tile_out = (int64_t)aux->host_words[2];
     return GS_OK;
   }
+  GS_CHECK_ARG((a->tile_lo == 0 && a->tile_hi == 0) || a->hits != nullptr, "render_stage_a: a tile range needs the hit-record buffer");
   // ---- tile mapper, first half (two-level ordering): depth order -> counts -> scan -> K ----
   GS_TRY(gs_depth_order(a->ndc, v, a->use_depth16, a->order, a->ws_order, a->ws_order_bytes, stream));
   if (a->hits != nullptr)   // count and emit share one grid query through per-Gaussian hit records
-    GS_TRY(gs_tile_count_ordered_hits(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, a->hits, stream));
+    GS_TRY(gs_tile_count_ordered_hits(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->tile_lo, a->tile_hi,
+                                      a->counts, a->hits, stream));
   else
     GS_TRY(gs_tile_count_ordered(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, stream));
   GS_TRY(gs_tile_scan(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[1], stream));
@@ -233,7 +235,8 @@ static int gs::stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64
     }
     if (k > 0) {
       if (a->hits != nullptr && !binned)
-        GS_TRY(gs_tile_emit_hits(a->points, a->order, a->cum, a->hits, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p, stream));
+        GS_TRY(gs_tile_emit_hits(a->points, a->order, a->cum, a->hits, v, w_pad, h_pad, ts, c.alpha_threshold, a->tile_lo,
+                                 a->tile_hi, tiles, o2p, stream));
       else
         GS_TRY(gs_tile_emit_ordered(a->points, a->order, a->cum, v, w_pad, h_pad, ts, c.alpha_threshold, tiles, o2p,
                                     stream));

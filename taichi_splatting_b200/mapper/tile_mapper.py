@@ -95,14 +95,16 @@ def bin_and_sort_binned(g: torch.Tensor, d: torch.Tensor, image_size, config, us
   return o2p, tile_ranges
 
 
-def bin_and_sort(g: torch.Tensor, d: torch.Tensor, image_size, config, use_depth16: bool = False):
+def bin_and_sort(g: torch.Tensor, d: torch.Tensor, image_size, config, use_depth16: bool = False,
+                 tile_range=(0, 0)):
   """The two-level ordering on contiguous fp32 inputs g (V,7), d (V,) -> (overlap_to_point (K,), tile_ranges
   (TH,TW,2), sorted tile ids (K,) int32, order (V,) int32, counts in depth order (V,) int32).
 
   Same final order as the reference's single 48-bit LSD radix sort over (tile | depth) (tile_mapper.py:148-157):
   such a sort is a stable sort by depth followed by a stable sort by tile, and all overlaps of one Gaussian share
   its depth, so the depth passes run on the V Gaussians before the expansion to K overlaps (gs_depth_order), the
-  overlaps are emitted in that order keyed by tile id only, and one stable sort on ceil(log2 T) bits finishes it."""
+  overlaps are emitted in that order keyed by tile id only, and one stable sort on ceil(log2 T) bits finishes it.
+  tile_range (lo, hi): keep only the overlaps of tiles lo <= id < hi (a tile-sharded multi-GPU rank); (0, 0): all."""
   device = g.device
   ts = config.tile_size
   w_pad, h_pad = pad_to_tile(image_size, ts)
@@ -124,7 +126,8 @@ def bin_and_sort(g: torch.Tensor, d: torch.Tensor, image_size, config, use_depth
   cum = torch.empty((v + 1,), dtype=torch.int32, device=device)
   # count and emit share ONE grid query: the count kernel leaves a 16-byte hit record per Gaussian for the emit kernel
   hits = torch.empty((v, 2), dtype=torch.int64, device=device)
-  call("gs_tile_count_ordered_hits", ptr(g), ptr(order), v, w_pad, h_pad, ts, thr, ptr(counts), ptr(hits), stream)
+  call("gs_tile_count_ordered_hits", ptr(g), ptr(order), v, w_pad, h_pad, ts, thr, tile_range[0], tile_range[1], ptr(counts),
+       ptr(hits), stream)
   call("gs_tile_scan_workspace_bytes", v, nbytes)
   ws2 = _lib.workspace(nbytes.value, device)
   word = _lib.host_word(device)
@@ -135,8 +138,8 @@ def bin_and_sort(g: torch.Tensor, d: torch.Tensor, image_size, config, use_depth
   tiles = torch.empty((2, k), dtype=torch.int32, device=device)
   o2p = torch.empty((2, k), dtype=torch.int32, device=device)
   if k > 0:
-    call("gs_tile_emit_hits", ptr(g), ptr(order), ptr(cum), ptr(hits), v, w_pad, h_pad, ts, thr, ptr(tiles[0]), ptr(o2p[0]),
-         stream)
+    call("gs_tile_emit_hits", ptr(g), ptr(order), ptr(cum), ptr(hits), v, w_pad, h_pad, ts, thr, tile_range[0], tile_range[1],
+         ptr(tiles[0]), ptr(o2p[0]), stream)
     call("gs_sort_pairs_workspace_bytes", k, 4, nbytes)
     ws3 = _lib.workspace(nbytes.value, device)
     call("gs_sort_pairs", ptr(tiles[0]), ptr(o2p[0]), ptr(tiles[1]), ptr(o2p[1]), k, 4, 0, tile_bits(num_tiles),

@@ -180,6 +180,54 @@ def mask_tile_ranges(tile_ranges: torch.Tensor, lo: int, hi: int) -> torch.Tenso
   return out.view_as(tile_ranges)
 
 
+class TileShard:
+  """This rank's share of a tile-sharded single view (`render_tile_sharded`).
+
+  The tile grid is cut into `world` contiguous tile-id ranges.  Every rank runs the cheap O(N) front end on the whole
+  cloud (projection, SH, depth order) but counts / emits / sorts / packs / rasterises ONLY the overlaps of its own
+  tiles (the tile mapper filters by tile id), so the K-sized work is divided by `world`.  The backward sums the
+  per-Gaussian gradients of the packed 2D Gaussians and features over ranks with ONE NCCL all-reduce (40 B per visible
+  Gaussian at 3 features) and then runs the SH / projection backward replicated, so every rank ends with the full
+  parameter gradients.
+
+  Boundaries start as equal tile counts; `rebalance(tile_ranges)` (call it after a frame: one small all-reduce and a
+  host read) moves them so that every rank holds the same number of overlaps, using that frame's per-tile counts --
+  consecutive frames of a training run see almost the same distribution."""
+  kind = "tile"
+
+  def __init__(self, group=None):
+    self.group = group
+    self.rank, self.world = world_info(group)
+    self.bounds = None        # (world + 1,) int64 CPU tensor of tile-id boundaries
+    self.num_tiles = None
+    self.last_tile_ranges = None   # this rank's (TH,TW,2) tile ranges of the last frame rendered through this shard
+    self.last_k = 0                # ... and its number of overlaps
+
+  def tile_range(self, num_tiles: int) -> Tuple[int, int]:
+    if self.bounds is None or self.num_tiles != num_tiles:
+      self.bounds = torch.tensor([(num_tiles * r) // self.world for r in range(self.world + 1)], dtype=torch.int64)
+      self.num_tiles = num_tiles
+    return int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+
+  def rebalance(self, tile_ranges: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tile_ranges: this rank's (TH,TW,2) ranges of a frame (foreign tiles are (0,0)); default: the last frame rendered
+    through this shard.  Returns the new bounds."""
+    tile_ranges = tile_ranges if tile_ranges is not None else self.last_tile_ranges
+    assert tile_ranges is not None, "rebalance: render a frame through this shard first"
+    r = tile_ranges.reshape(-1, 2)
+    counts = (r[:, 1] - r[:, 0]).clamp_min(0).to(torch.int64)
+    if self.world > 1:
+      dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)   # tile ownership is disjoint: the sum is the union
+    csum = torch.cumsum(counts, 0)
+    self.bounds = partition_tiles(torch.stack([csum - counts, csum], dim=1), self.world)
+    self.num_tiles = counts.shape[0]
+    return self.bounds
+
+  def reduce(self, flat: torch.Tensor) -> None:
+    if self.world > 1:
+      dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+
+
 class _ReduceGradAcrossRanks(torch.autograd.Function):
   """Identity in the forward; all-reduce(sum) of the incoming gradients in the backward."""
 
@@ -204,16 +252,43 @@ def reduce_across_ranks(*tensors: torch.Tensor, group=None):
   return _ReduceGradAcrossRanks.apply(group, *tensors)
 
 
-def render_tile_sharded(gaussians, camera_params, config, use_sh: bool = False, group=None):
-  """Single view split over ranks by tile ranges.  Returns (Rendering, (tile_lo, tile_hi)); the rendering's image
-  holds this rank's tiles only (zeros elsewhere), so a per-pixel loss can be evaluated locally and summed."""
+def render_tile_sharded(gaussians, camera_params, config, use_sh: bool = False, group=None, shard: Optional[TileShard] = None,
+                        use_depth16: bool = False, render_median_depth: bool = False):
+  """Single view split over ranks by contiguous tile-id ranges.  Returns (Rendering, (tile_lo, tile_hi)); the
+  rendering's image holds this rank's tiles only (zeros elsewhere), so a per-pixel loss can be evaluated locally and
+  summed; `points.visibility` / heuristics are this rank's partial sums (sum over ranks = the single-GPU values).
+
+  Pass the same `shard` object every frame (and call `shard.rebalance(...)` now and then) to keep the overlap counts
+  of the ranks balanced; without it the tile grid is cut into equal tile counts.  fp32 / tile 16 / alpha blending run
+  through the whole-frame drivers (this rank bins, sorts, packs and rasterises only its own tiles); other
+  configurations fall back to the operator chain with masked tile ranges."""
+  from .renderer import _RenderFunction, _wrap_rendering
+  from .rasterizer.function import tuned_supported
+  shard = shard if shard is not None else TileShard(group)
+  feature = gaussians.feature
+  channels = feature.shape[1] if feature.ndim >= 2 else 0
+  if (feature.dtype == torch.float32 and config.use_alpha_blending and tuned_supported(config, channels, feature.dtype)
+      and feature.ndim == (3 if use_sh else 2)):
+    outs = _RenderFunction.apply(*gaussians.shape_tensors(), feature, camera_params.T_camera_world,
+                                 camera_params.projection, camera_params, config, use_sh, use_depth16,
+                                 render_median_depth, shard)
+    ts = config.tile_size
+    w, h = camera_params.image_size
+    num_tiles = ((w + ts - 1) // ts) * ((h + ts - 1) // ts)
+    shard.last_tile_ranges, shard.last_k = outs[-1].detach(), int(outs[-2].shape[0])
+    return _wrap_rendering(outs, camera_params, config, render_median_depth), shard.tile_range(num_tiles)
+  return _render_tile_sharded_operators(gaussians, camera_params, config, use_sh, shard)
+
+
+def _render_tile_sharded_operators(gaussians, camera_params, config, use_sh, shard):
+  """Operator-chain form of render_tile_sharded (any dtype / tile size): every rank maps all overlaps, empties the
+  ranges of foreign tiles, and an identity-forward / all-reduce-backward node sums the 2D gradients."""
   from .mapper.tile_mapper import map_to_tiles
   from .perspective.projection import apply_with_ndc, camera_position
   from .rasterizer.function import rasterize_with_tiles
   from .rendering import RenderedPoints, Rendering
   from .spherical_harmonics import evaluate_sh_at
 
-  rank, world = world_info(group)
   g2d, depths, indexes, ndc = apply_with_ndc(
       *gaussians.shape_tensors(), camera_params.T_camera_world, camera_params.projection, camera_params.image_size,
       camera_params.depth_range, config.blur_cov, config.clamp_margin, config.alpha_threshold)
@@ -223,10 +298,9 @@ def render_tile_sharded(gaussians, camera_params, config, use_sh: bool = False, 
   else:
     features = gaussians.feature[indexes]
   overlap_to_point, tile_ranges = map_to_tiles(g2d, ndc, camera_params.image_size, config)
-  bounds = partition_tiles(tile_ranges, world)
-  lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+  lo, hi = shard.tile_range(tile_ranges.shape[0] * tile_ranges.shape[1])
   local_ranges = mask_tile_ranges(tile_ranges, lo, hi)
-  g2d_r, features_r = reduce_across_ranks(g2d, features, group=group)
+  g2d_r, features_r = reduce_across_ranks(g2d, features, group=shard.group)
   raster = rasterize_with_tiles(g2d_r, features_r, overlap_to_point, local_ranges.view(-1, 2),
                                 camera_params.image_size, config)
   points = RenderedPoints(idx=indexes, depths=depths, gaussians2d=g2d,

@@ -68,6 +68,8 @@ class _RenderFunction(torch.autograd.Function):
     channels = feature.shape[1] if feature.ndim >= 2 else 0
     ctx.fused_host = (_FUSED_HOST and dtype == torch.float32 and config.use_alpha_blending
                       and tuned_supported(config, channels, dtype) and feature.ndim == (3 if use_sh else 2))
+    assert getattr(sh_exchange, "kind", None) != "tile" or ctx.fused_host, \
+        "tile-sharded rendering runs through the whole-frame drivers (fp32, tile 16, alpha blending, GS_FUSED_HOST != 0)"
     if ctx.fused_host:
       return _RenderFunction._forward_fused_host(ctx, position, log_scaling, rotation, alpha_logit, feature,
                                                  T_camera_world, projection, camera, config, use_sh, use_depth16,
@@ -229,7 +231,11 @@ class _RenderFunction(torch.autograd.Function):
         ws[0].data_ptr(), ws[0].numel(), ws[1].data_ptr(), ws[1].numel(), ws[2].data_ptr(), ws[2].numel(),
         ptr(image), ptr(alpha), ptr(median) if render_median_depth else None, ptr(tile_ranges),
         _event_handle(ev_fwd[0] if ev_fwd else None), _event_handle(ev_fwd[1] if ev_fwd else None),
-        ptr(tile_counts), ptr(tile_cursor), ptr(tile_totals), None, None, ptr(hits))
+        ptr(tile_counts), ptr(tile_cursor), ptr(tile_totals), None, None, ptr(hits), 0, 0)
+    tile_shard = sh_exchange if getattr(sh_exchange, "kind", None) == "tile" else None
+    if tile_shard is not None:   # this rank bins, sorts, packs and rasterises its own contiguous tile-id range only
+      assert ORDERING != "binned", "tile sharding uses the two-level ordering"
+      args.tile_lo, args.tile_hi = tile_shard.tile_range(num_tiles)
     rec_cols = 12 if F <= 3 else 16   # floats per packed raster record (gs_raster_pack_bytes)
     # K-sized buffers: sized from the previous frame on this device (+25 %), so that the driver can go from the
     # host read of K straight into key emission; if K outgrew them, allocate exactly and run stage B from here
@@ -276,8 +282,10 @@ class _RenderFunction(torch.autograd.Function):
     return image, alpha, g2d, depths, indexes, features, visibility, heuristic, median, overlap_to_point, tile_ranges
 
   @staticmethod
-  def _backward_fused_host(ctx, d_image, d_g2d, d_depths, d_features):
-    """The backward through gs_render_backward_f32 (single GPU; view-parallel runs use the staged path)."""
+  def _backward_fused_host(ctx, d_image, d_g2d, d_depths, d_features, tile_shard=None):
+    """The backward through gs_render_backward_f32.  tile_shard (tile-sharded multi-GPU run): the raster backward
+    leaves this rank's partial sums of the packed-2D / feature gradients (its own tiles only) in ONE flat buffer,
+    which is summed over ranks by a single NCCL all-reduce before the replicated SH / projection backward."""
     (position, log_scaling, rotation, alpha_logit, T_camera_world, projection, feature, indexes, g2d, features, image,
      overlap_to_point, ranges, cam_pos, digest) = ctx.saved_tensors
     config, (w, h), blur, margin, use_sh, heuristic = ctx.meta
@@ -288,8 +296,16 @@ class _RenderFunction(torch.autograd.Function):
     grads = [torch.empty_like(t) if need[i] else None
              for t, i in ((position, 0), (log_scaling, 1), (rotation, 2), (alpha_logit, 3), (T_camera_world, 5), (projection, 6))]
     d_feature = torch.empty_like(feature) if need[4] else None
-    grad_g = d_g2d.clone() if d_g2d is not None else torch.empty_like(g2d)
-    grad_f = (d_features.clone() if d_features is not None else torch.empty_like(features)) if need[4] else None
+    if tile_shard is not None:
+      flat = torch.empty((v * (7 + F),), dtype=torch.float32, device=device)
+      grad_g, grad_f = flat[:7 * v].view(v, 7), flat[7 * v:].view(v, F)
+      if d_g2d is not None:        # incoming gradients enter the sum once (they are replicated over ranks)
+        grad_g.copy_(d_g2d if tile_shard.rank == 0 else torch.zeros_like(d_g2d))
+      if d_features is not None:
+        grad_f.copy_(d_features if tile_shard.rank == 0 else torch.zeros_like(d_features))
+    else:
+      grad_g = d_g2d.clone() if d_g2d is not None else torch.empty_like(g2d)
+      grad_f = (d_features.clone() if d_features is not None else torch.empty_like(features)) if need[4] else None
     # the SH view directions depend on the camera centre inverse(T)[:3,3]: when the pose is trained, its gradient
     # through them is chained into d_T_camera_world below (reference: autograd through camera_params.camera_position)
     d_cam = torch.empty((3,), dtype=torch.float32, device=device) if (use_sh and need[4] and need[5]) else None
@@ -311,6 +327,11 @@ class _RenderFunction(torch.autograd.Function):
         *[ptr(g) for g in grads], ptr(d_feature),
         _event_handle(ev_bwd[0] if ev_bwd else None), _event_handle(ev_bwd[1] if ev_bwd else None), d_image_strides,
         ptr(d_cam), 0)
+    if tile_shard is not None and tile_shard.world > 1:
+      args.phases = _lib.GS_BWD_RASTER
+      _lib.call("gs_render_backward_f32", args, _lib.stream_ptr(device))
+      tile_shard.reduce(flat)      # THE collective of the tile-sharded path: 4 (7 + F) bytes per visible Gaussian
+      args.phases = _lib.GS_BWD_FEATURE | _lib.GS_BWD_PROJECT
     _lib.call("gs_render_backward_f32", args, _lib.stream_ptr(device))
     if d_cam is not None:
       grads[4] += camera_position_vjp(T_camera_world, cam_pos, d_cam)
@@ -371,6 +392,8 @@ class _RenderFunction(torch.autograd.Function):
   def backward(ctx, d_image, d_alpha, d_g2d, d_depths, d_indexes, d_features, *unused):
     if ctx.fused_host:
       exchange = ctx.sh_exchange
+      if getattr(exchange, "kind", None) == "tile":
+        return _RenderFunction._backward_fused_host(ctx, d_image, d_g2d, d_depths, d_features, tile_shard=exchange)
       if exchange is None or exchange.world <= 1 or not (ctx.needs_input_grad[4] and ctx.meta[4]):
         return _RenderFunction._backward_fused_host(ctx, d_image, d_g2d, d_depths, d_features)
       if os.environ.get("GS_VIEW_PARALLEL_STAGED", "0") != "1":

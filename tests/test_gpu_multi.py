@@ -51,16 +51,39 @@ def _worker(rank, world, port, results):
     (ref.image * R).sum().backward()
     ref_grads = {k: getattr(cloud, k).grad.clone() for k in names}
 
-    # ---- tile-sharded ----
-    cloud2, cam2, _ = _scene(ts, dev)
-    out, (lo, hi) = parallel.render_tile_sharded(cloud2, cam2, cfg, use_sh=True)
-    (out.image * R).sum().backward()
-    full = out.image.detach().clone()
-    dist.all_reduce(full)                       # strips are disjoint, so the sum is the union
-    assert _rel(full, ref.image.detach()) < 1e-6, _rel(full, ref.image.detach())
+    # ---- tile-sharded: whole-frame drivers (each rank bins / sorts / packs / rasterises its own tile range), first with
+    # equal tile counts, then rebalanced to equal overlap counts; then the operator-chain form (tile size 8) ----
+    shard = parallel.TileShard()
+    ks = []
+    for frame in range(2):
+      cloud2, cam2, _ = _scene(ts, dev)
+      out, (lo, hi) = parallel.render_tile_sharded(cloud2, cam2, cfg, use_sh=True, shard=shard)
+      (out.image * R).sum().backward()
+      full = out.image.detach().clone()
+      dist.all_reduce(full)                       # strips are disjoint, so the sum is the union
+      assert _rel(full, ref.image.detach()) < 1e-6, _rel(full, ref.image.detach())
+      for k in names:
+        assert _rel(getattr(cloud2, k).grad, ref_grads[k]) < 2e-5, (frame, k, _rel(getattr(cloud2, k).grad, ref_grads[k]))
+      assert 0 <= lo <= hi
+      k_all = torch.tensor([shard.last_k], device=dev)
+      gathered = [torch.zeros_like(k_all) for _ in range(world)]
+      dist.all_gather(gathered, k_all)
+      ks.append([int(x) for x in gathered])
+      shard.rebalance()
+    assert sum(ks[0]) == sum(ks[1])                                            # same overlaps, cut differently
+    assert max(ks[1]) - min(ks[1]) <= max(ks[0]) - min(ks[0]) + 600, ks         # rebalanced: no worse than equal tiles
+    cfg8 = ts.RasterConfig(tile_size=8)
+    ref8_cloud, ref8_cam, _ = _scene(ts, dev)
+    ref8 = ts.render_gaussians(ref8_cloud, ref8_cam, cfg8, use_sh=True)
+    (ref8.image * R).sum().backward()
+    cloud3, cam3, _ = _scene(ts, dev)
+    out8, _ = parallel.render_tile_sharded(cloud3, cam3, cfg8, use_sh=True)
+    (out8.image * R).sum().backward()
+    full8 = out8.image.detach().clone()
+    dist.all_reduce(full8)
+    assert _rel(full8, ref8.image.detach()) < 1e-6
     for k in names:
-      assert _rel(getattr(cloud2, k).grad, ref_grads[k]) < 2e-5, (k, _rel(getattr(cloud2, k).grad, ref_grads[k]))
-    assert 0 <= lo <= hi
+      assert _rel(getattr(cloud3, k).grad, getattr(ref8_cloud, k).grad) < 2e-5, ("operators", k)
 
     # ---- view-parallel ----
     per_view = []

@@ -148,5 +148,8 @@ def test_bench_line_contract():
   spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
   bench = importlib.util.module_from_spec(spec)
   spec.loader.exec_module(bench)
-  _, total = bench.algorithmic_bytes(1_000_000, 1_000_000, 3_838_201, 2048 * 2048, 16384, 3, 16)
+  _, total = bench.algorithmic_bytes(1_000_000, 1_000_000, 3_838_201, 2048 * 2048, 16384, 3, 16, dense_grad_image=True)
   assert abs(total / 1e9 - 2.22) < 0.02, total
+  # the bench's image.sum() loss hands the backward an expanded scalar instead of a dense (H,W,3) gradient: 4PF fewer bytes
+  _, total_sum = bench.algorithmic_bytes(1_000_000, 1_000_000, 3_838_201, 2048 * 2048, 16384, 3, 16)
+  assert total - total_sum == 4 * 2048 * 2048 * 3

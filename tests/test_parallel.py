@@ -44,6 +44,23 @@ def _worker(rank, world, port, results):
     assert torch.allclose(x.grad, 2 * x.detach() * sum(k + 1 for k in range(world)))
     assert torch.allclose(y.grad, torch.full((4,), float(sum(k + 2 for k in range(world))), dtype=torch.float64))
     assert parallel.views_for_rank(8, rank, world) == list(range(rank, 8, world))
+    # tile shard: equal tile counts first, then equal overlap counts from the ranks' own (disjoint) tile ranges
+    shard = parallel.TileShard()
+    T = 40
+    lo, hi = shard.tile_range(T)
+    assert (lo, hi) == (T * rank // world, T * (rank + 1) // world)
+    counts = torch.arange(T, dtype=torch.int32) * 3 + 1             # heavier tiles at the end of the grid
+    ends = torch.cumsum(counts, 0).to(torch.int32)
+    full = torch.stack([ends - counts, ends], 1)
+    mine = torch.zeros_like(full)
+    mine[lo:hi] = full[lo:hi] - full[lo, 0]                         # a rank's ranges index its OWN overlap list
+    b = shard.rebalance(mine.view(4, 10, 2))
+    assert b.tolist() == parallel.partition_tiles(full, world).tolist() and shard.tile_range(T) == (int(b[rank]), int(b[rank + 1]))
+    per_rank = [int(counts[int(b[r]):int(b[r + 1])].sum()) for r in range(world)]
+    assert max(per_rank) - min(per_rank) <= int(counts.max())
+    flat = torch.full((6,), float(rank + 1))
+    shard.reduce(flat)
+    assert torch.equal(flat, torch.full((6,), float(sum(k + 1 for k in range(world)))))
     results[rank] = "ok"
   finally:
     dist.destroy_process_group()
