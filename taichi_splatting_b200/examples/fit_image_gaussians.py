@@ -3,10 +3,14 @@
 Reference: taichi_splatting/examples/fit_image_gaussians.py:89-147,234-358 (BASELINE config 1: 256x256, n=2000).
 Same forward / loss / backward through `rasterize` as the reference, and by default the reference's optimiser setup
 (:267-281): VisibilityAwareLaProp over the visible points with a `local_vector` position group stepped in each
-Gaussian's own basis, through `taichi_splatting_b200.optim`.  `--opt adam` uses torch.optim.Adam instead.  The
-reference's split / prune densification (host-side torch, :190-230) is not part of this version.
+Gaussian's own basis, through `taichi_splatting_b200.optim`.  `--opt adam` uses torch.optim.Adam instead.
+`--target N` turns on the reference's densification (:190-230, 299-340): training runs in epochs; the raster backward's
+per-point heuristics (prune cost, split score) are accumulated over an epoch, and between epochs the least useful
+points are pruned and the most pulled-on ones split until the cloud has N points (`misc/densify.py`), the sparse
+optimiser's per-point state following its rows.
 
   python -m taichi_splatting_b200.examples.fit_image_gaussians [--image path.png] [--n 2000] [--iters 200] [--opt laprop]
+      [--target 4000 --epoch 50 --prune_rate 0.04]
 """
 import argparse
 import math
@@ -15,6 +19,7 @@ import torch
 
 from ..benchmarks.scenes import random_2d_gaussians
 from ..data_types import RasterConfig
+from ..misc.densify import split_prune
 from ..misc.renderer2d import point_basis, project_gaussians2d
 from ..optim import SparseAdam, VisibilityAwareLaProp
 from ..rasterizer import rasterize
@@ -40,6 +45,9 @@ def main(argv=None):
   ap.add_argument("--opt", type=str, default="laprop", choices=["laprop", "sparse_adam", "adam"],
                   help="laprop: VisibilityAwareLaProp (the reference's choice); sparse_adam: SparseAdam; adam: torch Adam")
   ap.add_argument("--device", type=str, default="cuda:0")
+  ap.add_argument("--target", type=int, default=None, help="densify: split / prune between epochs until the cloud has this many points")
+  ap.add_argument("--epoch", type=int, default=50, help="iterations per densification epoch")
+  ap.add_argument("--prune_rate", type=float, default=0.04, help="fraction of points pruned per epoch (decays to 0 over training)")
   args = ap.parse_args(argv)
   device = torch.device(args.device)
 
@@ -68,13 +76,25 @@ def main(argv=None):
       opt = VisibilityAwareLaProp(groups, vis_smooth=0.1, vis_beta=0.8, betas=(0.9, 0.9), eps=1e-16, bias_correction=True)
     else:
       opt = SparseAdam(groups, betas=(0.9, 0.95), eps=1e-16, bias_correction=True)
-  config = RasterConfig(tile_size=args.tile_size, compute_visibility=True)
+  densify = args.target is not None
+  assert not (densify and args.opt == "adam"), "densification carries per-point optimiser state: use --opt laprop | sparse_adam"
+  config = RasterConfig(tile_size=args.tile_size, compute_visibility=True, compute_point_heuristic=densify)
+  heuristics = torch.zeros((g.batch_size[0], 2), device=device)
 
   for it in range(args.iters):
+    if densify and it > 0 and it % args.epoch == 0 and it + args.epoch <= args.iters:
+      # between epochs: prune by accumulated prune cost, split by accumulated split score (reference :299-340)
+      n_before = g.batch_size[0]
+      g, info = split_prune(g, t=it / args.iters, target=args.target, prune_rate=args.prune_rate,
+                            heuristics=(heuristics[:, 0], heuristics[:, 1]), optimizer=opt)
+      heuristics = torch.zeros((g.batch_size[0], 2), device=device)
+      print(f"iter {it:5d}  densify: {n_before} -> {g.batch_size[0]} points (split {info['split']}, pruned {info['prune']})")
     opt.zero_grad(set_to_none=True)
     raster = rasterize(project_gaussians2d(g), torch.clamp(g.depths, 0, 1), g.feature, (w, h), config)
     loss = torch.nn.functional.mse_loss(raster.image, ref_image)
     loss.backward()
+    if densify:
+      heuristics += raster.point_heuristic
     if args.opt == "adam":
       opt.step()
     else:   # step the visible points only (:125-136)
@@ -87,7 +107,7 @@ def main(argv=None):
         opt.step(indexes=visible, basis=basis)
     if it % 50 == 0 or it == args.iters - 1:
       visible = int((raster.visibility > 0).sum())
-      print(f"iter {it:5d}  psnr {psnr(raster.image.detach(), ref_image):6.2f} dB  visible {visible}/{args.n}")
+      print(f"iter {it:5d}  psnr {psnr(raster.image.detach(), ref_image):6.2f} dB  visible {visible}/{g.batch_size[0]}")
   return psnr(raster.image.detach(), ref_image)
 
 

