@@ -891,6 +891,22 @@ def test_fit_image_example_converges(ts):
 
 
 # --------------------------------------------------------------------------------------- N4: Morton ordering
+def test_benchmark_clis_run(ts, capsys):
+  """N2: the four benchmark CLIs of the reference (pyproject.toml:37-43) run end to end on small inputs and report
+  positive rates for every phase they time."""
+  from taichi_splatting_b200.benchmarks import bench_projection, bench_rasterizer, bench_sh, bench_tilemapper
+  r = bench_projection.main(["--n", "20000", "--iters", "3", "--image_size", "320,240"])
+  assert set(r) == {"forward", "backward (gaussians)", "backward (extrinsics)", "backward (intrinsics)", "backward (everything)"}
+  assert all(v > 0 for v in r.values())
+  r = bench_sh.main(["--n", "20000", "--iters", "3", "--degree", "2"])
+  assert set(r) == {"forward", "backward (sh_features)", "backward (all)"} and all(v > 0 for v in r.values())
+  r = bench_tilemapper.main(["--n", "20000", "--iters", "3", "--image_size", "320,240", "--reference_sort"])
+  assert len(r) == 2 and all(v > 0 for v in r.values())
+  bench_rasterizer.main(["--n", "20000", "--iters", "2", "--image_size", "320,240"])
+  out = capsys.readouterr().out
+  assert "point_overlap=" in out and "backward (all)" in out
+
+
 def test_fit_image_with_densification_beats_fixed_cloud(ts):
   """N4: the image-fitting loop with heuristics-driven split / prune (600 -> 2400 points) ends above the same loop on
   the fixed 600-point cloud, the cloud reaches its target size, and the optimiser's per-point state follows the rows."""
