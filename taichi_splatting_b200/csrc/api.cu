@@ -5,9 +5,14 @@
 #include <mutex>
 #include <utility>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace gs {
+NvtxRange::NvtxRange(const char *name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+
 static thread_local char g_error[512] = "";
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -43,5 +48,5 @@ void *stream_workspace(cudaStream_t stream, size_t bytes) {
 }
 }  // namespace gs
 
-extern "C" int gs_version(void) { return 110; }
+extern "C" int gs_version(void) { return 120; }
 extern "C" const char *gs_last_error_string(void) { return gs::g_error; }

@@ -39,6 +39,15 @@ void *stream_workspace(cudaStream_t stream, size_t bytes);   // api.cu: library-
     }                                                                                  \
   } while (0)
 
+// NVTX ranges around the phases of the whole-frame drivers and the per-stage entry points (header-only NVTX v3: no
+// library to link; a no-op unless a profiler -- nsys, ncu --nvtx -- is attached).  The reference wraps its Taichi
+// launches in torch.profiler record_function ranges.
+struct NvtxRange {
+  explicit NvtxRange(const char *name);
+  ~NvtxRange();
+};
+#define GS_NVTX(name) gs::NvtxRange _gs_nvtx_range(name)
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -196,7 +196,7 @@ struct OptimMultiArgs {
 };
 
 template <bool LAPROP, bool BIAS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)   // 48 registers like the single-group kernels (62 without the bound: 4 blocks / SM)
 optim_multi_kernel(const int64_t *__restrict__ indexes, const float *__restrict__ weight,
                    const float *__restrict__ grad_scale, const float *__restrict__ total_weight,
                    const __grid_constant__ OptimMultiArgs a) {

@@ -121,6 +121,7 @@ extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, in
   DeviceAux *aux = device_aux(stream);
   if (aux == nullptr) { set_error("render_stage_a: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
   std::lock_guard<std::recursive_mutex> frame_lock(aux->frame_mu);
+  GS_NVTX("gs_render_stage_a: project, SH, digest, depth order, tile count, scan");
   cudaStream_t side = use_side_stream() ? aux->side_stream : stream;
   const int rc = stage_a_impl(a, v_out, k_out, max_per_tile_out, stream, aux, side);
   if (rc != GS_OK) SideJoin(stream, side, aux->bwd_join);   // error after auxiliary work was enqueued: join before returning
@@ -202,6 +203,7 @@ extern "C" int gs_render_stage_b_f32(const gs_render_args *a, int64_t v, int64_t
   DeviceAux *aux = device_aux(stream);
   if (aux == nullptr) { set_error("render_stage_b: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
   std::lock_guard<std::recursive_mutex> frame_lock(aux->frame_mu);
+  GS_NVTX("gs_render_stage_b: key emit, tile sort, ranges, raster pack, raster forward");
   const int rc = stage_b_impl(a, v, k, max_per_tile, k_stride, tiles, o2p, ws_sort, ws_sort_bytes, stream, aux);
   if (rc != GS_OK) GS_CUDA(cudaStreamWaitEvent(stream, aux->side_done, 0));   // stage A's auxiliary work still holds caller buffers
   return rc;
@@ -291,7 +293,8 @@ extern "C" int gs_render_backward_f32(const gs_render_bwd_args *a, void *stream_
   cudaStream_t stream = (cudaStream_t)stream_;
   DeviceAux *aux = device_aux(stream);
   if (aux == nullptr) { set_error("render_backward: cannot create the auxiliary stream"); return GS_ERR_CUDA; }
-  std::lock_guard<std::recursive_mutex> frame_lock(aux->frame_mu);   // one frame at a time per device: events / side stream are shared
+  std::lock_guard<std::recursive_mutex> frame_lock(aux->frame_mu);   // one frame at a time per (device, stream): events / side stream are shared
+  GS_NVTX("gs_render_backward: raster backward, SH backward, projection backward");
   cudaStream_t side = use_side_stream() ? aux->side_stream : stream;
   const int64_t n = a->n, v = a->v;
   const int F = a->channels;
