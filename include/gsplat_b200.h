@@ -307,10 +307,11 @@ int gs_raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int
                        int32_t width, int32_t height, int32_t num_features, void *records, void *flush_records,
                        void *stream);
 /* Same records from the sorted tile-id array (one thread per overlap instead of one CTA per tile; the whole-frame
- * driver has the array from its tile sort). */
+ * driver has the array from its tile sort).  tile_ranges_out (tiles, 2) or NULL: the same pass also writes the tile
+ * ranges (= gs_tile_ranges_from_tiles; replaces find_ranges_kernel, mapper/tile_mapper.py:92-112). */
 int gs_raster_pack_sorted_f32(const void *digest, const uint32_t *sorted_tiles, const int32_t *overlap_to_point,
                               int64_t k, int32_t width, int32_t height, int32_t num_features, void *records,
-                              void *flush_records, void *stream);
+                              void *flush_records, int32_t *tile_ranges_out, void *stream);
 int gs_raster_fwd_packed_f32(const void *records, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t v,
                              int64_t k, int32_t width, int32_t height, int32_t num_features,
                              const gs_raster_config *config, double median_threshold, float *image, float *image_alpha,
@@ -466,20 +467,6 @@ int gs_optim_step_f32(int32_t algorithm, int32_t vector, int32_t bias_correction
                       float *m_state, float *v_state, const float *total_weight, const float *grad, double lr,
                       double beta1, double beta2, double eps, float *lr_step, float *param, double clip,
                       const float *mask_lr, const float *point_lr, void *stream);
-/* Every fusable parameter group (scalar / vector kinds with `param` updated in place) of one optimiser step in ONE
- * launch -- the reference issues its kernel + torch passes once per group (optim/fractional.py:172-199).  All groups
- * share indexes / weight / grad_scale / total_weight; bias_correction and algorithm are per optimiser. */
-typedef struct gs_optim_group {
-  float *m_state, *v_state, *param;   /* (N,d); v_state (N,d) scalar kinds | (N) vector kinds */
-  const float *grad;                  /* (N,d) */
-  const float *mask_lr, *point_lr;    /* (d) / (N) or NULL */
-  double lr, beta1, beta2, eps, clip; /* clip <= 0: none */
-  int32_t d, vector;
-} gs_optim_group;
-int gs_optim_step_groups_f32(int32_t algorithm, int32_t bias_correction, const gs_optim_group *groups,
-                             int32_t num_groups /* <= 8 */, const int64_t *indexes, const float *weight,
-                             const float *grad_scale, double grad_smooth, int64_t m_rows, const float *total_weight,
-                             void *stream);
 int gs_optim_update_visibility_f32(float *running_vis, const float *visibility, const int64_t *indexes,
                                    float *total_weight, double beta, double eps, int64_t m_rows, float *weight_out,
                                    void *stream);

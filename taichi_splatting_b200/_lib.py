@@ -74,12 +74,6 @@ class RenderBwdArgsC(ctypes.Structure):
   ]
 
 
-class OptimGroupC(ctypes.Structure):
-  """struct gs_optim_group"""
-  _fields_ = [("m_state", P), ("v_state", P), ("param", P), ("grad", P), ("mask_lr", P), ("point_lr", P),
-              ("lr", D), ("beta1", D), ("beta2", D), ("eps", D), ("clip", D), ("d", I32), ("vector", I32)]
-
-
 _PROJECT_CULL = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, D, P, SZ, P, P]
 _PROJECT_WRITE = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, P, P, P, P, P, P]
 _PROJECT_BWD = [P, P, P, P, P, P, P, I64, I32, I32, D, D, P, P, P, P, P, P, P, P, P]
@@ -129,7 +123,7 @@ SIGNATURES = {
     "gs_raster_bwd_digest_strided_f32": ([P, P, P, P, P, POINTER(I64), I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
     "gs_raster_pack_bytes": ([I64, I32, POINTER(SZ), POINTER(SZ)], c_int32),
     "gs_raster_pack_f32": ([P, P, P, I64, I32, I32, I32, P, P, P], c_int32),
-    "gs_raster_pack_sorted_f32": ([P, P, P, I64, I32, I32, I32, P, P, P], c_int32),
+    "gs_raster_pack_sorted_f32": ([P, P, P, I64, I32, I32, I32, P, P, P, P], c_int32),
     "gs_raster_fwd_packed_f32": ([P, P, P, I64, I64, I32, I32, I32, POINTER(RasterConfigC), D, P, P, P, P, P], c_int32),
     "gs_raster_bwd_packed_f32": ([P, P, P, P, P, P, POINTER(I64), I64, I64, I32, I32, I32, POINTER(RasterConfigC), P, P, P, P], c_int32),
     "gs_render_stage_a_f32": ([POINTER(RenderArgsC), POINTER(I64), POINTER(I64), POINTER(I64), P], c_int32),
@@ -140,7 +134,6 @@ SIGNATURES = {
     "gs_morton_codes64": ([P, I64, POINTER(ctypes.c_float), POINTER(ctypes.c_float), I64, P, P, P], c_int32),
     "gs_optim_step_f32": ([I32, I32, I32, P, P, P, D, I64, I32, P, P, P, P, D, D, D, D, P, P, D, P, P, P], c_int32),
     "gs_optim_update_visibility_f32": ([P, P, P, P, D, D, I64, P, P], c_int32),
-    "gs_optim_step_groups_f32": ([I32, I32, POINTER(OptimGroupC), I32, P, P, P, D, I64, P, P], c_int32),
 }
 
 GS_BWD_RASTER, GS_BWD_FEATURE, GS_BWD_PROJECT = 1, 2, 4   # gs_render_bwd_args.phases
@@ -188,7 +181,7 @@ OWN_KERNELS = {
     # whole-frame drivers: cull, camera position, write, SH, digest, depth key, count, scan tail | emit, ranges, raster |
     # raster backward, projection backward, SH backward
     "gs_render_stage_a_f32": 8, "gs_render_stage_b_f32": 4, "gs_render_backward_f32": 3, "gs_render_forward_f32": 8,
-    "gs_optim_step_f32": 1, "gs_optim_step_groups_f32": 1, "gs_optim_update_visibility_f32": 1, "gs_morton_codes64": 1,
+    "gs_optim_step_f32": 1, "gs_optim_update_visibility_f32": 1, "gs_morton_codes64": 1,
 }
 
 

@@ -36,14 +36,14 @@ __device__ __forceinline__ float finish_step(float step, float w, int j, int64_t
 // saturate(w): five transcendental calls) are formed once per thread instead of once per component, and rows whose
 // width is a multiple of 4 move as float4.
 template <bool LAPROP, bool BIAS, bool VEC4>
-__device__ __forceinline__ void optim_scalar_body(int64_t t, const int64_t *__restrict__ indexes,
-                                                  const float *__restrict__ weight, const float *__restrict__ grad_scale,
-                                                  float *__restrict__ m_arr, float *__restrict__ v_arr,
-                                                  const float *__restrict__ total_weight, const float *__restrict__ grad,
-                                                  const OptimParams &p, float *__restrict__ lr_step,
-                                                  float *__restrict__ param, const float *__restrict__ mask_lr,
-                                                  const float *__restrict__ point_lr) {
+__global__ void __launch_bounds__(256)
+optim_scalar_kernel(const int64_t *__restrict__ indexes, const float *__restrict__ weight,
+                    const float *__restrict__ grad_scale, float *__restrict__ m_arr, float *__restrict__ v_arr,
+                    const float *__restrict__ total_weight, const float *__restrict__ grad, OptimParams p,
+                    float *__restrict__ lr_step, float *__restrict__ param, const float *__restrict__ mask_lr,
+                    const float *__restrict__ point_lr) {
   const int groups = (p.d + 3) >> 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.m_rows * groups) return;
   const int64_t i = t / groups;
   const int j0 = (int)(t - i * groups) * 4;
@@ -110,26 +110,15 @@ __device__ __forceinline__ void optim_scalar_body(int64_t t, const int64_t *__re
   }
 }
 
-template <bool LAPROP, bool BIAS, bool VEC4>
+// vector kinds: one running second moment per row (squared gradient norm); one thread per visible row
+template <bool LAPROP, bool BIAS>
 __global__ void __launch_bounds__(256)
-optim_scalar_kernel(const int64_t *__restrict__ indexes, const float *__restrict__ weight,
+optim_vector_kernel(const int64_t *__restrict__ indexes, const float *__restrict__ weight,
                     const float *__restrict__ grad_scale, float *__restrict__ m_arr, float *__restrict__ v_arr,
                     const float *__restrict__ total_weight, const float *__restrict__ grad, OptimParams p,
                     float *__restrict__ lr_step, float *__restrict__ param, const float *__restrict__ mask_lr,
                     const float *__restrict__ point_lr) {
-  optim_scalar_body<LAPROP, BIAS, VEC4>((int64_t)blockIdx.x * blockDim.x + threadIdx.x, indexes, weight, grad_scale, m_arr,
-                                        v_arr, total_weight, grad, p, lr_step, param, mask_lr, point_lr);
-}
-
-// vector kinds: one running second moment per row (squared gradient norm); one thread per visible row
-template <bool LAPROP, bool BIAS>
-__device__ __forceinline__ void optim_vector_body(int64_t i, const int64_t *__restrict__ indexes,
-                                                  const float *__restrict__ weight, const float *__restrict__ grad_scale,
-                                                  float *__restrict__ m_arr, float *__restrict__ v_arr,
-                                                  const float *__restrict__ total_weight, const float *__restrict__ grad,
-                                                  const OptimParams &p, float *__restrict__ lr_step,
-                                                  float *__restrict__ param, const float *__restrict__ mask_lr,
-                                                  const float *__restrict__ point_lr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.m_rows) return;
   const int64_t idx = indexes[i];
   const float w = weight[i], tw = total_weight[idx];
@@ -167,54 +156,6 @@ __device__ __forceinline__ void optim_vector_body(int64_t i, const int64_t *__re
     if (param != nullptr) param[e] -= finish_step(step, w, j, idx, p, mask_lr, point_lr) * sat;
   }
   v_arr[idx] = v;
-}
-
-template <bool LAPROP, bool BIAS>
-__global__ void __launch_bounds__(256)
-optim_vector_kernel(const int64_t *__restrict__ indexes, const float *__restrict__ weight,
-                    const float *__restrict__ grad_scale, float *__restrict__ m_arr, float *__restrict__ v_arr,
-                    const float *__restrict__ total_weight, const float *__restrict__ grad, OptimParams p,
-                    float *__restrict__ lr_step, float *__restrict__ param, const float *__restrict__ mask_lr,
-                    const float *__restrict__ point_lr) {
-  optim_vector_body<LAPROP, BIAS>((int64_t)blockIdx.x * blockDim.x + threadIdx.x, indexes, weight, grad_scale, m_arr, v_arr,
-                                  total_weight, grad, p, lr_step, param, mask_lr, point_lr);
-}
-
-// every parameter group of an optimiser step in ONE launch: the block index selects the group (a handful of
-// groups: linear search over their block offsets), then the same per-thread bodies as the single-group kernels.
-struct OptimGroupDev {
-  float *m_state, *v_state, *param;
-  const float *grad, *mask_lr, *point_lr;
-  OptimParams p;
-  int vector, vec4;
-  unsigned block_begin;
-};
-constexpr int kMaxOptimGroups = 8;
-struct OptimMultiArgs {
-  OptimGroupDev g[kMaxOptimGroups];
-  int n;
-};
-
-template <bool LAPROP, bool BIAS>
-__global__ void __launch_bounds__(256, 5)   // 48 registers like the single-group kernels (62 without the bound: 4 blocks / SM)
-optim_multi_kernel(const int64_t *__restrict__ indexes, const float *__restrict__ weight,
-                   const float *__restrict__ grad_scale, const float *__restrict__ total_weight,
-                   const __grid_constant__ OptimMultiArgs a) {
-  int gi = 0;
-#pragma unroll
-  for (int k = 1; k < kMaxOptimGroups; ++k)
-    if (k < a.n && blockIdx.x >= a.g[k].block_begin) gi = k;
-  const OptimGroupDev &g = a.g[gi];
-  const int64_t t = (int64_t)(blockIdx.x - g.block_begin) * blockDim.x + threadIdx.x;
-  if (g.vector)
-    optim_vector_body<LAPROP, BIAS>(t, indexes, weight, grad_scale, g.m_state, g.v_state, total_weight, g.grad, g.p, nullptr,
-                                    g.param, g.mask_lr, g.point_lr);
-  else if (g.vec4)
-    optim_scalar_body<LAPROP, BIAS, true>(t, indexes, weight, grad_scale, g.m_state, g.v_state, total_weight, g.grad, g.p,
-                                          nullptr, g.param, g.mask_lr, g.point_lr);
-  else
-    optim_scalar_body<LAPROP, BIAS, false>(t, indexes, weight, grad_scale, g.m_state, g.v_state, total_weight, g.grad, g.p,
-                                           nullptr, g.param, g.mask_lr, g.point_lr);
 }
 
 // running visibility (visibility_aware.py:37-48) and the per-point step counter (:90-91)
@@ -272,45 +213,6 @@ extern "C" int gs_optim_step_f32(int32_t algorithm, int32_t vector, int32_t bias
   }
 #undef GS_OPT_SCALAR
 #undef GS_OPT
-  GS_LAUNCH_CHECK();
-  return GS_OK;
-}
-
-extern "C" int gs_optim_step_groups_f32(int32_t algorithm, int32_t bias_correction, const gs_optim_group *groups,
-                                        int32_t num_groups, const int64_t *indexes, const float *weight,
-                                        const float *grad_scale, double grad_smooth, int64_t m_rows,
-                                        const float *total_weight, void *stream_) {
-  using namespace gs;
-  GS_CHECK_ARG(algorithm == GS_OPTIM_ADAM || algorithm == GS_OPTIM_LAPROP, "optim_step_groups: unknown algorithm %d", algorithm);
-  GS_CHECK_ARG(groups != nullptr && num_groups >= 1 && num_groups <= kMaxOptimGroups, "optim_step_groups: 1..%d groups, got %d", kMaxOptimGroups, num_groups);
-  GS_CHECK_ARG(m_rows >= 0, "optim_step_groups: bad row count");
-  if (m_rows == 0) return GS_OK;
-  auto aligned16 = [](const void *q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  OptimMultiArgs a;
-  a.n = num_groups;
-  unsigned blocks = 0;
-  for (int k = 0; k < num_groups; ++k) {
-    const gs_optim_group &src = groups[k];
-    GS_CHECK_ARG(src.d >= 1 && src.param != nullptr && src.grad != nullptr && src.m_state != nullptr && src.v_state != nullptr,
-                 "optim_step_groups: group %d is incomplete", k);
-    OptimGroupDev &g = a.g[k];
-    g.m_state = src.m_state; g.v_state = src.v_state; g.param = src.param; g.grad = src.grad;
-    g.mask_lr = src.mask_lr; g.point_lr = src.point_lr;
-    g.p.lr = (float)src.lr; g.p.beta1 = (float)src.beta1; g.p.beta2 = (float)src.beta2; g.p.eps = (float)src.eps;
-    g.p.clip = (float)src.clip; g.p.grad_smooth = (float)grad_smooth; g.p.d = src.d; g.p.m_rows = m_rows;
-    g.vector = src.vector != 0;
-    g.vec4 = !g.vector && src.d % 4 == 0 && aligned16(src.m_state) && aligned16(src.v_state) && aligned16(src.grad) &&
-             aligned16(src.param);
-    g.block_begin = blocks;
-    const int64_t threads = g.vector ? m_rows : m_rows * ((src.d + 3) / 4);
-    blocks += (unsigned)ceil_div(threads, 256);
-  }
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const bool laprop = algorithm == GS_OPTIM_LAPROP, bias = bias_correction != 0;
-#define GS_OPT_MULTI(L_, B_) optim_multi_kernel<L_, B_><<<blocks, 256, 0, stream>>>(indexes, weight, grad_scale, total_weight, a)
-  if (laprop) { if (bias) GS_OPT_MULTI(true, true); else GS_OPT_MULTI(true, false); }
-  else        { if (bias) GS_OPT_MULTI(false, true); else GS_OPT_MULTI(false, false); }
-#undef GS_OPT_MULTI
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

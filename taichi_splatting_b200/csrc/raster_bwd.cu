@@ -24,7 +24,7 @@ int raster_digest_f32(const float *points, const float *features, const float *d
                       double alpha_threshold, void *digest, cudaStream_t stream);   // raster_digest.cu
 int raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t k,
                     int32_t width, int32_t height, int32_t F, void *records, void *flush, cudaStream_t stream,
-                    const uint32_t *sorted_tiles = nullptr);   // raster_pack.cu
+                    const uint32_t *sorted_tiles = nullptr, int32_t *ranges_out = nullptr);   // raster_pack.cu
 
 constexpr int kTileB = 16;
 

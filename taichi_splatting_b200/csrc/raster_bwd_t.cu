@@ -86,7 +86,6 @@ struct Smem {
   // "next" entries of a chunk (k = h0 + 1 .. h0 + 8) are two aligned 16-byte loads
   alignas(16) unsigned list[kWarps][kBatch + kChunk + 4];
   alignas(8) uint64_t full[2];           // mbarriers: "buffer b holds its batch"
-  int warp_done[kWarps];
 };
 
 template <int F, bool GP, bool GF, bool HEUR, int RECW>
@@ -173,18 +172,18 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
     if (nbatches > 0) issue(0);
     if (nbatches > 1) issue(1);
   }
-  if (lane == 0) sm.warp_done[warp] = 0;
+  int warp_saturated = 0;   // every pixel of this warp's block is saturated (uniform over the warp)
 #pragma unroll
   for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
 
   for (int b = 0; b < nbatches; ++b) {
     const int buf = b & 1;
     const int base = start + b * kBatch, nb = min(kBatch, end - base);
-    __syncthreads();   // previous flush finished: its buffer is free, accumulators are zero again, warp_done visible
+    // previous flush finished: its buffer is free, accumulators are zero again.  The barrier also decides, identically
+    // for every thread, whether the whole tile is saturated (a shared flag per warp, re-read after the barrier while
+    // fast warps already set theirs again, let warps disagree: compute-sanitizer racecheck).
     {
-      int all_done = 1;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) all_done &= sm.warp_done[w];
+      const int all_done = __syncthreads_and(warp_saturated);
       // refill the buffer the previous batch just released (the flush still read its records, so not earlier); the
       // copy of batch b + 1 then runs beside the sweep of batch b.  Every issued copy is waited for before the CTA
       // exits: when every pixel is saturated nothing new is issued and batch b is the last one in flight.
@@ -370,7 +369,7 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
       __syncwarp();
       if (__all_sync(full, trans[0] <= t_min && trans[1] <= t_min)) break;
     }
-    if (__all_sync(full, trans[0] <= t_min && trans[1] <= t_min) && lane == 0) sm.warp_done[warp] = 1;
+    warp_saturated = __all_sync(full, trans[0] <= t_min && trans[1] <= t_min);
 
     // ---- flush: one thread per splat of the batch ----
     __syncthreads();

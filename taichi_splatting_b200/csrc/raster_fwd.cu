@@ -63,7 +63,6 @@ struct FwdSmem {
   float vis[kBatch + 1];
   unsigned char mask[kBatch];
   alignas(16) unsigned list[kWarps][kBatch + kUnroll];   // byte offsets (16 j) of the records a warp must visit
-  int warp_done[kWarps];
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -162,7 +161,7 @@ raster_fwd_kernel(const float4 *__restrict__ digest, const int32_t *__restrict__
   const unsigned char *rec_b = reinterpret_cast<const unsigned char *>(sm.b);
   const unsigned char *rec_f = reinterpret_cast<const unsigned char *>(sm.f);
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
-  if (lane == 0) sm.warp_done[warp] = 0;
+  int warp_is_done = 0;   // nothing can change any more in this warp's block (uniform over the warp)
   if (tid == 0) {  // null record: alpha = 0 never passes the threshold
     sm.a[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
     sm.b[kBatch] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -171,13 +170,9 @@ raster_fwd_kernel(const float4 *__restrict__ digest, const int32_t *__restrict__
 
   for (int base = start; base < end; base += kBatch) {
     const int nb = min(kBatch, end - base);
-    __syncthreads();  // previous batch fully consumed (and warp_done visible)
-    {
-      int all_done = 1;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) all_done &= sm.warp_done[w];
-      if (all_done) break;
-    }
+    // previous batch fully consumed; the barrier also decides, identically for every thread, whether the tile is done
+    // (a shared flag per warp re-read after the barrier raced with fast warps setting theirs again: racecheck)
+    if (__syncthreads_and(warp_is_done)) break;
     for (int j = tid; j < nb; j += kThreads) {
       int id = overlap_to_point[base + j];
       float4 A, B, fv;
@@ -279,7 +274,7 @@ raster_fwd_kernel(const float4 *__restrict__ digest, const int32_t *__restrict__
     }
     {
       const bool now_done = BLEND ? (trans[0] <= eps && trans[1] <= eps) : (done[0] && done[1]);
-      if (__all_sync(full, now_done) && lane == 0) sm.warp_done[warp] = 1;
+      warp_is_done = __all_sync(full, now_done);
     }
 
     if (VIS) {
@@ -328,7 +323,7 @@ int raster_digest_f32(const float *points, const float *features, const float *d
                       double alpha_threshold, void *digest, cudaStream_t stream);   // raster_digest.cu
 int raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t k,
                     int32_t width, int32_t height, int32_t F, void *records, void *flush, cudaStream_t stream,
-                    const uint32_t *sorted_tiles = nullptr);   // raster_pack.cu
+                    const uint32_t *sorted_tiles = nullptr, int32_t *ranges_out = nullptr);   // raster_pack.cu
 
 // GS_RASTER_STAGING=gather keeps the in-kernel digest gather of this file for alpha blending too (A/B switch);
 // default: packed records + bulk-copy staging (raster_pack.cu, raster_fwd_bulk.cu).

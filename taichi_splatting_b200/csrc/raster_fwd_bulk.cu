@@ -58,7 +58,6 @@ struct Smem {
   float vis[2][kBatch];                 // per-splat visibility of the batch (double-buffered like the records)
   alignas(16) unsigned list[kWarps][kBatch + kUnroll];   // byte offsets of the records a warp must visit
   alignas(8) uint64_t full[2];          // mbarriers: "buffer b holds its batch"
-  int warp_done[kWarps];
 };
 
 // N values per lane -> every lane of group g = lane / (32 / N) ends with the warp-wide sum of value g in v[0]
@@ -129,7 +128,6 @@ raster_fwd_bulk_kernel(const float4 *__restrict__ records, const int32_t *__rest
     if (nbatches > 0) issue(0);
     if (nbatches > 1) issue(1);
   }
-  if (lane == 0) sm.warp_done[warp] = 0;
   if (VIS) {
 #pragma unroll
     for (int j = tid; j < kBatch; j += kThreads) { sm.vis[0][j] = 0.f; sm.vis[1][j] = 0.f; }
@@ -224,12 +222,9 @@ raster_fwd_bulk_kernel(const float4 *__restrict__ records, const int32_t *__rest
       }
       if (__all_sync(full, trans[0] <= eps && trans[1] <= eps)) break;
     }
-    if (__all_sync(full, trans[0] <= eps && trans[1] <= eps) && lane == 0) sm.warp_done[warp] = 1;
-
-    __syncthreads();   // every warp is through with this buffer (records and visibility sums)
-    int all_done = 1;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) all_done &= sm.warp_done[w];
+    // every warp is through with this buffer (records and visibility sums); the barrier also decides, identically for
+    // every thread, whether all pixels of the tile are done
+    const int all_done = __syncthreads_and(__all_sync(full, trans[0] <= eps && trans[1] <= eps));
     if (tid == 0 && b + 2 < nbatches && !all_done) issue(b + 2);   // refill the buffer just released
     if (VIS) {
 #pragma unroll

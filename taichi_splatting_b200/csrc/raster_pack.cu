@@ -100,17 +100,26 @@ template <int RECW, bool FLUSH>
 __global__ void __launch_bounds__(kPackThreads)
 raster_pack_flat_kernel(const float4 *__restrict__ digest, const uint32_t *__restrict__ sorted_tiles,
                         const int32_t *__restrict__ overlap_to_point, int64_t k_total, int tiles_wide,
-                        float4 *__restrict__ records, float4 *__restrict__ flush) {
+                        float4 *__restrict__ records, float4 *__restrict__ flush, int32_t *__restrict__ ranges_out) {
   const int64_t k = (int64_t)blockIdx.x * kPackThreads + threadIdx.x;
   if (k >= k_total) return;
   const int tile = (int)sorted_tiles[k];
+  if (ranges_out != nullptr) {
+    // the tile ranges (find_ranges_kernel, mapper/tile_mapper.py:92-112) fall out of the same pass over the sorted
+    // tile ids: a range ends where the next overlap belongs to another tile (ranges_out is zero-filled beforehand)
+    const int next = k + 1 < k_total ? (int)sorted_tiles[k + 1] : -1;
+    if (next != tile) {
+      ranges_out[2 * tile + 1] = (int32_t)(k + 1);
+      if (next >= 0) ranges_out[2 * next] = (int32_t)(k + 1);
+    }
+  }
   const float tile_cx = (float)((tile % tiles_wide) * 16) + 8.0f, tile_cy = (float)((tile / tiles_wide) * 16) + 8.0f;
   pack_one<RECW, FLUSH>(digest, overlap_to_point, k, tile_cx, tile_cy, records, flush);
 }
 
 int raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_t *overlap_to_point, int64_t k,
                     int32_t width, int32_t height, int32_t F, void *records, void *flush, cudaStream_t stream,
-                    const uint32_t *sorted_tiles) {
+                    const uint32_t *sorted_tiles, int32_t *ranges_out) {
   GS_CHECK_ARG(F >= 1 && F <= 4, "raster_pack: 1..4 features, got %d", F);
   GS_CHECK_ARG(width > 0 && height > 0, "raster_pack: bad image size %dx%d", width, height);
   if (k == 0) return GS_OK;
@@ -126,7 +135,7 @@ int raster_pack_f32(const void *digest, const int32_t *tile_ranges, const int32_
   do {                                                                                                                \
     if (sorted_tiles != nullptr)                                                                                      \
       raster_pack_flat_kernel<RECW_, FLUSH_><<<flat_grid, kPackThreads, 0, stream>>>(d, sorted_tiles, overlap_to_point, k, \
-                                                                                    tiles_wide, r, f);                \
+                                                                                    tiles_wide, r, f, ranges_out);    \
     else                                                                                                              \
       raster_pack_kernel<RECW_, FLUSH_><<<tiles, kPackThreads, 0, stream>>>(d, tile_ranges, overlap_to_point, tiles_wide, r, f); \
   } while (0)
@@ -150,13 +159,19 @@ extern "C" int gs_raster_pack_f32(const void *digest, const int32_t *tile_ranges
                                   int64_t k, int32_t width, int32_t height, int32_t num_features, void *records,
                                   void *flush_records, void *stream) {
   return gs::raster_pack_f32(digest, tile_ranges, overlap_to_point, k, width, height, num_features, records,
-                             flush_records, (cudaStream_t)stream, nullptr);
+                             flush_records, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 extern "C" int gs_raster_pack_sorted_f32(const void *digest, const uint32_t *sorted_tiles,
                                          const int32_t *overlap_to_point, int64_t k, int32_t width, int32_t height,
-                                         int32_t num_features, void *records, void *flush_records, void *stream) {
+                                         int32_t num_features, void *records, void *flush_records,
+                                         int32_t *tile_ranges_out, void *stream_) {
   GS_CHECK_ARG(sorted_tiles != nullptr || k == 0, "raster_pack_sorted: sorted_tiles is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (tile_ranges_out != nullptr) {   // untouched tiles stay (0, 0) (tile_mapper.py:186-188)
+    const int64_t tiles = (int64_t)((width + 15) / 16) * ((height + 15) / 16);
+    GS_CUDA(cudaMemsetAsync(tile_ranges_out, 0, sizeof(int32_t) * 2 * tiles, stream));
+  }
   return gs::raster_pack_f32(digest, nullptr, overlap_to_point, k, width, height, num_features, records, flush_records,
-                             (cudaStream_t)stream, sorted_tiles);
+                             stream, sorted_tiles, tile_ranges_out);
 }

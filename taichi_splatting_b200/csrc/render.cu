@@ -218,6 +218,7 @@ static int gs::stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64
   const int64_t num_tiles = (int64_t)(w_pad / ts) * (h_pad / ts);
   const int32_t *sorted_o2p = o2p + k_stride;
   const bool binned = a->ordering == GS_ORDERING_BINNED;
+  bool two_level_sorted = false;
   if (binned && max_per_tile <= gs_tile_bin_max_per_tile()) {
     // binned ordering, second half: slot emission, then one shared-memory sort per tile.  `tiles` (2 k_stride u32)
     // holds the k 64-bit keys.
@@ -245,17 +246,21 @@ static int gs::stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64
       GS_TRY(gs_sort_pairs(tiles, o2p, tiles + k_stride, o2p + k_stride, k, 4, 0, tile_bits(num_tiles), ws_sort,
                            ws_sort_bytes, stream));
     }
-    GS_TRY(gs_tile_ranges_from_tiles(tiles + k_stride, k, a->tile_ranges, num_tiles, stream));
+    // the tile ranges come out of the raster-pack pass below (same walk over the sorted tile ids); without packed
+    // record buffers (or nothing to rasterise) they get their own kernel
+    two_level_sorted = true;
+    if (a->records == nullptr || k == 0)
+      GS_TRY(gs_tile_ranges_from_tiles(tiles + k_stride, k, a->tile_ranges, num_tiles, stream));
   }
   GS_CUDA(cudaStreamWaitEvent(stream, aux->side_done, 0));
   if (a->records != nullptr || k == 0) {
     // per-overlap records in sorted order (kept for the backward), then the bulk-copy staged forward kernel
-    if (binned && max_per_tile <= gs_tile_bin_max_per_tile())   // binned ordering: no sorted tile-id array
+    if (!two_level_sorted)   // binned ordering: no sorted tile-id array, ranges already known
       GS_TRY(gs_raster_pack_f32(a->digest, a->tile_ranges, sorted_o2p, k, a->width, a->height, a->channels, a->records,
                                 a->flush_records, stream));
-    else
+    else if (k > 0)
       GS_TRY(gs_raster_pack_sorted_f32(a->digest, tiles + k_stride, sorted_o2p, k, a->width, a->height, a->channels,
-                                       a->records, a->flush_records, stream));
+                                       a->records, a->flush_records, a->tile_ranges, stream));
     if (a->ev_raster_start != nullptr) GS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_raster_start, stream));
     GS_TRY(gs_raster_fwd_packed_f32(a->records, a->tile_ranges, sorted_o2p, v, k, a->width, a->height, a->channels,
                                     &a->config, a->median_threshold, a->image, a->image_alpha, a->visibility,

@@ -133,43 +133,6 @@ def apply_step(group: Group, weight, indexes, total_weight, algorithm: int, basi
           None, group.param)
 
 
-def apply_steps(groups, weight, indexes, total_weight, algorithm: int, basis=None, grad_scale=None,
-                grad_smooth: float = 0.0):
-  """One optimiser step over all parameter groups.  Scalar / vector groups sharing one bias-correction setting go to
-  the device in ONE launch (gs_optim_step_groups_f32); `local_vector` groups (basis change in torch around the
-  kernel) and any leftovers take the per-group path."""
-  fused, rest = [], []
-  for g in groups:
-    if g.grad is None:
-      continue
-    ok = (g.type in ("vector", "scalar") and g.param.dtype == torch.float32 and g.grad.dtype == torch.float32
-          and g.param.is_contiguous() and g.grad.is_contiguous())
-    (fused if ok and (not fused or g.bias_correction == fused[0].bias_correction) and len(fused) < 8 else rest).append(g)
-  if len(fused) >= 2:
-    _lib.require_cuda(indexes=indexes, weight=weight)
-    assert indexes.dtype == torch.int64, f"indexes must be int64, got {indexes.dtype}"
-    ptr = _lib.ptr
-    keep = []   # contiguous fp32 copies of mask_lr / point_lr must outlive the launch
-    arr = (_lib.OptimGroupC * len(fused))()
-    for k, g in enumerate(fused):
-      vector = g.type == "vector"
-      first, second = _moment_state(g.state, g.param, vector)
-      mask_lr = g.mask_lr.to(torch.float32).contiguous().view(-1) if g.mask_lr is not None else None
-      point_lr = g.point_lr.to(torch.float32).contiguous().view(-1) if g.point_lr is not None else None
-      keep += [mask_lr, point_lr]
-      arr[k] = _lib.OptimGroupC(ptr(first), ptr(second), ptr(g.param), ptr(g.grad), ptr(mask_lr), ptr(point_lr),
-                                float(g.lr), float(g.betas[0]), float(g.betas[1]), float(g.eps),
-                                float(g.clip) if g.clip is not None else 0.0, g.param.shape[1], int(vector))
-    _lib.call("gs_optim_step_groups_f32", algorithm, int(fused[0].bias_correction), arr, len(fused),
-              ptr(indexes.contiguous()), ptr(weight.contiguous()),
-              ptr(grad_scale.contiguous()) if grad_scale is not None else None, float(grad_smooth), indexes.shape[0],
-              ptr(total_weight), _lib.stream_ptr(fused[0].param.device))
-  else:
-    rest = fused + rest
-  for g in rest:
-    apply_step(g, weight, indexes, total_weight, algorithm, basis, grad_scale, grad_smooth)
-
-
 def resolve_algorithm(kernels) -> int:
   """ADAM / LAPROP; a reference-style kernel module (fractional_adam / fractional_laprop) is accepted too."""
   if isinstance(kernels, types.ModuleType):
@@ -203,8 +166,10 @@ class FractionalOpt(torch.optim.Optimizer):
     total_weight = get_total_weight(groups[0].state, n, device=weight.device)
     total_weight[indexes] += weight
     for group in groups:
-      assert group.grad is None or group.num_points == n, f"param shape {group.num_points} != {n}"
-    apply_steps(groups, weight, indexes, total_weight, self.kernels, basis)
+      if group.grad is None:
+        continue
+      assert group.num_points == n, f"param shape {group.num_points} != {n}"
+      apply_step(group, weight, indexes, total_weight, self.kernels, basis)
 
 
 class FractionalAdam(FractionalOpt):

@@ -51,9 +51,10 @@ class VisibilityOptimizer(torch.optim.Optimizer):
     vis = visibility.to(torch.float32).contiguous()
     weight = update_visibility(get_running_vis(shared, n, device), vis, indexes, total_weight, self.vis_beta)
     for group in groups:
-      assert group.grad is None or group.num_points == n, f"param shape {group.num_points} != {n}"
-    fr.apply_steps(groups, weight, indexes, total_weight, self.kernels, basis, grad_scale=vis,
-                   grad_smooth=self.vis_smooth)
+      if group.grad is not None:
+        assert group.num_points == n, f"param shape {group.num_points} != {n}"
+        fr.apply_step(group, weight, indexes, total_weight, self.kernels, basis, grad_scale=vis,
+                      grad_smooth=self.vis_smooth)
 
 
 def _visibility_optimiser(name: str, algorithm: int):

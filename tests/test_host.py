@@ -110,7 +110,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
   import subprocess
   from taichi_splatting_b200 import _lib
   structs = {"gs_raster_config": _lib.RasterConfigC, "gs_render_args": _lib.RenderArgsC,
-             "gs_render_bwd_args": _lib.RenderBwdArgsC, "gs_optim_group": _lib.OptimGroupC}
+             "gs_render_bwd_args": _lib.RenderBwdArgsC}
   lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gsplat_b200.h"', 'int main(void) {']
   for cname, cls in structs.items():
     lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
