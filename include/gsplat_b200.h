@@ -68,6 +68,23 @@ int gs_project_cull_f32(const float *position, const float *log_scaling, const f
                         int64_t n, int32_t width, int32_t height, double near_plane, double far_plane,
                         double blur_cov, double clamp_margin, double alpha_threshold,
                         void *workspace, size_t workspace_bytes, int32_t *num_visible_host, void *stream);
+/* Single-pass alternative to gs_project_cull_* + gs_project_write_*: project, cull and compact IN ORDER in one kernel
+ * (the projection is the load of a cub::DeviceSelect stream compaction), each Gaussian projected once.  Outputs need
+ * capacity n rows (V rows are written; V arrives in *num_visible_host after the stream is synchronised); ndc_depth may
+ * be NULL.  Same results as the two-kernel form.  Workspace: gs_project_workspace_bytes(n) is enough. */
+int gs_project_compact_workspace_bytes(int64_t n, int32_t fp64, size_t *bytes);
+int gs_project_compact_f32(const float *position, const float *log_scaling, const float *rotation,
+                           const float *alpha_logit, const float *T_camera_world, const float *projection, int64_t n,
+                           int32_t width, int32_t height, double near_plane, double far_plane, double blur_cov,
+                           double clamp_margin, double alpha_threshold, void *workspace, size_t workspace_bytes,
+                           float *points, float *depth, int64_t *indexes, float *ndc_depth, int32_t *num_visible_host,
+                           void *stream);
+int gs_project_compact_f64(const double *position, const double *log_scaling, const double *rotation,
+                           const double *alpha_logit, const double *T_camera_world, const double *projection, int64_t n,
+                           int32_t width, int32_t height, double near_plane, double far_plane, double blur_cov,
+                           double clamp_margin, double alpha_threshold, void *workspace, size_t workspace_bytes,
+                           double *points, double *depth, int64_t *indexes, double *ndc_depth,
+                           int32_t *num_visible_host, void *stream);
 int gs_project_write_f32(const float *position, const float *log_scaling, const float *rotation,
                          const float *alpha_logit, const float *T_camera_world, const float *projection,
                          int64_t n, int32_t width, int32_t height, double near_plane, double far_plane,

@@ -75,6 +75,7 @@ class RenderBwdArgsC(ctypes.Structure):
 
 
 _PROJECT_CULL = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, D, P, SZ, P, P]
+_PROJECT_COMPACT = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, D, P, SZ, P, P, P, P, P, P]
 _PROJECT_WRITE = [P, P, P, P, P, P, I64, I32, I32, D, D, D, D, P, P, P, P, P, P]
 _PROJECT_BWD = [P, P, P, P, P, P, P, I64, I32, I32, D, D, P, P, P, P, P, P, P, P, P]
 _SH_FWD = [P, P, P, P, I64, I32, I32, P, P]
@@ -87,6 +88,8 @@ SIGNATURES = {
     "gs_last_error_string": ([], ctypes.c_char_p),
     "gs_project_workspace_bytes": ([I64, POINTER(SZ)], c_int32),
     "gs_project_cull_f32": (_PROJECT_CULL, c_int32), "gs_project_cull_f64": (_PROJECT_CULL, c_int32),
+    "gs_project_compact_workspace_bytes": ([I64, I32, POINTER(SZ)], c_int32),
+    "gs_project_compact_f32": (_PROJECT_COMPACT, c_int32), "gs_project_compact_f64": (_PROJECT_COMPACT, c_int32),
     "gs_project_write_f32": (_PROJECT_WRITE, c_int32), "gs_project_write_f64": (_PROJECT_WRITE, c_int32),
     "gs_project_bwd_f32": (_PROJECT_BWD, c_int32), "gs_project_bwd_f64": (_PROJECT_BWD, c_int32),
     "gs_camera_position_f32": ([P, P, P], c_int32), "gs_camera_position_f64": ([P, P, P], c_int32),
@@ -170,7 +173,7 @@ def check(code: int, what: str) -> None:
 
 # Hand-written kernels each entry point launches (CUB scan / onesweep launches are not counted).
 OWN_KERNELS = {
-    "gs_project_cull_f32": 1, "gs_project_cull_f64": 1, "gs_project_write_f32": 1, "gs_project_write_f64": 1,
+    "gs_project_cull_f32": 1, "gs_project_cull_f64": 1, "gs_project_compact_f32": 1, "gs_project_compact_f64": 1, "gs_project_write_f32": 1, "gs_project_write_f64": 1,
     "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_camera_position_f32": 1, "gs_camera_position_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
     "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_sh_bwd_views_f32": 1, "gs_sh_pack_factors_f32": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
     "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1, "gs_tile_count_ordered_hits": 1, "gs_tile_emit_hits": 1,

@@ -6,6 +6,11 @@
 // How it is computed is this library's own: one thread per Gaussian, camera held in registers,
 // in-view flags -> single scan -> order-preserving compaction, camera gradients block-reduced.
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <iterator>
 
 #include "common.cuh"
 
@@ -171,6 +176,141 @@ project_write_kernel(const real *__restrict__ position, const real *__restrict__
   depth[k] = z;
   indexes[k] = i;
   if (ndc) ndc[k] = real(1) - (real(1) / z - inv_far) / ndc_denom;  // torch_lib/projection.py:123
+}
+
+// ---- single-pass project + cull + ORDERED compaction ------------------------------------------------------------
+// project_cull / project_write above project every Gaussian twice (flags -> scan -> recompute and write), because the
+// output position of a visible Gaussian is only known after the scan.  Here the projection is the *load* of a stream
+// compaction: cub::DeviceSelect::If pulls items through a transform iterator that projects Gaussian i on access, keeps
+// the ones in view (stable: indexes stay ascending, as torch.nonzero gives them in the reference, projection.py:147) with
+// its single-pass decoupled look-back scan, and scatters them through an output iterator that splits the item into
+// the reference's separate arrays.  One projection per Gaussian, one kernel instead of three.
+template <typename real>
+struct ProjItem {
+  real pts[7];
+  real depth, ndc;
+  int32_t index, visible;
+};
+
+template <typename real>
+struct ProjectOp {
+  const real *position, *log_scaling, *rotation, *alpha_logit, *T, *proj;   // camera stays in device memory (no host read)
+  real width, height, near_plane, far_plane, blur, margin, alpha_threshold, inv_far, ndc_denom;
+  __device__ __forceinline__ ProjItem<real> operator()(int i) const {
+    const Camera<real> cam = load_camera(T, proj);
+    Projected<real> o;
+    project_one(cam, position + 3 * (int64_t)i, log_scaling + 3 * (int64_t)i, rotation + 4 * (int64_t)i, alpha_logit[i],
+                width, height, blur, margin, o);
+    ProjItem<real> it;
+    it.pts[0] = o.uv[0]; it.pts[1] = o.uv[1]; it.pts[2] = o.v1[0]; it.pts[3] = o.v1[1];
+    it.pts[4] = o.sigma[0]; it.pts[5] = o.sigma[1]; it.pts[6] = o.alpha;
+    const real z = o.cam_xyz[2];
+    it.depth = z;
+    it.ndc = real(1) - (real(1) / z - inv_far) / ndc_denom;   // torch_lib/projection.py:123
+    it.index = i;
+    it.visible = in_view(o, width, height, near_plane, far_plane, alpha_threshold) ? 1 : 0;
+    return it;
+  }
+};
+
+template <typename real>
+struct ProjVisible {
+  __device__ __forceinline__ bool operator()(const ProjItem<real> &it) const { return it.visible != 0; }
+};
+
+// output iterator: `out[k] = item` writes row k of points / depth / indexes / ndc
+template <typename real>
+struct ProjSink {
+  real *points, *depth, *ndc;
+  int64_t *indexes;
+  int64_t k;
+  __device__ __forceinline__ const ProjSink &operator=(const ProjItem<real> &it) const {
+    real *row = points + 7 * k;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) row[c] = it.pts[c];
+    depth[k] = it.depth;
+    indexes[k] = it.index;
+    if (ndc != nullptr) ndc[k] = it.ndc;
+    return *this;
+  }
+};
+
+template <typename real>
+struct ProjOutIt {
+  using iterator_category = std::random_access_iterator_tag;
+  using value_type = ProjItem<real>;
+  using difference_type = int64_t;
+  using pointer = void;
+  using reference = ProjSink<real>;
+  real *points, *depth, *ndc;
+  int64_t *indexes;
+  int64_t base;
+  __host__ __device__ __forceinline__ ProjSink<real> operator[](int64_t k) const {
+    return ProjSink<real>{points, depth, ndc, indexes, base + k};
+  }
+  __host__ __device__ __forceinline__ ProjSink<real> operator*() const { return (*this)[0]; }
+  __host__ __device__ __forceinline__ ProjOutIt operator+(int64_t d) const {
+    ProjOutIt r = *this;
+    r.base += d;
+    return r;
+  }
+};
+
+template <typename real>
+static ProjectOp<real> make_project_op(const real *position, const real *log_scaling, const real *rotation,
+                                       const real *alpha_logit, const real *T, const real *proj, int32_t width,
+                                       int32_t height, double near_plane, double far_plane, double blur_cov,
+                                       double clamp_margin, double alpha_threshold) {
+  ProjectOp<real> op;
+  op.position = position; op.log_scaling = log_scaling; op.rotation = rotation; op.alpha_logit = alpha_logit;
+  op.T = T; op.proj = proj;
+  op.width = (real)width; op.height = (real)height; op.near_plane = (real)near_plane; op.far_plane = (real)far_plane;
+  op.blur = (real)blur_cov; op.margin = (real)clamp_margin; op.alpha_threshold = (real)alpha_threshold;
+  // eager-torch semantics of ndc_depth: python-float scalars are rounded to the tensor dtype
+  op.inv_far = (real)(1.0 / far_plane); op.ndc_denom = (real)(1.0 / near_plane - 1.0 / far_plane);
+  return op;
+}
+
+template <typename real>
+using ProjInIt = cub::TransformInputIterator<ProjItem<real>, ProjectOp<real>, cub::CountingInputIterator<int>>;
+
+template <typename real>
+size_t project_compact_temp_bytes(int64_t n) {
+  size_t temp = 0;
+  if (n > 0) {
+    ProjInIt<real> in(cub::CountingInputIterator<int>(0), ProjectOp<real>{});
+    ProjOutIt<real> out{nullptr, nullptr, nullptr, nullptr, 0};
+    cub::DeviceSelect::If(nullptr, temp, in, out, (int32_t *)nullptr, (int)n, ProjVisible<real>());
+  }
+  return temp;
+}
+
+template <typename real>
+int project_compact(const real *position, const real *log_scaling, const real *rotation, const real *alpha_logit,
+                    const real *T, const real *proj, int64_t n, int32_t width, int32_t height, double near_plane,
+                    double far_plane, double blur_cov, double clamp_margin, double alpha_threshold, void *workspace,
+                    size_t workspace_bytes, real *points, real *depth, int64_t *indexes, real *ndc,
+                    int32_t *num_visible_host, cudaStream_t stream) {
+  GS_CHECK_ARG(n >= 0 && n < (int64_t(1) << 31), "project: n=%lld out of range", (long long)n);
+  GS_CHECK_ARG(num_visible_host != nullptr, "project: num_visible_host is NULL");
+  if (n == 0) {
+    *num_visible_host = 0;
+    return GS_OK;
+  }
+  size_t temp_bytes = project_compact_temp_bytes<real>(n);
+  if (workspace == nullptr || workspace_bytes < 256 + temp_bytes) {
+    set_error("project_compact: workspace too small (%zu < %zu)", workspace_bytes, 256 + temp_bytes);
+    return GS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  int32_t *num_dev = (int32_t *)workspace;                 // first 256 bytes: the selected count
+  void *temp = (unsigned char *)workspace + 256;
+  ProjInIt<real> in(cub::CountingInputIterator<int>(0),
+                    make_project_op<real>(position, log_scaling, rotation, alpha_logit, T, proj, width, height, near_plane,
+                                          far_plane, blur_cov, clamp_margin, alpha_threshold));
+  ProjOutIt<real> out{points, depth, ndc, indexes, 0};
+  GS_CUDA(cub::DeviceSelect::If(temp, temp_bytes, in, out, num_dev, (int)n, ProjVisible<real>(), stream));
+  GS_CUDA(cudaMemcpyAsync(num_visible_host, num_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  return GS_OK;
 }
 
 template <typename real, int N>
@@ -413,6 +553,17 @@ extern "C" int gs_project_workspace_bytes(int64_t n, size_t *bytes) {
   size_t temp = 0;
   if (n > 0) cub::DeviceScan::InclusiveSum(nullptr, temp, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n);
   *bytes = 2 * gs::align_up((size_t)(n > 0 ? n : 0), 64) * sizeof(int32_t) + gs::align_up(temp, 256) + 256;
+  // the same workspace serves gs_project_compact_*
+  size_t compact = 0;
+  gs_project_compact_workspace_bytes(n, 1, &compact);
+  if (compact > *bytes) *bytes = compact;
+  return GS_OK;
+}
+
+extern "C" int gs_project_compact_workspace_bytes(int64_t n, int32_t fp64, size_t *bytes) {
+  GS_CHECK_ARG(bytes != nullptr && n >= 0, "project_compact_workspace_bytes: bad arguments");
+  const size_t temp = fp64 ? gs::project_compact_temp_bytes<double>(n) : gs::project_compact_temp_bytes<float>(n);
+  *bytes = 256 + gs::align_up(temp, 256) + 256;
   return GS_OK;
 }
 
@@ -425,6 +576,17 @@ extern "C" int gs_project_workspace_bytes(int64_t n, size_t *bytes) {
     return gs::project_cull<real>(position, log_scaling, rotation, alpha_logit, T, projection, n, width, height,  \
                                   near_plane, far_plane, blur_cov, clamp_margin, alpha_threshold, workspace,      \
                                   workspace_bytes, num_visible_host, (cudaStream_t)stream);                       \
+  }                                                                                                               \
+  extern "C" int gs_project_compact_##SUFFIX(                                                                     \
+      const real *position, const real *log_scaling, const real *rotation, const real *alpha_logit,               \
+      const real *T, const real *projection, int64_t n, int32_t width, int32_t height, double near_plane,         \
+      double far_plane, double blur_cov, double clamp_margin, double alpha_threshold, void *workspace,            \
+      size_t workspace_bytes, real *points, real *depth, int64_t *indexes, real *ndc_depth,                       \
+      int32_t *num_visible_host, void *stream) {                                                                  \
+    return gs::project_compact<real>(position, log_scaling, rotation, alpha_logit, T, projection, n, width,       \
+                                     height, near_plane, far_plane, blur_cov, clamp_margin, alpha_threshold,      \
+                                     workspace, workspace_bytes, points, depth, indexes, ndc_depth,               \
+                                     num_visible_host, (cudaStream_t)stream);                                     \
   }                                                                                                               \
   extern "C" int gs_project_write_##SUFFIX(                                                                       \
       const real *position, const real *log_scaling, const real *rotation, const real *alpha_logit,               \

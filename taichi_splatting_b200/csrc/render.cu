@@ -134,18 +134,15 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
   const int64_t n = a->n;
   *v_out = 0; *k_out = 0; *max_per_tile_out = 0;
 
-  // ---- projection: cull -> V -> compacted write (+ ndc depth) ----
-  GS_TRY(gs_project_cull_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
-                             a->projection, n, a->width, a->height, a->near_plane, a->far_plane, a->blur_cov,
-                             a->clamp_margin, c.alpha_threshold, a->ws_project, a->ws_project_bytes,
-                             &aux->host_words[0], stream));
+  // ---- projection: single-pass project + cull + ordered compaction (+ ndc depth) -> V ----
+  GS_TRY(gs_project_compact_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
+                                a->projection, n, a->width, a->height, a->near_plane, a->far_plane, a->blur_cov,
+                                a->clamp_margin, c.alpha_threshold, a->ws_project, a->ws_project_bytes, a->points,
+                                a->depths, a->indexes, a->ndc, &aux->host_words[0], stream));
   if (a->use_sh) GS_TRY(gs_camera_position_f32(a->T_camera_world, a->camera_pos, stream));
   GS_CUDA(cudaStreamSynchronize(stream));
   const int64_t v = aux->host_words[0];
   *v_out = v;
-  GS_TRY(gs_project_write_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
-                              a->projection, n, a->width, a->height, a->near_plane, a->far_plane, a->blur_cov,
-                              a->clamp_margin, a->ws_project, a->points, a->depths, a->indexes, a->ndc, stream));
 
   // ---- auxiliary stream: features, zero fills, raster digest (none of it feeds the mapper) ----
   GS_CUDA(cudaEventRecord(aux->fence, stream));

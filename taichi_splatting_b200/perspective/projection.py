@@ -1,7 +1,8 @@
 """Perspective projection operator (reference: taichi_splatting/perspective/projection.py:27-255).
 
 `apply` / `project_to_image` keep the reference's signatures and autograd contract; the device work is
-gs_project_cull / gs_project_write / gs_project_bwd in libgsplat_b200.so (csrc/projection.cu).
+gs_project_compact (single-pass project + cull + ordered compaction) / gs_project_bwd in libgsplat_b200.so
+(csrc/projection.cu); gs_project_cull + gs_project_write remain as the two-kernel form of the same forward.
 """
 from numbers import Integral
 from beartype.typing import Tuple
@@ -30,20 +31,22 @@ class _ProjectFunction(torch.autograd.Function):
     near, far = float(depth_range[0]), float(depth_range[1])
     stream = _lib.stream_ptr(device)
 
+    # single-pass project + cull + ordered compaction: outputs are written into capacity-n buffers, V arrives with the
+    # one host sync of this operator (reference: torch.nonzero), and the results are the first V rows
     nbytes = _lib.c_size_t()
     _lib.call("gs_project_workspace_bytes", n, nbytes)
     ws = _lib.workspace(nbytes.value, device)
     word = _lib.host_word(device)
-    _lib.call(f"gs_project_cull_{sfx}", *p, n, w, h, near, far, float(blur_cov), float(clamp_margin),
-              float(alpha_threshold), ws.data_ptr(), ws.numel(), word.data_ptr(), stream)
-    v = _lib.read_host_word(word, device)   # the one host sync of this operator (reference: torch.nonzero)
-
-    points = torch.empty((v, 7), dtype=dtype, device=device)
-    depth = torch.empty((v, 1), dtype=dtype, device=device)
-    indexes = torch.empty((v,), dtype=torch.int64, device=device)
-    ndc = torch.empty((v, 1), dtype=dtype, device=device) if want_ndc else None
-    _lib.call(f"gs_project_write_{sfx}", *p, n, w, h, near, far, float(blur_cov), float(clamp_margin),
-              ws.data_ptr(), _lib.ptr(points), _lib.ptr(depth), _lib.ptr(indexes), _lib.ptr(ndc), stream)
+    points_n = torch.empty((n, 7), dtype=dtype, device=device)
+    depth_n = torch.empty((n, 1), dtype=dtype, device=device)
+    indexes_n = torch.empty((n,), dtype=torch.int64, device=device)
+    ndc_n = torch.empty((n, 1), dtype=dtype, device=device) if want_ndc else None
+    _lib.call(f"gs_project_compact_{sfx}", *p, n, w, h, near, far, float(blur_cov), float(clamp_margin),
+              float(alpha_threshold), ws.data_ptr(), ws.numel(), _lib.ptr(points_n), _lib.ptr(depth_n),
+              _lib.ptr(indexes_n), _lib.ptr(ndc_n), word.data_ptr(), stream)
+    v = _lib.read_host_word(word, device)
+    points, depth, indexes = points_n[:v], depth_n[:v], indexes_n[:v]
+    ndc = ndc_n[:v] if want_ndc else None
 
     ctx.save_for_backward(*tensors, indexes)
     ctx.image_size, ctx.blur_cov, ctx.clamp_margin = (w, h), float(blur_cov), float(clamp_margin)
