@@ -231,12 +231,58 @@ sh_bwd_views_kernel(const real *__restrict__ positions, const real *__restrict__
   store_row<real, D>(d_params + t * D, acc);
 }
 
+// Three channels (the render path): one thread per Gaussian, so the direction and the basis Y are evaluated once per
+// view instead of once per (view, channel) -- the kernel is bound by that arithmetic, not by its 12 B read per view.
+template <typename real, int DEG>
+__global__ void __launch_bounds__(128)
+sh_bwd_views_rgb_kernel(const real *__restrict__ positions, const real *__restrict__ cam_positions,
+                        const real *__restrict__ g_all, int64_t n, int views, int64_t view_stride,
+                        real *__restrict__ d_params) {
+  constexpr int D = (DEG + 1) * (DEG + 1);
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const real px = positions[3 * i], py = positions[3 * i + 1], pz = positions[3 * i + 2];
+  real acc[3][D];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[c][d] = 0;
+  for (int w = 0; w < views; ++w) {
+    const real *g = g_all + w * view_stride + 3 * i;
+    const real g0 = g[0], g1 = g[1], g2 = g[2];
+    if (g0 == real(0) && g1 == real(0) && g2 == real(0)) continue;
+    const real vx = px - cam_positions[3 * w], vy = py - cam_positions[3 * w + 1], vz = pz - cam_positions[3 * w + 2];
+    const real inv = real(1) / math<real>::sqrt(vx * vx + vy * vy + vz * vz);
+    real Y[D];
+    rsh<real, DEG>(vx * inv, vy * inv, vz * inv, Y);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      acc[0][d] += Y[d] * g0;
+      acc[1][d] += Y[d] * g1;
+      acc[2][d] += Y[d] * g2;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) store_row<real, D>(d_params + (3 * i + c) * D, acc[c]);
+}
+
 template <typename real>
 int sh_bwd_views(const real *positions, const real *cam_positions, const real *g_all, int64_t n, int views,
                  int channels, int64_t view_stride, int degree, real *d_params, cudaStream_t stream) {
   GS_CHECK_ARG(degree >= 0 && degree <= 3, "sh: degree %d not in 0..3", degree);
   int64_t total = n * channels;
   if (total == 0) return GS_OK;
+  if (channels == 3) {
+    const unsigned grid3 = (unsigned)ceil_div(n, 128);
+    switch (degree) {
+      case 0: sh_bwd_views_rgb_kernel<real, 0><<<grid3, 128, 0, stream>>>(positions, cam_positions, g_all, n, views, view_stride, d_params); break;
+      case 1: sh_bwd_views_rgb_kernel<real, 1><<<grid3, 128, 0, stream>>>(positions, cam_positions, g_all, n, views, view_stride, d_params); break;
+      case 2: sh_bwd_views_rgb_kernel<real, 2><<<grid3, 128, 0, stream>>>(positions, cam_positions, g_all, n, views, view_stride, d_params); break;
+      default: sh_bwd_views_rgb_kernel<real, 3><<<grid3, 128, 0, stream>>>(positions, cam_positions, g_all, n, views, view_stride, d_params); break;
+    }
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+  }
   unsigned grid = (unsigned)ceil_div(total, 256);
 #define GS_SH_VIEWS(DEG) \
   sh_bwd_views_kernel<real, DEG><<<grid, 256, 0, stream>>>(positions, cam_positions, g_all, n, views, channels, view_stride, d_params)
