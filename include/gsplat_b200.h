@@ -162,6 +162,15 @@ int gs_sh_bwd_views_f32(const float *positions, const float *cam_positions, cons
  * centre.  d_colours / colours (v, channels), indexes (v). */
 int gs_sh_pack_factors_f32(const float *colours, const float *d_colours, const int64_t *indexes,
                            const float *camera_pos, int64_t v, int32_t channels, int64_t n, float *out, void *stream);
+/* The same pack FUSED with the all-gather, over peer memory: every value is stored straight into this rank's slot of
+ * the gathered buffer of every rank.  peer_bases_host[w] = device pointer (valid in THIS process: symmetric-memory /
+ * CUDA IPC mapping) of rank w's gathered buffer; values land at element slot_offset + (the gs_sh_pack_factors_f32
+ * layout), so the caller passes slot_offset = buffer_slot * world * view_stride + rank * view_stride.  The stores to
+ * remote buffers travel over NVLink while the kernel runs; the caller orders them before the readers with a
+ * symmetric-memory barrier on the same stream. */
+int gs_sh_pack_factors_peers_f32(const float *colours, const float *d_colours, const int64_t *indexes,
+                                 const float *camera_pos, int64_t v, int32_t channels, int64_t n,
+                                 const uint64_t *peer_bases_host, int32_t world, int64_t slot_offset, void *stream);
 
 /* ---- R3-R7: tile mapper -------------------------------------------------------------------------
  * gs_tile_count      replaces tile_overlaps_kernel (mapper/tile_mapper.py:75-86, grid_query.py:46-93)

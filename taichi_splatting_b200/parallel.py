@@ -81,20 +81,62 @@ class ShGradientExchange:
   sum_w Y_w * g_w locally with one kernel (gs_sh_bwd_views_f32).  The result equals the all-reduced gradient up to
   fp32 summation order.  Used through `render_view_parallel`; the renderer's backward calls `sum_sh_gradient`."""
 
-  def __init__(self, group=None, reduce_geometry=False):
+  def __init__(self, group=None, reduce_geometry=False, peer_memory: Optional[bool] = None):
     self.group = group
     self.rank, self.world = world_info(group)
     # reduce_geometry: the backward also all-reduces the geometry gradients (position, log_scaling, rotation,
     # alpha_logit), written by the projection backward into ONE flat buffer, while the SH gradient is rebuilt -- the
     # caller then needs no collective of its own after loss.backward()
     self.reduce_geometry = reduce_geometry
+    # peer_memory: the all-gather of the factors is FUSED into the kernel that packs them -- it stores straight into
+    # every rank's gathered buffer over NVLink (symmetric memory) -- instead of pack + NCCL all-gather.  None: use it
+    # when the symmetric-memory rendezvous works (GS_PEER_EXCHANGE=0 forces NCCL).
+    self.peer_memory = peer_memory
+    self._peer = {}      # (n, channels) -> symmetric gathered buffer (2 slots), its handle, frame counter
+
+  def _peer_state(self, n, channels, device):
+    """Two gathered slots (alternating per frame, so that a fast rank writing frame i + 1 never touches what a slow
+    rank still reads for frame i; one barrier per frame orders the rest) in symmetric memory, mapped on every rank."""
+    import os
+    key = (n, channels, device.index)
+    if key in self._peer:
+      return self._peer[key]
+    state = None
+    want = self.peer_memory if self.peer_memory is not None else os.environ.get("GS_PEER_EXCHANGE", "1") != "0"
+    if want and self.world > 1 and device.type == "cuda" and dist.get_backend(self.group) == "nccl":
+      try:
+        import torch.distributed._symmetric_memory as symm_mem
+        stride = n * channels + 3
+        buf = symm_mem.empty((2, self.world, stride), dtype=torch.float32, device=device)
+        handle = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        bases = [int(p) for p in handle.buffer_ptrs]
+        assert len(bases) == self.world and all(bases)
+        state = dict(buf=buf, handle=handle, bases=bases, stride=stride, frame=0)
+      except Exception as e:   # no peer mapping on this system: the NCCL path is always there
+        if self.peer_memory:
+          raise
+        state = None
+        self._peer_error = repr(e)
+    self._peer[key] = state
+    return state
 
   def start(self, sh_params, indexes, colours, d_colours, camera_pos):
-    """Launch the all-gather of this rank's factors (asynchronously: the caller overlaps the projection backward).
-    One kernel packs them (gs_sh_pack_factors_f32: clamp mask, scatter to dense rows, camera centre)."""
+    """Make this rank's factors available on every rank (asynchronously: the caller overlaps the projection backward).
+    Peer-memory mode: ONE kernel packs them (clamp mask, scatter to dense rows, camera centre) and stores them into
+    every rank's gathered buffer (gs_sh_pack_factors_peers_f32).  Otherwise: gs_sh_pack_factors_f32 + NCCL all-gather."""
     from . import _lib
     n, channels = sh_params.shape[0], sh_params.shape[1]
     device = sh_params.device
+    peer = self._peer_state(n, channels, device)
+    if peer is not None:
+      slot = peer["frame"] % 2
+      peer["frame"] += 1
+      stride = peer["stride"]
+      bases = (_lib.ctypes.c_uint64 * self.world)(*peer["bases"])
+      _lib.call("gs_sh_pack_factors_peers_f32", _lib.ptr(colours), _lib.ptr(d_colours), _lib.ptr(indexes),
+                _lib.ptr(camera_pos), indexes.shape[0], channels, n, bases, self.world,
+                (slot * self.world + self.rank) * stride, _lib.stream_ptr(device))
+      return ("peer", peer, slot, stride)
     stride = n * channels + 3
     local = torch.empty((stride,), dtype=torch.float32, device=device)
     _lib.call("gs_sh_pack_factors_f32", _lib.ptr(colours), _lib.ptr(d_colours), _lib.ptr(indexes), _lib.ptr(camera_pos),
@@ -106,8 +148,15 @@ class ShGradientExchange:
   def finish(self, pending, sh_params, positions, degree):
     """Wait for the gathered factors and rebuild sum_w Y_w * g_w -> d_params (N, C, D)."""
     from . import _lib
-    work, gathered, _local, stride = pending
-    work.wait()
+    if pending[0] == "peer":
+      _, peer, slot, stride = pending
+      # every rank's stores into every gathered buffer are complete and visible once all ranks have passed this
+      # barrier (signal pads of the symmetric allocation, enqueued on the current stream: no host involvement)
+      peer["handle"].barrier(channel=slot)
+      gathered = peer["buf"][slot]
+    else:
+      work, gathered, _local, stride = pending
+      work.wait()
     n, channels = sh_params.shape[0], sh_params.shape[1]
     cams = gathered[:, n * channels:].contiguous()
     d_params = torch.empty_like(sh_params)
