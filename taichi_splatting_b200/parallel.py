@@ -150,53 +150,6 @@ class ShGradientExchange:
     work = dist.all_gather_into_tensor(gathered, local, group=self.group, async_op=True)
     return (work, gathered, local, stride)
 
-  # ---- geometry gradients: all-reduce of one flat buffer, in symmetric memory when the system maps it --------------
-  def geometry_buffer(self, n: int, device) -> torch.Tensor:
-    """The flat (11 n) buffer the projection backward writes position | log_scaling | rotation | alpha_logit gradients
-    into.  With peer memory it is a persistent symmetric allocation (so that `reduce_geometry_async` can use the
-    NVLink-switch all-reduce of torch's symm_mem ops instead of an NCCL ring); the caller copies the reduced values
-    out, the buffer is reused by the next frame."""
-    peer = self._peer_state_any(device)
-    if peer is None:
-      return torch.empty((11 * n,), dtype=torch.float32, device=device)
-    key = ("geom", n, device.index)
-    if key not in self._peer:
-      import torch.distributed._symmetric_memory as symm_mem
-      buf = symm_mem.empty((11 * n,), dtype=torch.float32, device=device)
-      handle = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-      self._peer[key] = dict(buf=buf, handle=handle, stream=torch.cuda.Stream(device=device))
-    return self._peer[key]["buf"]
-
-  def _peer_state_any(self, device):
-    for key, state in self._peer.items():
-      if state is not None and key[0] != "geom" and key[-1] == device.index:
-        return state
-    return None
-
-  def reduce_geometry_async(self, flat: torch.Tensor):
-    """Sum `flat` over ranks.  Returns a callable that, when called, makes the current stream wait for the result.
-    Symmetric buffer: torch's symm_mem all-reduce (multimem through the NVLink switch when supported, else two-shot
-    over peer pointers) on a side stream; otherwise an async NCCL all-reduce."""
-    key = ("geom", flat.numel() // 11, flat.device.index)
-    state = self._peer.get(key)
-    if state is not None and state["buf"].data_ptr() == flat.data_ptr():
-      group = self.group if self.group is not None else dist.group.WORLD
-      ops = torch.ops.symm_mem
-      side = state["stream"]
-      side.wait_stream(torch.cuda.current_stream(flat.device))
-      try:
-        with torch.cuda.stream(side):
-          if state["handle"].has_multicast_support and hasattr(ops, "multimem_all_reduce_"):
-            ops.multimem_all_reduce_(flat, "sum", group.group_name)
-          else:
-            ops.two_shot_all_reduce_(flat, "sum", group.group_name)
-        return lambda: torch.cuda.current_stream(flat.device).wait_stream(side)
-      except Exception as e:   # op missing / unsupported size on this build: NCCL below
-        self._peer_error = repr(e)
-        torch.cuda.current_stream(flat.device).wait_stream(side)
-    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-    return work.wait
-
   def finish(self, pending, sh_params, positions, degree):
     """Wait for the gathered factors and rebuild sum_w Y_w * g_w -> d_params (N, C, D)."""
     from . import _lib
