@@ -318,8 +318,10 @@ def run_ours(args):
   # step on the copy stream (five collectives per step made the ranks' copy streams wait on each other five times),
   # then five strided device copies unpack [rank][tensor] into the parameter tensors.
   lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+  # GS_E2E_UPLOAD=full: every rank uploads the whole cloud over its own PCIe link instead (A/B switch)
+  sharded_upload = world > 1 and os.environ.get("GS_E2E_UPLOAD", "sharded") != "full"
   upload_group = dist.new_group() if world > 1 else None   # own communicator: uploads never queue behind gradients
-  if world > 1:
+  if sharded_upload:
     assert n % world == 0, "sharded upload assumes n divisible by the number of ranks"
     h2d_bytes = sum(pinned[k][lo:hi].numel() * 4 for k in names) + sum(t.numel() * 4 for t in cam_pinned)
     shard_sizes = [pinned[k][lo:hi].numel() for k in names]
@@ -332,7 +334,7 @@ def run_ours(args):
   def prefetch(slot):
     with torch.cuda.stream(copy_stream), torch.no_grad():
       copy_stream.wait_event(slot["free"])          # the previous user of this slot has finished computing
-      if world > 1:
+      if sharded_upload:
         slot["shard"].copy_(packed_host, non_blocking=True)
         dist.all_gather_into_tensor(slot["gathered"].view(-1), slot["shard"], group=upload_group)
         for k, off, size in zip(names, shard_offsets, shard_sizes):
@@ -446,7 +448,7 @@ def run_ours(args):
       "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
               "note": ("per rank: 1/N row shard of the cloud + camera over PCIe, shards all-gathered over NVLink"
-                       if world > 1 else "whole cloud + camera over PCIe") + "; image (H,W,3) + loss read back every step; copies double-buffered against compute"},
+                       if sharded_upload else "whole cloud + camera over PCIe (every rank)") + "; image (H,W,3) + loss read back every step; copies double-buffered against compute"},
       "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "stages_ms": stages_ms,
   }
   if multi_gpu_check is not None:
