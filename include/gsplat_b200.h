@@ -168,6 +168,10 @@ int gs_sh_pack_factors_f32(const float *colours, const float *d_colours, const i
  * layout), so the caller passes slot_offset = buffer_slot * world * view_stride + rank * view_stride.  The stores to
  * remote buffers travel over NVLink while the kernel runs; the caller orders them before the readers with a
  * symmetric-memory barrier on the same stream. */
+/* In-place all-reduce (sum) of `count` floats (multiple of 4) over peer memory: peer_bases_host[w] = rank w's copy of the
+ * buffer as mapped in this process (16-byte aligned).  Rank r sums its 1/world slice from every copy and stores the sum
+ * into every copy; the caller puts a symmetric-memory barrier before (all copies written) and after (all sums landed). */
+int gs_allreduce_peers_f32(const uint64_t *peer_bases_host, int32_t world, int32_t rank, int64_t count, void *stream);
 int gs_sh_pack_factors_peers_f32(const float *colours, const float *d_colours, const int64_t *indexes,
                                  const float *camera_pos, int64_t v, int32_t channels, int64_t n,
                                  const uint64_t *peer_bases_host, int32_t world, int64_t slot_offset, void *stream);

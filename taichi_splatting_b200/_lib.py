@@ -95,6 +95,7 @@ SIGNATURES = {
     "gs_camera_position_f32": ([P, P, P], c_int32), "gs_camera_position_f64": ([P, P, P], c_int32),
     "gs_sh_bwd_views_f32": ([P, P, P, I64, I32, I32, I64, I32, P, P], c_int32),
     "gs_sh_pack_factors_f32": ([P, P, P, P, I64, I32, I64, P, P], c_int32),
+    "gs_allreduce_peers_f32": ([POINTER(ctypes.c_uint64), I32, I32, I64, P], c_int32),
     "gs_sh_pack_factors_peers_f32": ([P, P, P, P, I64, I32, I64, POINTER(ctypes.c_uint64), I32, I64, P], c_int32),
     "gs_sh_fwd_f32": (_SH_FWD, c_int32), "gs_sh_fwd_f64": (_SH_FWD, c_int32),
     "gs_sh_bwd_f32": (_SH_BWD, c_int32), "gs_sh_bwd_f64": (_SH_BWD, c_int32),
@@ -176,7 +177,7 @@ def check(code: int, what: str) -> None:
 OWN_KERNELS = {
     "gs_project_cull_f32": 1, "gs_project_cull_f64": 1, "gs_project_compact_f32": 1, "gs_project_compact_f64": 1, "gs_project_write_f32": 1, "gs_project_write_f64": 1,
     "gs_project_bwd_f32": 1, "gs_project_bwd_f64": 1, "gs_camera_position_f32": 1, "gs_camera_position_f64": 1, "gs_sh_fwd_f32": 1, "gs_sh_fwd_f64": 1,
-    "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_sh_bwd_views_f32": 1, "gs_sh_pack_factors_f32": 1, "gs_sh_pack_factors_peers_f32": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
+    "gs_sh_bwd_f32": 1, "gs_sh_bwd_f64": 1, "gs_sh_bwd_views_f32": 1, "gs_sh_pack_factors_f32": 1, "gs_sh_pack_factors_peers_f32": 1, "gs_allreduce_peers_f32": 1, "gs_tile_count": 1, "gs_tile_scan": 1, "gs_tile_emit_keys": 1,
     "gs_tile_ranges": 1, "gs_depth_order": 1, "gs_tile_count_ordered": 1, "gs_tile_emit_ordered": 1, "gs_tile_count_ordered_hits": 1, "gs_tile_emit_hits": 1,
     "gs_tile_ranges_from_tiles": 1, "gs_tile_bin_count": 1, "gs_tile_bin_offsets": 1, "gs_tile_bin_emit": 1,
     "gs_tile_bin_sort": 1, "gs_raster_fwd_f32": 3, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 3, "gs_raster_bwd_f32": 3,

@@ -354,8 +354,10 @@ class _RenderFunction(torch.autograd.Function):
     need = ctx.needs_input_grad
     # position | log_scaling | rotation | alpha_logit as consecutive blocks of one buffer: one collective, no
     # concatenation and no copy back
-    flat = torch.empty((11 * n,), dtype=torch.float32, device=device)
-    geom = [flat[0:3 * n].view(n, 3), flat[3 * n:6 * n].view(n, 3), flat[6 * n:10 * n].view(n, 4), flat[10 * n:].view(n, 1)]
+    # with peer memory the flat buffer is a persistent symmetric allocation, all-reduced in place by our own kernel
+    geom_state = exchange.geometry_state(n, device) if exchange.reduce_geometry else None
+    flat = geom_state["buf"] if geom_state is not None else torch.empty((11 * n,), dtype=torch.float32, device=device)
+    geom = [flat[0:3 * n].view(n, 3), flat[3 * n:6 * n].view(n, 3), flat[6 * n:10 * n].view(n, 4), flat[10 * n:11 * n].view(n, 1)]
     d_T = torch.empty_like(T_camera_world) if need[5] else None
     d_proj = torch.empty_like(projection) if need[6] else None
     grad_g = d_g2d.clone() if d_g2d is not None else torch.empty_like(g2d)
@@ -381,7 +383,12 @@ class _RenderFunction(torch.autograd.Function):
     pending = exchange.start(feature, indexes, features, grad_f, cam_pos)
     args.phases = _lib.GS_BWD_PROJECT
     _lib.call("gs_render_backward_f32", args, stream)
-    # the geometry all-reduce stays NCCL's: torch's symmetric-memory multimem all-reduce of this 44 MB buffer was measured
+    if geom_state is not None and pending[0] == "peer":
+      d_feature, flat = exchange.finish_with_geometry(pending, geom_state, feature, position, check_sh_degree(feature))
+      geom = [flat[0:3 * n].view(n, 3), flat[3 * n:6 * n].view(n, 3), flat[6 * n:10 * n].view(n, 4), flat[10 * n:11 * n].view(n, 1)]
+      grads = [g if need[i] else None for i, g in enumerate(geom)]
+      return (grads[0], grads[1], grads[2], grads[3], d_feature, d_T, d_proj, None, None, None, None, None, None)
+    # NCCL path.  torch's own symmetric-memory all-reduce is no alternative: torch's symmetric-memory multimem all-reduce of this 44 MB buffer was measured
     # at 0.40 ms on 2 GPUs against 0.11-0.17 ms for the NCCL ring (profiles/r02/r02o_timeline_n2.txt)
     reduce = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=exchange.group, async_op=True) if exchange.reduce_geometry else None
     d_feature = exchange.finish(pending, feature, position, check_sh_degree(feature))
