@@ -402,17 +402,20 @@ __global__ void __launch_bounds__(256)
 sh_pack_factors_peers_kernel(const float *__restrict__ colours, const float *__restrict__ d_colours,
                              const int64_t *__restrict__ indexes, const float *__restrict__ camera_pos, int64_t v,
                              int channels, int64_t n, const __grid_constant__ PeerTable peers, int64_t slot_offset) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t < 3) {
-    const float c = camera_pos[t];
-    for (int w = 0; w < peers.world; ++w) peers.base[w][slot_offset + n * channels + t] = c;
+  // grid-stride over a SMALL grid: the kernel is bound by NVLink egress, which a few SMs' store pipes saturate, and it
+  // runs beside the projection backward, which needs the other SMs
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t0 < 3) {
+    const float c = camera_pos[t0];
+    for (int w = 0; w < peers.world; ++w) peers.base[w][slot_offset + n * channels + t0] = c;
   }
-  if (t >= v * channels) return;
-  const int64_t i = t / channels;
-  const float col = colours[t];
-  const float g = (col > 0.f && col < 1.f) ? d_colours[t] : 0.f;
-  const int64_t at = slot_offset + indexes[i] * channels + (t - i * channels);
-  for (int w = 0; w < peers.world; ++w) peers.base[w][at] = g;
+  for (int64_t t = t0; t < v * channels; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / channels;
+    const float col = colours[t];
+    const float g = (col > 0.f && col < 1.f) ? d_colours[t] : 0.f;
+    const int64_t at = slot_offset + indexes[i] * channels + (t - i * channels);
+    for (int w = 0; w < peers.world; ++w) peers.base[w][at] = g;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -439,7 +442,8 @@ extern "C" int gs_sh_pack_factors_peers_f32(const float *colours, const float *d
     GS_LAUNCH_CHECK();
   }
   const int64_t total = v * channels > 3 ? v * channels : 3;
-  gs::sh_pack_factors_peers_kernel<<<(unsigned)gs::ceil_div(total, 256), 256, 0, stream>>>(
+  const int64_t blocks = gs::ceil_div(total, 256);
+  gs::sh_pack_factors_peers_kernel<<<(unsigned)(blocks < 96 ? blocks : 96), 256, 0, stream>>>(
       colours, d_colours, indexes, camera_pos, v, channels, n, peers, slot_offset);
   GS_LAUNCH_CHECK();
   return GS_OK;

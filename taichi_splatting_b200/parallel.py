@@ -94,8 +94,8 @@ class ShGradientExchange:
     # caller then needs no collective of its own after loss.backward()
     self.reduce_geometry = reduce_geometry
     # peer_memory: the all-gather of the factors is FUSED into the kernel that packs them -- it stores straight into
-    # every rank's gathered buffer over NVLink (symmetric memory) -- instead of pack + NCCL all-gather.  None: use it
-    # when the symmetric-memory rendezvous works (GS_PEER_EXCHANGE=0 forces NCCL).
+    # every rank's gathered buffer over NVLink (symmetric memory) -- instead of pack + NCCL all-gather; the geometry
+    # buffer is then all-reduced in place by gs_allreduce_peers_f32.  None: only when GS_PEER_EXCHANGE=1.
     self.peer_memory = peer_memory
     self._peer = _PEER_STATE.setdefault(id(group) if group is not None else 0, {})   # shared across frames
 
@@ -104,24 +104,27 @@ class ShGradientExchange:
     rank still reads for frame i; one barrier per frame orders the rest) in symmetric memory, mapped on every rank."""
     import os
     key = (n, channels, device.index)
+    state = None
+    # default OFF: at 8 ranks the NCCL exchange measured 2.53 ms per step against 2.58-2.64 with peer memory (equal at
+    # 2 and 4 ranks; profiles/r02/r02q_*, r02s_*) -- opt in with peer_memory=True or GS_PEER_EXCHANGE=1
+    want = self.peer_memory if self.peer_memory is not None else os.environ.get("GS_PEER_EXCHANGE", "0") == "1"
+    if not (want and self.world > 1 and device.type == "cuda" and dist.get_backend(self.group) == "nccl"):
+      return None
     if key in self._peer:
       return self._peer[key]
-    state = None
-    want = self.peer_memory if self.peer_memory is not None else os.environ.get("GS_PEER_EXCHANGE", "1") != "0"
-    if want and self.world > 1 and device.type == "cuda" and dist.get_backend(self.group) == "nccl":
-      try:
-        import torch.distributed._symmetric_memory as symm_mem
-        stride = n * channels + 3
-        buf = symm_mem.empty((2, self.world, stride), dtype=torch.float32, device=device)
-        handle = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-        bases = [int(p) for p in handle.buffer_ptrs]
-        assert len(bases) == self.world and all(bases)
-        state = dict(buf=buf, handle=handle, bases=bases, stride=stride, frame=0, stream=torch.cuda.Stream(device=device))
-      except Exception as e:   # no peer mapping on this system: the NCCL path is always there
-        if self.peer_memory:
-          raise
-        state = None
-        self._peer_error = repr(e)
+    try:
+      import torch.distributed._symmetric_memory as symm_mem
+      stride = n * channels + 3
+      buf = symm_mem.empty((2, self.world, stride), dtype=torch.float32, device=device)
+      handle = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+      bases = [int(p) for p in handle.buffer_ptrs]
+      assert len(bases) == self.world and all(bases)
+      state = dict(buf=buf, handle=handle, bases=bases, stride=stride, frame=0, stream=torch.cuda.Stream(device=device))
+    except Exception as e:   # no peer mapping on this system: the NCCL path is always there
+      if self.peer_memory:
+        raise
+      state = None
+      self._peer_error = repr(e)
     self._peer[key] = state
     return state
 
@@ -162,7 +165,9 @@ class ShGradientExchange:
   def geometry_state(self, n: int, device):
     """Persistent symmetric (11 n, padded to a multiple of 4) buffer for position | log_scaling | rotation | alpha_logit
     gradients, or None when peer memory is not in use (first frame included: the factor buffers are set up first)."""
-    if not any(st is not None and k[0] != "geom" and k[-1] == device.index for k, st in self._peer.items()):
+    import os
+    want = self.peer_memory if self.peer_memory is not None else os.environ.get("GS_PEER_EXCHANGE", "0") == "1"
+    if not want or not any(st is not None and k[0] != "geom" and k[-1] == device.index for k, st in self._peer.items()):
       return None
     key = ("geom", n, device.index)
     if key not in self._peer:

@@ -107,6 +107,18 @@ def _worker(rank, world, port, results):
     for k in names:
       want = sum(pv[k] for pv in per_view)
       assert _rel(getattr(c, k).grad, want) < 2e-5, ("structured", k, _rel(getattr(c, k).grad, want))
+    # ... with everything reduced inside the backward, over NCCL and over peer memory (fused pack + all-gather kernel,
+    # in-place peer all-reduce); several frames, so that both gathered slots and the persistent buffers are reused
+    for mode in ("0", "1"):
+      os.environ["GS_PEER_EXCHANGE"] = mode
+      for frame in range(4):
+        c, cm, _ = _scene(ts, dev, yaw=2.0 * rank)
+        o = parallel.render_view_parallel(c, cm, cfg, use_sh=True, reduce_in_backward=True)
+        (o.image * R).sum().backward()
+        for k in names:
+          want = sum(pv[k] for pv in per_view)
+          assert _rel(getattr(c, k).grad, want) < 2e-5, ("in-backward", mode, frame, k, _rel(getattr(c, k).grad, want))
+    os.environ.pop("GS_PEER_EXCHANGE", None)
     results[rank] = "ok"
   finally:
     dist.destroy_process_group()
