@@ -19,7 +19,9 @@ path = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 rows = list(csv.DictReader([l for l in open(path) if not l.startswith("==")]))
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 if steps > 1:   # warm step only: the first steps pay module loading and cold caches
-  starts = [i for i, r in enumerate(rows) if "project_cull" in r["Kernel Name"]]
+  # first kernel of a step: the compaction init of the single-pass projection (round 2), else the round-1 cull kernel
+  starts = [i for i, r in enumerate(rows) if "DeviceCompactInitKernel" in r["Kernel Name"]] or \
+           [i for i, r in enumerate(rows) if "project_cull" in r["Kernel Name"]]
   rows = rows[starts[-1]:]
 agg, tot = {}, 0.0
 for r in rows:
@@ -55,7 +57,7 @@ want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occup
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 traffic = {}
-lines += ["## `ncu --set full` captures (raster kernels)", ""]
+lines += ["## `ncu --set full` captures (every hand-written kernel of the step)", ""]
 for r in rr[2:]:
   if len(r) != len(hdr):
     continue
