@@ -426,7 +426,9 @@ def run_ours(args):
       "traffic": traffic, "algorithmic_bytes_per_launch": stage_bytes["raster_bwd"], "kernel_ms": round(bwd_ms, 4) if bwd_ms else None,
       "note": "raster kernels are bound by the L1/shared-memory data pipe (broadcast loads of the per-splat records, the "
               "backward's transpose panel), not by HBM (~100 flop per gathered byte), so their HBM fraction is low by "
-              "construction; see limiter and the pipeline-level figure in pipeline_hbm",
+              "construction; see limiter and the pipeline-level figure in pipeline_hbm.  `traffic` (ncu, same build) is above "
+              "the SURVEY formula's bytes because a tile's batch is bulk-copied as 64 bytes per overlap (48-byte sweep record + "
+              "16-byte flush record + 4-byte index) where the formula counts a 44-byte gather; nothing is read twice",
       "limiter": limiter,
       "pipeline_hbm": {"algorithmic_bytes_per_step": total_bytes,
                        "achieved": round(total_bytes / (ms_per_step * 1e-3) / 1e9, 2),
