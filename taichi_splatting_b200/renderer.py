@@ -332,6 +332,8 @@ class _RenderFunction(torch.autograd.Function):
       _lib.call("gs_render_backward_f32", args, _lib.stream_ptr(device))
       tile_shard.reduce(flat)      # THE collective of the tile-sharded path: 4 (7 + F) bytes per visible Gaussian
       args.phases = _lib.GS_BWD_FEATURE | _lib.GS_BWD_PROJECT
+      if _lib.profiler is not None:   # the two phase calls together launch the driver's 3 kernels once
+        _lib.profiler.launches -= _lib.OWN_KERNELS["gs_render_backward_f32"]
     _lib.call("gs_render_backward_f32", args, _lib.stream_ptr(device))
     if d_cam is not None:
       grads[4] += camera_position_vjp(T_camera_world, cam_pos, d_cam)
@@ -383,6 +385,8 @@ class _RenderFunction(torch.autograd.Function):
     pending = exchange.start(feature, indexes, features, grad_f, cam_pos)
     args.phases = _lib.GS_BWD_PROJECT
     _lib.call("gs_render_backward_f32", args, stream)
+    if _lib.profiler is not None:   # two phase calls, each counted as the whole driver (3 kernels): raster + projection = 2
+      _lib.profiler.launches -= 2 * _lib.OWN_KERNELS["gs_render_backward_f32"] - 2
     if geom_state is not None and pending[0] == "peer":
       d_feature, flat = exchange.finish_with_geometry(pending, geom_state, feature, position, check_sh_degree(feature))
       geom = [flat[0:3 * n].view(n, 3), flat[3 * n:6 * n].view(n, 3), flat[6 * n:10 * n].view(n, 4), flat[10 * n:11 * n].view(n, 1)]
