@@ -37,7 +37,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
 # keep the second step only
-mid = [i for i, e in enumerate(evs) if "project_cull" in e.name]
+mid = [i for i, e in enumerate(evs) if "DeviceCompactInitKernel" in e.name]   # first kernel of gs_project_compact
 evs = evs[mid[1]:]
 t0 = evs[0].time_range.start
 prev_end = t0

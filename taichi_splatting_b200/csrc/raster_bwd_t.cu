@@ -74,9 +74,25 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// Feature part of a raster_pack record behind Q1 = {uy, wy, alpha, f0}: {f1, f2, depth, mask} (1..3 features) |
+// {f1, f2, f3, depth} (4 features).  The backward never needs the depth: 0, 4, 8 or 16 bytes are read.
+template <int F>
+__device__ __forceinline__ float4 load_tail(const unsigned char *q2) {
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (F == 4) {
+    t = *reinterpret_cast<const float4 *>(q2);
+  } else if (F == 3) {
+    const float2 h = *reinterpret_cast<const float2 *>(q2);
+    t.x = h.x; t.y = h.y;
+  } else if (F == 2) {
+    t.x = *reinterpret_cast<const float *>(q2);
+  }
+  return t;
+}
+
 template <int RECW>
 struct Smem {
-  // two landing buffers of raster_pack records {tx0, ty0, ux, wx | uy, wy, alpha, depth | features (, mask)}
+  // two landing buffers of raster_pack records {tx0, ty0, ux, wx | uy, wy, alpha, f0 | f1, f2, (f3,) depth, mask}
   // (+1: null record that pads the hit lists)
   float4 rec[2][(kBatch + 1) * RECW];
   float acc[kBatch * kAcc];
@@ -108,7 +124,7 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
   const bool in_bounds[2] = {px < P.width && py[0] < P.height, px < P.width && py[1] < P.height};
   // pixel centre relative to the tile centre: (tx, ty) = lx (ux, wx) + ly (uy, wy) + (tx0, ty0)
   const float lx = (float)bx - 7.5f, ly0 = (float)by - 7.5f;
-  const f32x2 lx2 = pk(lx, lx), ly2[2] = {pk(ly0, ly0), pk(ly0 + 4.0f, ly0 + 4.0f)};
+  const f32x2 lx2 = pk(lx, lx), lyp = pk(ly0, ly0 + 4.0f);   // the lane's column; the rows of its two pixels
   const float clamp_max = P.clamp_max, thr = P.thr;
   const float t_min = 1.0f - P.sat;   // a pixel is saturated (backward.py:131) once its transmittance is <= 1 - sat
 
@@ -219,7 +235,7 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
       const unsigned off = sm.list[warp][3];
       A = *reinterpret_cast<const float4 *>(rec + off);
       B = *reinterpret_cast<const float4 *>(rec + off + 16);
-      fv = *reinterpret_cast<const float4 *>(rec + off + 32);
+      fv = load_tail<F>(rec + off + 32);
     }
     for (int h0 = 0; h0 < nhit; h0 += kChunk) {
       // ---- phase 1: lane = two pixels; 8 splats in depth order ----
@@ -232,15 +248,16 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
         const unsigned off_next = next_off[u];
         const float4 An = *reinterpret_cast<const float4 *>(rec + off_next);
         const float4 Bn = *reinterpret_cast<const float4 *>(rec + off_next + 16);
-        const float4 fn = *reinterpret_cast<const float4 *>(rec + off_next + 32);
-        const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
-        const f32x2 uw_x = pk(A.z, A.w), uw_y = pk(B.x, B.y);
-        const f32x2 tbase = fma2(lx2, uw_x, pk(A.x, A.y));
-        const f32x2 t2[2] = {fma2(ly2[0], uw_y, tbase), fma2(ly2[1], uw_y, tbase)};
-        float t0x, t0y, t1x, t1y;
-        upk(t2[0], t0x, t0y);
-        upk(t2[1], t1x, t1y);
-        const float g0 = ex2_approx(-fmaf(t0x, t0x, t0y * t0y)), g1 = ex2_approx(-fmaf(t1x, t1x, t1y * t1y));
+        const float4 fn = load_tail<F>(rec + off_next + 32);
+        const float feat[4] = {B.w, fv.x, fv.y, fv.z};
+        // t = lx (ux, wx) + ly (uy, wy) + t0, kept component-major over the pixel pair -- tx2 = (tx of pixel 0, of
+        // pixel 1) -- so that |t|^2 of both pixels is one FMUL2 + one FFMA2 (scalar operands broadcast for free)
+        float cx, cy;
+        upk(fma2(lx2, pk(A.z, A.w), pk(A.x, A.y)), cx, cy);
+        const f32x2 tx2 = fma2(pk(B.x, B.x), lyp, pk(cx, cx)), ty2 = fma2(pk(B.y, B.y), lyp, pk(cy, cy));
+        float q0, q1;
+        upk(fma2(tx2, tx2, mul2(ty2, ty2)), q0, q1);
+        const float g0 = ex2_approx(-q0), g1 = ex2_approx(-q1);
         const f32x2 ga2 = pk(g0, g1), alpha_pt2 = pk(B.z, B.z);
         float a0, a1;
         upk(mul2(ga2, alpha_pt2), a0, a1);
@@ -275,12 +292,10 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
         if (HEUR) {
           // |G dpdf/dmean|_1 = |Gp| (|tx ux + ty wx| + |tx uy + ty wy|) / k^2  (t and u, w carry one factor k each;
           // the 1 / k^2 is applied once per splat in phase 2)
-          float p0, p1, q0, q1, r0, r1, v0, v1, hk0, hk1;
-          upk(mul2(t2[0], uw_x), p0, p1);
-          upk(mul2(t2[0], uw_y), q0, q1);
-          upk(mul2(t2[1], uw_x), r0, r1);
-          upk(mul2(t2[1], uw_y), v0, v1);
-          upk(mul2(pk(fabsf(p0 + p1) + fabsf(q0 + q1), fabsf(r0 + r1) + fabsf(v0 + v1)), Gp2), hk0, hk1);
+          float dx0, dx1, dy0, dy1, hk0, hk1;
+          upk(fma2(pk(A.z, A.z), tx2, mul2(pk(A.w, A.w), ty2)), dx0, dx1);   // tx ux + ty wx of both pixels
+          upk(fma2(pk(B.x, B.x), tx2, mul2(pk(B.y, B.y), ty2)), dy0, dy1);   // tx uy + ty wy
+          upk(mul2(pk(fabsf(dx0) + fabsf(dy0), fabsf(dx1) + fabsf(dy1)), Gp2), hk0, hk1);
           e0.z = fmaf(G0, G0, G1 * G1);
           e0.w = fabsf(hk0) + fabsf(hk1);
         }

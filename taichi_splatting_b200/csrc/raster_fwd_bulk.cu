@@ -52,6 +52,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Third quad of a raster_pack record: { f1, f2, depth, mask } (1..3 features) | { f1, f2, f3, depth } (4 features); f0
+// travels in Q1.w.  Only as much of it is read as the sweep needs.
+template <int F, bool DEPTH>
+__device__ __forceinline__ void load_tail(const unsigned char *q2, float f0, float (&feat)[4], float &depth) {
+  feat[0] = f0; feat[1] = feat[2] = feat[3] = 0.f; depth = 0.f;
+  if (F == 4 || DEPTH) {
+    const float4 t = *reinterpret_cast<const float4 *>(q2);
+    feat[1] = t.x; feat[2] = t.y;
+    if (F == 4) { feat[3] = t.z; depth = t.w; } else { depth = t.z; }
+  } else if (F == 3) {
+    const float2 t = *reinterpret_cast<const float2 *>(q2);
+    feat[1] = t.x; feat[2] = t.y;
+  } else if (F == 2) {
+    feat[1] = *reinterpret_cast<const float *>(q2);
+  }
+}
+
 template <int RECW>
 struct Smem {
   float4 rec[2][(kBatch + 1) * RECW];   // two landing buffers of raster_pack records (+1: null record for list padding)
@@ -96,7 +113,7 @@ raster_fwd_bulk_kernel(const float4 *__restrict__ records, const int32_t *__rest
   const int px = tile_x0 + bx, py[2] = {tile_y0 + by, tile_y0 + by + 4};
   const bool in_bounds[2] = {px < P.width && py[0] < P.height, px < P.width && py[1] < P.height};
   const float lx = (float)bx - 7.5f, ly0 = (float)by - 7.5f;
-  const f32x2 lx2 = pk(lx, lx), ly2[2] = {pk(ly0, ly0), pk(ly0 + 4.0f, ly0 + 4.0f)};
+  const f32x2 lx2 = pk(lx, lx), lyp = pk(ly0, ly0 + 4.0f);   // the lane's column; the rows of its two pixels
   const float clamp_max = P.clamp_max, thr = P.thr, eps = P.fwd_eps;
   const float median_trans = 1.0f - median_lim;   // sum of weights < lim  <=>  transmittance > 1 - lim
 
@@ -181,13 +198,16 @@ raster_fwd_bulk_kernel(const float4 *__restrict__ records, const int32_t *__rest
           const unsigned off = offs[u];
           const float4 A = *reinterpret_cast<const float4 *>(rb + off);
           const float4 B = *reinterpret_cast<const float4 *>(rb + off + 16);
-          const float4 fv = *reinterpret_cast<const float4 *>(rb + off + 32);
-          const float feat[4] = {fv.x, fv.y, fv.z, fv.w};
-          const f32x2 tbase = fma2(lx2, pk(A.z, A.w), pk(A.x, A.y)), uw_y = pk(B.x, B.y);
-          float t0x, t0y, t1x, t1y;
-          upk(fma2(ly2[0], uw_y, tbase), t0x, t0y);
-          upk(fma2(ly2[1], uw_y, tbase), t1x, t1y);
-          const float g0 = ex2_approx(-fmaf(t0x, t0x, t0y * t0y)), g1 = ex2_approx(-fmaf(t1x, t1x, t1y * t1y));
+          float feat[4], depth;
+          load_tail<F, kMedian>(rb + off + 32, B.w, feat, depth);
+          // t = lx (ux, wx) + ly (uy, wy) + t0, kept component-major over the pixel pair -- tx2 = (tx of pixel 0, of
+          // pixel 1) -- so that |t|^2 of both pixels is one FMUL2 + one FFMA2 (scalar operands broadcast for free)
+          float cx, cy;
+          upk(fma2(lx2, pk(A.z, A.w), pk(A.x, A.y)), cx, cy);
+          const f32x2 tx2 = fma2(pk(B.x, B.x), lyp, pk(cx, cx)), ty2 = fma2(pk(B.y, B.y), lyp, pk(cy, cy));
+          float q0, q1;
+          upk(fma2(tx2, tx2, mul2(ty2, ty2)), q0, q1);
+          const float g0 = ex2_approx(-q0), g1 = ex2_approx(-q1);
           float alpha[2], weight[2];
           upk(mul2(pk(g0, g1), pk(B.z, B.z)), alpha[0], alpha[1]);
           alpha[0] = fminf(alpha[0], clamp_max);
@@ -199,8 +219,8 @@ raster_fwd_bulk_kernel(const float4 *__restrict__ records, const int32_t *__rest
           weight[0] = hit[0] ? weight[0] : 0.f;
           weight[1] = hit[1] ? weight[1] : 0.f;
           if (kMedian) {   // the splat that crosses the limit is the last one entered below it
-            median[0] = (hit[0] && trans[0] > median_trans) ? B.w : median[0];
-            median[1] = (hit[1] && trans[1] > median_trans) ? B.w : median[1];
+            median[0] = (hit[0] && trans[0] > median_trans) ? depth : median[0];
+            median[1] = (hit[1] && trans[1] > median_trans) ? depth : median[1];
           }
           upk(sub2(pk(trans[0], trans[1]), pk(weight[0], weight[1])), trans[0], trans[1]);
           const f32x2 w2 = pk(weight[0], weight[1]);

@@ -7,9 +7,12 @@
 //
 //   records[k]  (48 bytes, 1..3 features | 64 bytes, 4 features), tile-centred, ready for the sweep:
 //       Q0 = { tx0, ty0, ux, wx }      (tx, ty) = X (ux, wx) + Y (uy, wy) + (tx0, ty0), (X, Y) = pixel - tile centre
-//       Q1 = { uy, wy, alpha, depth }
-//       Q2 = { f0, f1, f2, mask }      mask = bit w set: the splat can reach 8x8 pixel block w of its tile
-//      [Q3 = { mask, 0, 0, 0 }         only with 4 features, where Q2.w is f3]
+//       Q1 = { uy, wy, alpha, f0 }
+//       Q2 = { f1, f2, depth, mask }   mask = bit w set: the splat can reach 8x8 pixel block w of its tile
+//      [Q2 = { f1, f2, f3, depth }, Q3 = { mask, 0, 0, 0 }   with 4 features]
+//     ordered so that a sweep which does not need the depth (every sweep but the forward's first few splats of a
+//     pixel, which track the median depth) reads Q0, Q1 and only HALF of Q2: a warp-wide broadcast LDS.64 costs 1.63
+//     cycles of the shared-memory data pipe against 2.69 for an LDS.128 (profiles/r01p_micro.txt)
 //   flush[k]    (16 bytes, backward only) = { mean - tile centre, 1/sigma.x, 1/sigma.y }
 //
 // so the raster kernels fetch a batch with a single `cp.async.bulk` (bulk_copy.cuh) while they sweep the previous
@@ -72,11 +75,11 @@ __device__ __forceinline__ void pack_one(const float4 *__restrict__ digest, cons
   }
   float4 *out = records + (int64_t)RECW * k;
   out[0] = make_float4(tx0, ty0, ux, wx);
-  out[1] = R1;
+  out[1] = make_float4(R1.x, R1.y, R1.z, R2.x);
   if (RECW == 3) {
-    out[2] = make_float4(R2.x, R2.y, R2.z, __uint_as_float(mask));
+    out[2] = make_float4(R2.y, R2.z, R1.w, __uint_as_float(mask));
   } else {
-    out[2] = R2;
+    out[2] = make_float4(R2.y, R2.z, R2.w, R1.w);
     out[3] = make_float4(__uint_as_float(mask), 0.f, 0.f, 0.f);
   }
   if (FLUSH) flush[k] = make_float4(ddx, ddy, R3.y, R3.z);

@@ -85,25 +85,23 @@ class _RenderFunction(torch.autograd.Function):
     feature_c = feature.detach().contiguous()
     pin = [ptr(t) for t in tensors]
 
-    # ---- projection: cull -> V -> compacted write (+ ndc depth) ----
+    # ---- projection: single-pass project + cull + ordered compaction (+ ndc depth) into capacity-n buffers -> V ----
     nbytes = _lib.c_size_t()
     call("gs_project_workspace_bytes", n, nbytes)
     ws_proj = _lib.workspace(nbytes.value, device)
     word = _lib.host_word(device)
-    call(f"gs_project_cull_{sfx}", *pin, n, w, h, near, far, blur, margin, thr, ws_proj.data_ptr(), ws_proj.numel(),
-         word.data_ptr(), stream)
+    g2d_n = torch.empty((n, 7), dtype=dtype, device=device)
+    depths_n = torch.empty((n, 1), dtype=dtype, device=device)
+    ndc_n = torch.empty((n, 1), dtype=dtype, device=device)
+    indexes_n = torch.empty((n,), dtype=torch.int64, device=device)
+    call(f"gs_project_compact_{sfx}", *pin, n, w, h, near, far, blur, margin, thr, ws_proj.data_ptr(), ws_proj.numel(),
+         ptr(g2d_n), ptr(depths_n), ptr(indexes_n), ptr(ndc_n), word.data_ptr(), stream)
     cam_pos = None
     if use_sh:   # independent of V: enqueue while the host waits for it
       cam_pos = torch.empty((3,), dtype=dtype, device=device)
       call(f"gs_camera_position_{sfx}", pin[4], ptr(cam_pos), stream)
     v = _lib.read_host_word(word, device)
-
-    g2d = torch.empty((v, 7), dtype=dtype, device=device)
-    depths = torch.empty((v, 1), dtype=dtype, device=device)
-    ndc = torch.empty((v, 1), dtype=dtype, device=device)
-    indexes = torch.empty((v,), dtype=torch.int64, device=device)
-    call(f"gs_project_write_{sfx}", *pin, n, w, h, near, far, blur, margin, ws_proj.data_ptr(), ptr(g2d), ptr(depths),
-         ptr(indexes), ptr(ndc), stream)
+    g2d, depths, ndc, indexes = g2d_n[:v], depths_n[:v], ndc_n[:v], indexes_n[:v]
 
     # ---- features: SH at the visible set, or a plain gather ----
     if use_sh:

@@ -115,6 +115,34 @@ def test_projection_vs_oracle_random(ts):
       assert e < 5e-3, (seed, name, e)
 
 
+def test_projection_two_kernel_form_equals_single_pass(ts):
+  """gs_project_cull + gs_project_write (flags -> scan -> recompute and write) and gs_project_compact (one
+  cub::DeviceSelect pass whose load is the projection) are the same forward: identical indexes and bit-identical rows."""
+  from taichi_splatting_b200 import _lib
+  for dtype in (torch.float32, torch.float64):
+    torch.manual_seed(3)
+    cam = random_data.random_camera()
+    g = random_data.random_3d_gaussians(20000, cam, margin=0.5, scale_factor=0.8)
+    ins = [x.to(DEV, dtype).contiguous() for x in (g.position, g.log_scaling, g.rotation, g.alpha_logit, cam.T_camera_world, cam.projection)]
+    n, (w, h), sfx = ins[0].shape[0], cam.image_size, _lib.suffix(dtype)
+    near, far = cam.depth_range
+    pts, depth, idx, ndc = ts.perspective.projection.apply_with_ndc(*ins, cam.image_size, cam.depth_range, 0.3)
+    nbytes = _lib.c_size_t()
+    _lib.call("gs_project_workspace_bytes", n, nbytes)
+    ws = _lib.workspace(nbytes.value, torch.device(DEV))
+    word = _lib.host_word(torch.device(DEV))
+    p = [_lib.ptr(t) for t in ins]
+    stream = _lib.stream_ptr(torch.device(DEV))
+    _lib.call(f"gs_project_cull_{sfx}", *p, n, w, h, near, far, 0.3, 0.15, 1 / 255, ws.data_ptr(), ws.numel(), word.data_ptr(), stream)
+    v = _lib.read_host_word(word, torch.device(DEV))
+    assert v == idx.shape[0] and 0 < v < n
+    pts2, depth2 = torch.empty((v, 7), dtype=dtype, device=DEV), torch.empty((v, 1), dtype=dtype, device=DEV)
+    idx2, ndc2 = torch.empty((v,), dtype=torch.int64, device=DEV), torch.empty((v, 1), dtype=dtype, device=DEV)
+    _lib.call(f"gs_project_write_{sfx}", *p, n, w, h, near, far, 0.3, 0.15, ws.data_ptr(), _lib.ptr(pts2), _lib.ptr(depth2),
+              _lib.ptr(idx2), _lib.ptr(ndc2), stream)
+    assert torch.equal(idx, idx2) and torch.equal(pts, pts2) and torch.equal(depth, depth2) and torch.equal(ndc, ndc2)
+
+
 def test_projection_edge_cases(ts):
   cam = random_data.fixed_camera((64, 48))
   empty = [torch.zeros((0, k), device=DEV) for k in (3, 3, 4, 1)]
