@@ -43,6 +43,9 @@ namespace gs {
 #ifndef GS_BWDT_MIN_BLOCKS
 #define GS_BWDT_MIN_BLOCKS 4
 #endif
+#ifndef GS_BWDT_PAIRED
+#define GS_BWDT_PAIRED 1   // lane pairs pre-add through shuffles, one panel plane (0: two planes, the round-1 form)
+#endif
 
 namespace bwdt {
 
@@ -60,7 +63,6 @@ constexpr int kBatch = kThreads;   // splats staged per round: thread j stages a
 constexpr int kChunk = GS_BWDT_CHUNK;   // splats per phase-1 / phase-2 round: 8 | 4 (4: half the panel, more CTAs per SM)
 static_assert(kChunk == 8 || kChunk == 4, "phase 2 is written for chunks of 8 or 4 splats");
 constexpr int kRow = 33;           // panel row stride in float4 (32 lanes + 1 pad: conflict-free transposed reads)
-constexpr int kAcc = 13;           // accumulator stride: 6 moments, 4 features, 2 heuristics, 1 pad (odd)
 constexpr float kExpScale = 0.84932180028801904f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -90,14 +92,26 @@ __device__ __forceinline__ float4 load_tail(const unsigned char *q2) {
   return t;
 }
 
-template <int RECW>
+// lane pairs pre-add through shuffles and one panel plane carries everything (see the kernel)
+constexpr bool paired_panel(int F, bool GF) { return GS_BWDT_PAIRED && GF && F <= 3 && kChunk == 8; }
+constexpr int panel_planes(int F, bool GF) { return GF && !paired_panel(F, GF) ? 2 : 1; }
+// accumulator stride (odd: conflict-free).  Two planes: 6 moments, 4 features, 2 heuristics, 1 pad; paired: 6 moments,
+// sum G^2, sum |G dpdf/dmean|, 3 features
+constexpr int acc_stride(int F, bool GF) { return paired_panel(F, GF) ? 11 : 13; }
+// resident CTAs per SM the shared memory allows (37 KB | 38 KB | 55 KB per CTA); the register budget follows
+constexpr int min_blocks(int F, bool GF) {
+  return GS_BWDT_MIN_BLOCKS != 4 ? GS_BWDT_MIN_BLOCKS : paired_panel(F, GF) ? 6 : GF ? 4 : 5;
+}
+
+template <int RECW, int PLANES, int ACC>
 struct Smem {
   // two landing buffers of raster_pack records {tx0, ty0, ux, wx | uy, wy, alpha, f0 | f1, f2, (f3,) depth, mask}
   // (+1: null record that pads the hit lists)
   float4 rec[2][(kBatch + 1) * RECW];
-  float acc[kBatch * kAcc];
-  float4 panel0[kWarps][kChunk * kRow];  // per-warp [splat][lane] scratch: {S, D, sum G^2, sum |G dpdf/dmean|}
-  float4 panel1[kWarps][kChunk * kRow];  //                                 {sum weight dL/dimage[c]}
+  float acc[kBatch * ACC];
+  // per-warp [splat][lane] scratch.  Two planes: {S, D, sum G^2, sum |G dpdf/dmean|} and {sum weight dL/dimage[c]};
+  // one plane: without feature gradients, or what the lane pairs left (paired_panel)
+  float4 panel[PLANES][kWarps][kChunk * kRow];
   // byte offsets (16 RECW j) of the records a warp must visit; entry k lives at index k + 3, so that the eight
   // "next" entries of a chunk (k = h0 + 1 .. h0 + 8) are two aligned 16-byte loads
   alignas(16) unsigned list[kWarps][kBatch + kChunk + 4];
@@ -105,14 +119,26 @@ struct Smem {
 };
 
 template <int F, bool GP, bool GF, bool HEUR, int RECW>
-__global__ void __launch_bounds__(kThreads, GS_BWDT_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, min_blocks(F, GF))
 raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict__ flush_records,
                     const int32_t *__restrict__ ranges, const int32_t *__restrict__ overlap_to_point,
                     const float *__restrict__ image, const float *__restrict__ grad_image, RasterParams<float> P,
                     float *__restrict__ grad_points, float *__restrict__ grad_features,
                     float *__restrict__ heuristic) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<RECW> &sm = *reinterpret_cast<Smem<RECW> *>(smem_raw);
+  using SmemT = Smem<RECW, panel_planes(F, GF), acc_stride(F, GF)>;
+  SmemT &sm = *reinterpret_cast<SmemT *>(smem_raw);
+  constexpr int kAcc = acc_stride(F, GF);
+  // One panel plane instead of two (feature gradients of up to 3 channels, chunks of 8): lanes l and l ^ 16 -- same
+  // column, rows {r, r + 4} and {r + 2, r + 6} -- first add up through 4 shuffles, the lower lane keeping the three
+  // column moments {sum Gp, sum y Gp, sum y^2 Gp} and sum G^2, the upper one sum |G dpdf/dmean| and the 3 feature
+  // sums, so a splat costs the shared-memory data pipe one STS.128 + one LDS.128 per lane instead of two each
+  // (a shuffle is 0.58 cycles of that pipe, an STS.128 / LDS.128 4.04: profiles/r01p_micro.txt).  Without the
+  // feature-gradient plane the kernel ran 1.01 -> 0.82 ms (profiles/r02/r02v_bwd_variants.txt).
+  constexpr bool kPaired = paired_panel(F, GF);
+  // accumulator slots per splat: {M0, Lx, Ly, Lxx, Lxy, Lyy} + features + heuristics
+  constexpr int kSlots = kPaired ? 11 : 12;
+  constexpr int kSlotF = kPaired ? 8 : 6, kSlotH0 = kPaired ? 6 : 10, kSlotH1 = kPaired ? 7 : 11;
   constexpr unsigned kRecBytes = 16u * RECW;
   constexpr int kMaskWord = RECW == 3 ? 11 : 12;
   const unsigned full = 0xffffffffu;
@@ -125,6 +151,10 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
   // pixel centre relative to the tile centre: (tx, ty) = lx (ux, wx) + ly (uy, wy) + (tx0, ty0)
   const float lx = (float)bx - 7.5f, ly0 = (float)by - 7.5f;
   const f32x2 lx2 = pk(lx, lx), lyp = pk(ly0, ly0 + 4.0f);   // the lane's column; the rows of its two pixels
+  // paired mode: the lane's rows enter the y moments here, y Gp0 + (y + 4) Gp1 = y S + 4 D and
+  // y^2 Gp0 + (y + 4)^2 Gp1 = y^2 S + (8 y + 16) D
+  const f32x2 ymom = pk(ly0, ly0 * ly0), dmom = pk(4.0f, fmaf(8.0f, ly0, 16.0f));
+  const bool lower = (lane & 16) == 0;
   const float clamp_max = P.clamp_max, thr = P.thr;
   const float t_min = 1.0f - P.sat;   // a pixel is saturated (backward.py:131) once its transmittance is <= 1 - sat
 
@@ -160,7 +190,7 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
   const float lya = (float)((warp >> 1) * 8 + (kChunk == 8 ? q : (q >> 1))) - 7.5f;   // y of the upper row (other: + 4)
   const int slot_base = kChunk == 8 ? ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0)
                                     : ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0);
-  float4 *panel0 = sm.panel0[warp], *panel1 = sm.panel1[warp];
+  float4 *panel0 = sm.panel[0][warp], *panel1 = sm.panel[panel_planes(F, GF) - 1][warp];
   float g_scalar[2][4];               // dL/dimage of the two pixels as scalars (same registers as gpix2)
 #pragma unroll
   for (int c = 0; c < 4; ++c) { g_scalar[0][c] = 0.f; g_scalar[1][c] = 0.f; }
@@ -190,7 +220,7 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
   }
   int warp_saturated = 0;   // every pixel of this warp's block is saturated (uniform over the warp)
 #pragma unroll
-  for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
+  for (int c = 0; c < kSlots; ++c) sm.acc[tid * kAcc + c] = 0.f;
 
   for (int b = 0; b < nbatches; ++b) {
     const int buf = b & 1;
@@ -289,6 +319,11 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
         // the pixel pair shares its column, so the pair enters the panel pre-summed: S = Gp0 + Gp1 carries the
         // 1, x, x^2 moments and D = Gp1 (the pixel 4 rows down) completes the y moments
         float4 e0 = make_float4(Gp0 + Gp1, Gp1, 0.f, 0.f);
+        if (kPaired) {   // {S, y S + 4 D, y^2 S + (8 y + 16) D, sum G^2}
+          upk(fma2(ymom, pk(e0.x, e0.x), mul2(dmom, pk(Gp1, Gp1))), e0.y, e0.z);
+          e0.w = 0.f;
+        }
+        float heur_g2 = 0.f, heur_k = 0.f;
         if (HEUR) {
           // |G dpdf/dmean|_1 = |Gp| (|tx ux + ty wx| + |tx uy + ty wy|) / k^2  (t and u, w carry one factor k each;
           // the 1 / k^2 is applied once per splat in phase 2)
@@ -296,11 +331,26 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
           upk(fma2(pk(A.z, A.z), tx2, mul2(pk(A.w, A.w), ty2)), dx0, dx1);   // tx ux + ty wx of both pixels
           upk(fma2(pk(B.x, B.x), tx2, mul2(pk(B.y, B.y), ty2)), dy0, dy1);   // tx uy + ty wy
           upk(mul2(pk(fabsf(dx0) + fabsf(dy0), fabsf(dx1) + fabsf(dy1)), Gp2), hk0, hk1);
-          e0.z = fmaf(G0, G0, G1 * G1);
-          e0.w = fabsf(hk0) + fabsf(hk1);
+          heur_g2 = fmaf(G0, G0, G1 * G1);
+          heur_k = fabsf(hk0) + fabsf(hk1);
         }
-        panel0[u * kRow + lane] = e0;
-        if (GF) {
+        if (kPaired) {
+          const float4 mom = make_float4(e0.x, e0.y, e0.z, heur_g2);
+          const float4 pln = make_float4(heur_k, fmaf(w0, g_scalar[0][0], w1 * g_scalar[1][0]),
+                                         F > 1 ? fmaf(w0, g_scalar[0][1], w1 * g_scalar[1][1]) : 0.f,
+                                         F > 2 ? fmaf(w0, g_scalar[0][2], w1 * g_scalar[1][2]) : 0.f);
+          float4 out;
+          out.x = (lower ? mom.x : pln.x) + __shfl_xor_sync(full, lower ? pln.x : mom.x, 16);
+          out.y = (lower ? mom.y : pln.y) + __shfl_xor_sync(full, lower ? pln.y : mom.y, 16);
+          out.z = (lower ? mom.z : pln.z) + __shfl_xor_sync(full, lower ? pln.z : mom.z, 16);
+          out.w = (lower ? mom.w : pln.w) + __shfl_xor_sync(full, lower ? pln.w : mom.w, 16);
+          panel0[u * kRow + lane] = out;
+        } else {
+          e0.z = heur_g2;
+          e0.w = heur_k;
+          panel0[u * kRow + lane] = e0;
+        }
+        if (GF && !kPaired) {
           float4 e1 = make_float4(0.f, 0.f, 0.f, 0.f);
           e1.x = fmaf(w0, g_scalar[0][0], w1 * g_scalar[1][0]);
           if (F > 1) e1.y = fmaf(w0, g_scalar[0][1], w1 * g_scalar[1][1]);
@@ -318,68 +368,116 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
       }
       __syncwarp();
 
-      // ---- phase 2: lane = (splat s, row pair q): walk the 8 lane entries of rows q and q + 4 for one splat ----
-      f32x2 md = pk(0.f, 0.f), sd1 = pk(0.f, 0.f), hh = pk(0.f, 0.f), f01 = pk(0.f, 0.f), f23 = pk(0.f, 0.f);
-      float s2 = 0.f;
-      {
-        const float4 *row0 = panel0 + s * kRow + q * entries, *row1 = panel1 + s * kRow + q * entries;
+      if (kPaired) {
+        // ---- phase 2, one plane: lane = (splat s, role q).  q = 0, 1: the column moments of the even / odd rows of the
+        // block (entries of lanes 8 q .. 8 q + 7); q = 2, 3: the plain sums {|G dpdf/dmean|, features} of the same rows.
+        // Every lane runs the same arithmetic over its 8 entries (entry i = column i of the block); the roles differ in
+        // what the sums mean.
+        f32x2 a01 = pk(0.f, 0.f), a23 = pk(0.f, 0.f), i01 = pk(0.f, 0.f);
+        float ii0 = 0.f;
+        {
+          const float4 *row = panel0 + s * kRow + q * 8;
 #pragma unroll
-        for (int i = 0; i < entries; ++i) {
-          const float4 e0 = row0[i];
-          const f32x2 sd = pk(e0.x, e0.y);
-          md = add2(md, sd);                                         // (sum S, sum D)
-          sd1 = fma2(sd, pk((float)i, (float)i), sd1);               // (sum i S, sum i D)
-          s2 = fmaf(e0.x, (float)(i * i), s2);
-          if (HEUR) hh = add2(hh, pk(e0.z, e0.w));
-          if (GF) {
-            const float4 e1 = row1[i];
-            f01 = add2(f01, pk(e1.x, e1.y));
-            if (F > 2) f23 = add2(f23, pk(e1.z, e1.w));
+          for (int i = 0; i < 8; ++i) {
+            const float4 e = row[i];
+            const f32x2 xy = pk(e.x, e.y);
+            a01 = add2(a01, xy);                                       // (sum M0, sum My)      | (sum hk, sum f0)
+            a23 = add2(a23, pk(e.z, e.w));                             // (sum Myy, sum G^2)    | (sum f1, sum f2)
+            i01 = fma2(xy, pk((float)i, (float)i), i01);               // (sum i M0, sum i My)
+            ii0 = fmaf(e.x, (float)(i * i), ii0);                      // sum i^2 M0
           }
         }
-      }
-      float m0, d0, s1, d1, f0, f1, f2, f3, hh0, hh1;
-      upk(md, m0, d0);
-      upk(sd1, s1, d1);
-      upk(f01, f0, f1);
-      upk(f23, f2, f3);
-      upk(hh, hh0, hh1);
-      hh1 *= 1.0f / (kExpScale * kExpScale);
-      // lane-entry sums -> tile-centred moments (x = bx0 + i; y = lya for S - D, lya + 4 for D)
-      const float Lx = fmaf(bx0, m0, s1);
-      const float Lxx = fmaf(bx0, fmaf(bx0, m0, 2.0f * s1), s2);
-      const float Ly = fmaf(lya, m0, 4.0f * d0);
-      const float Lxy = fmaf(lya, Lx, 4.0f * fmaf(bx0, d0, d1));
-      const float Lyy = fmaf(lya * lya, m0, fmaf(8.0f, lya, 16.0f) * d0);
-      float v[12] = {m0, Lx, Ly, Lxx, Lxy, Lyy, f0, f1, f2, f3, hh0, hh1};
-      // sum over the 4 row pairs with a 2-stage transposed butterfly: 6 + 3 shuffles, 3 finished sums per lane
-      {
-        const bool up = (lane & 16) != 0;
+        float m0, my, s1, s1y, z0, z1;
+        upk(a01, m0, my);
+        upk(i01, s1, s1y);
+        upk(a23, z0, z1);
+        // column sums -> tile-centred moments (x = bx0 + i; the rows entered tile-centred in phase 1)
+        const float Lx = fmaf(bx0, m0, s1);
+        const float Lxx = fmaf(bx0, fmaf(bx0, m0, 2.0f * s1), ii0);
+        const float Lxy = fmaf(bx0, my, s1y);
+        const bool moments = q < 2;
+        // moment role: {M0, Lx, Ly, Lxx | Lxy, Lyy, sum G^2, -};  plain role: {hk, f0, f1, f2 | -, -, -, -}
+        float v[8] = {m0, moments ? Lx : my, moments ? my : z0, moments ? Lxx : z1, Lxy, z0, z1, 0.f};
+        {   // sum over the two row parities: q = 0 and 2 end with v[0..3], q = 1 with v[4..7] (q = 3: nothing)
+          const bool up = (lane & 8) != 0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          float send = up ? v[i] : v[i + 6];
-          float keep = up ? v[i + 6] : v[i];
-          v[i] = keep + __shfl_xor_sync(full, send, 16);
+          for (int i = 0; i < 4; ++i) {
+            float send = up ? v[i] : v[i + 4];
+            float keep = up ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(full, send, 8);
+          }
         }
-      }
-      {
-        const bool up = (lane & 8) != 0;
+        if (h0 + s < nhit && q < 3) {
+          // slots 0..3 | 4..6 (the lane's fourth sum is an exact zero) | 7..10
+          float *dst = sm.acc + (sm.list[warp][3 + h0 + s] / kRecBytes) * kAcc + (q == 2 ? 7 : 4 * q);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          float send = up ? v[i] : v[i + 3];
-          float keep = up ? v[i + 3] : v[i];
-          v[i] = keep + __shfl_xor_sync(full, send, 8);
+          for (int i = 0; i < 4; ++i)
+            if (v[i] != 0.f) atomicAdd(dst + i, v[i]);
         }
-      }
-      if (kChunk == 4) {   // third stage: the two halves of a row pair (both lanes end with the sums; one adds them)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) v[i] += __shfl_xor_sync(full, v[i], 4);
-      }
-      if (h0 + s < nhit && (kChunk == 8 || (lane & 4) == 0)) {
-        float *dst = sm.acc + (sm.list[warp][3 + h0 + s] / kRecBytes) * kAcc + slot_base;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-          if (v[i] != 0.f) atomicAdd(dst + i, v[i]);
+      } else {
+        // ---- phase 2: lane = (splat s, row pair q): walk the 8 lane entries of rows q and q + 4 for one splat ----
+        f32x2 md = pk(0.f, 0.f), sd1 = pk(0.f, 0.f), hh = pk(0.f, 0.f), f01 = pk(0.f, 0.f), f23 = pk(0.f, 0.f);
+        float s2 = 0.f;
+        {
+          const float4 *row0 = panel0 + s * kRow + q * entries, *row1 = panel1 + s * kRow + q * entries;
+  #pragma unroll
+          for (int i = 0; i < entries; ++i) {
+            const float4 e0 = row0[i];
+            const f32x2 sd = pk(e0.x, e0.y);
+            md = add2(md, sd);                                         // (sum S, sum D)
+            sd1 = fma2(sd, pk((float)i, (float)i), sd1);               // (sum i S, sum i D)
+            s2 = fmaf(e0.x, (float)(i * i), s2);
+            if (HEUR) hh = add2(hh, pk(e0.z, e0.w));
+            if (GF) {
+              const float4 e1 = row1[i];
+              f01 = add2(f01, pk(e1.x, e1.y));
+              if (F > 2) f23 = add2(f23, pk(e1.z, e1.w));
+            }
+          }
+        }
+        float m0, d0, s1, d1, f0, f1, f2, f3, hh0, hh1;
+        upk(md, m0, d0);
+        upk(sd1, s1, d1);
+        upk(f01, f0, f1);
+        upk(f23, f2, f3);
+        upk(hh, hh0, hh1);
+        hh1 *= 1.0f / (kExpScale * kExpScale);
+        // lane-entry sums -> tile-centred moments (x = bx0 + i; y = lya for S - D, lya + 4 for D)
+        const float Lx = fmaf(bx0, m0, s1);
+        const float Lxx = fmaf(bx0, fmaf(bx0, m0, 2.0f * s1), s2);
+        const float Ly = fmaf(lya, m0, 4.0f * d0);
+        const float Lxy = fmaf(lya, Lx, 4.0f * fmaf(bx0, d0, d1));
+        const float Lyy = fmaf(lya * lya, m0, fmaf(8.0f, lya, 16.0f) * d0);
+        float v[12] = {m0, Lx, Ly, Lxx, Lxy, Lyy, f0, f1, f2, f3, hh0, hh1};
+        // sum over the 4 row pairs with a 2-stage transposed butterfly: 6 + 3 shuffles, 3 finished sums per lane
+        {
+          const bool up = (lane & 16) != 0;
+  #pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            float send = up ? v[i] : v[i + 6];
+            float keep = up ? v[i + 6] : v[i];
+            v[i] = keep + __shfl_xor_sync(full, send, 16);
+          }
+        }
+        {
+          const bool up = (lane & 8) != 0;
+  #pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            float send = up ? v[i] : v[i + 3];
+            float keep = up ? v[i + 3] : v[i];
+            v[i] = keep + __shfl_xor_sync(full, send, 8);
+          }
+        }
+        if (kChunk == 4) {   // third stage: the two halves of a row pair (both lanes end with the sums; one adds them)
+  #pragma unroll
+          for (int i = 0; i < 3; ++i) v[i] += __shfl_xor_sync(full, v[i], 4);
+        }
+        if (h0 + s < nhit && (kChunk == 8 || (lane & 4) == 0)) {
+          float *dst = sm.acc + (sm.list[warp][3 + h0 + s] / kRecBytes) * kAcc + slot_base;
+  #pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (v[i] != 0.f) atomicAdd(dst + i, v[i]);
+        }
       }
       __syncwarp();
       if (__all_sync(full, trans[0] <= t_min && trans[1] <= t_min)) break;
@@ -389,13 +487,13 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
     // ---- flush: one thread per splat of the batch ----
     __syncthreads();
     if (tid < nb) {
-      float S[12];
+      float S[kSlots];
       bool any = false;
 #pragma unroll
-      for (int c = 0; c < 12; ++c) { S[c] = sm.acc[tid * kAcc + c]; any |= (S[c] != 0.f); }
+      for (int c = 0; c < kSlots; ++c) { S[c] = sm.acc[tid * kAcc + c]; any |= (S[c] != 0.f); }
       if (any) {
 #pragma unroll
-        for (int c = 0; c < 12; ++c) sm.acc[tid * kAcc + c] = 0.f;
+        for (int c = 0; c < kSlots; ++c) sm.acc[tid * kAcc + c] = 0.f;
         const int my_id = __ldg(overlap_to_point + base + tid);
         if (GP) {
           // shift the tile-centred moments to the splat mean: d = l + c
@@ -424,11 +522,13 @@ raster_bwd_t_kernel(const float4 *__restrict__ records, const float4 *__restrict
         if (GF) {
           float *gf = grad_features + (int64_t)F * my_id;
 #pragma unroll
-          for (int c = 0; c < F; ++c) atomicAdd(gf + c, S[6 + c]);
+          for (int c = 0; c < F; ++c) atomicAdd(gf + c, S[kSlotF + c]);
         }
         if (HEUR) {
-          atomicAdd(heuristic + 2 * (int64_t)my_id, S[10]);
-          atomicAdd(heuristic + 2 * (int64_t)my_id + 1, S[11]);
+          // paired mode leaves the 1 / k^2 of |G dpdf/dmean| (t and u, w carry one factor k each) to this point
+          const float hk = kPaired ? S[kSlotH1] * (1.0f / (kExpScale * kExpScale)) : S[kSlotH1];
+          atomicAdd(heuristic + 2 * (int64_t)my_id, S[kSlotH0]);
+          atomicAdd(heuristic + 2 * (int64_t)my_id + 1, hk);
         }
       }
     }
@@ -446,12 +546,13 @@ int launch_bwd_transpose(const float4 *records, const float4 *flush_records, con
 #ifndef GS_BWDT_EXTRA_SMEM
 #define GS_BWDT_EXTRA_SMEM 0   // profiling aid: extra dynamic shared memory per CTA lowers the residency
 #endif
-  const size_t smem = sizeof(bwdt::Smem<RECW>) + GS_BWDT_EXTRA_SMEM;
   int dev = 0;
   GS_CUDA(cudaGetDevice(&dev));
 #define GS_BWDT(GP_, GF_, HE_)                                                                                  \
   do {                                                                                                          \
     auto kern = bwdt::raster_bwd_t_kernel<F, GP_, GF_, HE_, RECW>;                                              \
+    const size_t smem = sizeof(bwdt::Smem<RECW, bwdt::panel_planes(F, GF_), bwdt::acc_stride(F, GF_)>) +        \
+                        GS_BWDT_EXTRA_SMEM;                                                                     \
     /* the attribute is per device (and per kernel instantiation): one bit per device, set once each */         \
     static std::atomic<uint64_t> configured{0};                                                                 \
     const uint64_t dev_bit = 1ull << (dev & 63);                                                                \
