@@ -34,4 +34,5 @@ for _ in range(4):
   b.record()
   torch.cuda.synchronize()
   times.append(a.elapsed_time(b) / (steps // 4))
-print(f"variant '{os.environ.get('GS_BUILD_VARIANT', '')}': {min(times):.4f} ms/step (quarters: {' '.join(f'{t:.4f}' for t in times)})")
+switches = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("GS_") and k != "GS_BUILD_VARIANT")
+print(f"variant '{os.environ.get('GS_BUILD_VARIANT', '')}' {switches}: {min(times):.4f} ms/step (quarters: {' '.join(f'{t:.4f}' for t in times)})")

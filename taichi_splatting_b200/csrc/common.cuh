@@ -11,6 +11,19 @@ namespace gs {
 void set_error(const char *fmt, ...);
 void *stream_workspace(cudaStream_t stream, size_t bytes);   // api.cu: library-owned scratch per (device, stream)
 
+// How a count (V, K) reaches the host.  Public entry points: cudaMemcpyAsync into the caller's host word, valid after a
+// stream synchronisation.  Whole-frame drivers (render.cu): the words are MAPPED pinned memory, the producing kernel
+// stores the count there itself and the host polls for it -- no copy-engine operation on the stream and no blocking
+// synchronisation (together ~25 us of idle GPU per count in the step timeline, profiles/r02/r02ac_timeline.txt).
+constexpr int32_t kWordPending = INT32_MIN;   // the host writes this before the producer is enqueued
+int project_compact_f32_mapped(const float *position, const float *log_scaling, const float *rotation,
+                               const float *alpha_logit, const float *T, const float *proj, int64_t n, int32_t width,
+                               int32_t height, double near_plane, double far_plane, double blur_cov, double clamp_margin,
+                               double alpha_threshold, void *workspace, size_t workspace_bytes, float *points,
+                               float *depth, int64_t *indexes, float *ndc, int32_t *mapped_word, cudaStream_t stream);
+int tile_scan_mapped(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
+                     int32_t *mapped_word, cudaStream_t stream);
+
 #define GS_CHECK_ARG(cond, ...)                 \
   do {                                          \
     if (!(cond)) {                              \

@@ -345,11 +345,15 @@ tile_bin_sort_kernel(const uint64_t *__restrict__ keys, const int32_t *__restric
 }
 
 __global__ void finish_scan_kernel(const int32_t *__restrict__ counts, int32_t *__restrict__ cum, int64_t v,
-                                   int32_t *__restrict__ total_dev) {
+                                   int32_t *__restrict__ total_dev, volatile int32_t *total_mapped) {
   // cum[0..v-1] holds the exclusive scan; complete entry v (cuda_lib/full_cumsum.cu:6-10)
   int32_t t = cum[v - 1] + counts[v - 1];
   cum[v] = t;
   *total_dev = t;
+  if (total_mapped != nullptr) {   // mapped pinned host word the host polls (common.cuh: kWordPending)
+    *total_mapped = t;
+    __threadfence_system();
+  }
 }
 
 template <typename key_t>
@@ -387,9 +391,9 @@ extern "C" int gs_tile_scan_workspace_bytes(int64_t v, size_t *bytes) {
   return GS_OK;
 }
 
-extern "C" int gs_tile_scan(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
-                            int32_t *total_host, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+namespace gs {
+static int tile_scan_impl(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
+                          int32_t *total_host, cudaStream_t stream, bool mapped) {
   GS_CHECK_ARG(total_host != nullptr, "tile_scan: total_host is NULL");
   GS_CHECK_ARG(v >= 0 && v < (int64_t(1) << 31), "tile_scan: v out of range");
   if (v == 0) {
@@ -407,10 +411,21 @@ extern "C" int gs_tile_scan(const int32_t *counts, int64_t v, int32_t *cum, void
   void *temp = (char *)workspace + 256;
   size_t temp_bytes = workspace_bytes - 256;
   GS_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, cum, (int)v, stream));
-  gs::finish_scan_kernel<<<1, 1, 0, stream>>>(counts, cum, v, total_dev);
+  gs::finish_scan_kernel<<<1, 1, 0, stream>>>(counts, cum, v, total_dev, mapped ? total_host : nullptr);
   GS_LAUNCH_CHECK();
-  GS_CUDA(cudaMemcpyAsync(total_host, total_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  if (!mapped) GS_CUDA(cudaMemcpyAsync(total_host, total_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   return GS_OK;
+}
+
+int tile_scan_mapped(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
+                     int32_t *mapped_word, cudaStream_t stream) {
+  return tile_scan_impl(counts, v, cum, workspace, workspace_bytes, mapped_word, stream, true);
+}
+}  // namespace gs
+
+extern "C" int gs_tile_scan(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
+                            int32_t *total_host, void *stream_) {
+  return gs::tile_scan_impl(counts, v, cum, workspace, workspace_bytes, total_host, (cudaStream_t)stream_, false);
 }
 
 extern "C" int gs_tile_emit_keys(const float *gaussians, const float *depths, const int32_t *cum, int64_t v,

@@ -285,12 +285,17 @@ size_t project_compact_temp_bytes(int64_t n) {
   return temp;
 }
 
+__global__ void publish_word_kernel(const int32_t *__restrict__ dev, volatile int32_t *mapped) {
+  *mapped = *dev;
+  __threadfence_system();
+}
+
 template <typename real>
 int project_compact(const real *position, const real *log_scaling, const real *rotation, const real *alpha_logit,
                     const real *T, const real *proj, int64_t n, int32_t width, int32_t height, double near_plane,
                     double far_plane, double blur_cov, double clamp_margin, double alpha_threshold, void *workspace,
                     size_t workspace_bytes, real *points, real *depth, int64_t *indexes, real *ndc,
-                    int32_t *num_visible_host, cudaStream_t stream) {
+                    int32_t *num_visible_host, cudaStream_t stream, bool mapped = false) {
   GS_CHECK_ARG(n >= 0 && n < (int64_t(1) << 31), "project: n=%lld out of range", (long long)n);
   GS_CHECK_ARG(num_visible_host != nullptr, "project: num_visible_host is NULL");
   if (n == 0) {
@@ -309,8 +314,23 @@ int project_compact(const real *position, const real *log_scaling, const real *r
                                           far_plane, blur_cov, clamp_margin, alpha_threshold));
   ProjOutIt<real> out{points, depth, ndc, indexes, 0};
   GS_CUDA(cub::DeviceSelect::If(temp, temp_bytes, in, out, num_dev, (int)n, ProjVisible<real>(), stream));
-  GS_CUDA(cudaMemcpyAsync(num_visible_host, num_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  if (mapped) {
+    publish_word_kernel<<<1, 1, 0, stream>>>(num_dev, num_visible_host);
+    GS_LAUNCH_CHECK();
+  } else {
+    GS_CUDA(cudaMemcpyAsync(num_visible_host, num_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  }
   return GS_OK;
+}
+
+int project_compact_f32_mapped(const float *position, const float *log_scaling, const float *rotation,
+                               const float *alpha_logit, const float *T, const float *proj, int64_t n, int32_t width,
+                               int32_t height, double near_plane, double far_plane, double blur_cov, double clamp_margin,
+                               double alpha_threshold, void *workspace, size_t workspace_bytes, float *points,
+                               float *depth, int64_t *indexes, float *ndc, int32_t *mapped_word, cudaStream_t stream) {
+  return project_compact<float>(position, log_scaling, rotation, alpha_logit, T, proj, n, width, height, near_plane,
+                                far_plane, blur_cov, clamp_margin, alpha_threshold, workspace, workspace_bytes, points,
+                                depth, indexes, ndc, mapped_word, stream, true);
 }
 
 template <typename real, int N>

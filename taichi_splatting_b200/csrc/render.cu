@@ -54,7 +54,7 @@ static DeviceAux *device_aux(cudaStream_t stream) {
     cudaEventCreateWithFlags(&a.raster_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&a.fills_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&a.bwd_join, cudaEventDisableTiming);
-    if (cudaHostAlloc((void **)&a.host_words, 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc((void **)&a.host_words, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
   }
   return &a;
 }
@@ -128,6 +128,37 @@ extern "C" int gs_render_stage_a_f32(const gs_render_args *a, int64_t *v_out, in
   return rc;
 }
 
+// Waits for a count the device stores into mapped pinned memory (common.cuh: kWordPending).  The host spins on the
+// word; every few thousand polls it asks the stream whether it failed or drained without publishing, so a faulting
+// kernel ends in an error, not in a hang.
+static int wait_mapped_word(volatile int32_t *word, cudaStream_t stream, const char *what, int64_t *out) {
+  for (uint32_t spin = 1;; ++spin) {
+    const int32_t value = *word;
+    if (value != gs::kWordPending) { *out = value; return GS_OK; }
+    if ((spin & 0xfffu) == 0) {
+      const cudaError_t q = cudaStreamQuery(stream);
+      if (q == cudaSuccess) {   // everything enqueued has finished: the store is visible now or never
+        const int32_t last = *word;
+        if (last != gs::kWordPending) { *out = last; return GS_OK; }
+        gs::set_error("%s: the stream drained without publishing the count", what);
+        return GS_ERR_CUDA;
+      }
+      if (q != cudaErrorNotReady) {
+        gs::set_error("%s: %s", what, cudaGetErrorString(q));
+        return GS_ERR_CUDA;
+      }
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
+static bool use_mapped_words() {
+  static const bool on = [] { const char *e = getenv("GS_MAPPED_COUNTS"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_out, int64_t *max_per_tile_out,
                             cudaStream_t stream, DeviceAux *aux, cudaStream_t side) {
   const gs_raster_config &c = a->config;
@@ -135,13 +166,25 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
   *v_out = 0; *k_out = 0; *max_per_tile_out = 0;
 
   // ---- projection: single-pass project + cull + ordered compaction (+ ndc depth) -> V ----
-  GS_TRY(gs_project_compact_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
-                                a->projection, n, a->width, a->height, a->near_plane, a->far_plane, a->blur_cov,
-                                a->clamp_margin, c.alpha_threshold, a->ws_project, a->ws_project_bytes, a->points,
-                                a->depths, a->indexes, a->ndc, &aux->host_words[0], stream));
-  if (a->use_sh) GS_TRY(gs_camera_position_f32(a->T_camera_world, a->camera_pos, stream));
-  GS_CUDA(cudaStreamSynchronize(stream));
-  const int64_t v = aux->host_words[0];
+  const bool mapped = use_mapped_words();
+  int64_t v = 0;
+  if (mapped) {
+    aux->host_words[0] = kWordPending;
+    GS_TRY(project_compact_f32_mapped(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
+                                      a->projection, n, a->width, a->height, a->near_plane, a->far_plane, a->blur_cov,
+                                      a->clamp_margin, c.alpha_threshold, a->ws_project, a->ws_project_bytes, a->points,
+                                      a->depths, a->indexes, a->ndc, &aux->host_words[0], stream));
+    if (a->use_sh) GS_TRY(gs_camera_position_f32(a->T_camera_world, a->camera_pos, stream));
+    GS_TRY(wait_mapped_word(&aux->host_words[0], stream, "render_stage_a (V)", &v));
+  } else {
+    GS_TRY(gs_project_compact_f32(a->position, a->log_scaling, a->rotation, a->alpha_logit, a->T_camera_world,
+                                  a->projection, n, a->width, a->height, a->near_plane, a->far_plane, a->blur_cov,
+                                  a->clamp_margin, c.alpha_threshold, a->ws_project, a->ws_project_bytes, a->points,
+                                  a->depths, a->indexes, a->ndc, &aux->host_words[0], stream));
+    if (a->use_sh) GS_TRY(gs_camera_position_f32(a->T_camera_world, a->camera_pos, stream));
+    GS_CUDA(cudaStreamSynchronize(stream));
+    v = aux->host_words[0];
+  }
   *v_out = v;
 
   // ---- auxiliary stream: features, zero fills, raster digest (none of it feeds the mapper) ----
@@ -183,6 +226,14 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
                                       a->counts, a->hits, stream));
   else
     GS_TRY(gs_tile_count_ordered(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->counts, stream));
+  if (mapped) {
+    int64_t k = 0;
+    aux->host_words[1] = kWordPending;
+    GS_TRY(tile_scan_mapped(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[1], stream));
+    GS_TRY(wait_mapped_word(&aux->host_words[1], stream, "render_stage_a (K)", &k));
+    *k_out = v > 0 ? k : 0;
+    return GS_OK;
+  }
   GS_TRY(gs_tile_scan(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[1], stream));
   GS_CUDA(cudaStreamSynchronize(stream));
   *k_out = v > 0 ? (int64_t)aux->host_words[1] : 0;

@@ -25,9 +25,11 @@ from ..optim import SparseAdam, VisibilityAwareLaProp
 from ..rasterizer import rasterize
 
 
-def synthetic_image(w, h, device):
+def synthetic_image(w, h, device, detail=1.0):
+  """Smooth colour waves; `detail` scales their spatial frequency (more detail needs more Gaussians)."""
   ys, xs = torch.meshgrid(torch.linspace(0, 1, h, device=device), torch.linspace(0, 1, w, device=device), indexing="ij")
-  return torch.stack([0.5 + 0.5 * torch.sin(6.28 * xs), ys, 0.5 + 0.5 * torch.cos(9.4 * xs * ys)], dim=-1).contiguous()
+  return torch.stack([0.5 + 0.5 * torch.sin(6.28 * detail * xs), 0.5 + 0.5 * torch.sin(3.14 * (2 * detail - 1) * ys) if detail != 1.0 else ys,
+                      0.5 + 0.5 * torch.cos(9.4 * detail * detail * xs * ys)], dim=-1).contiguous()
 
 
 def psnr(a, b):
@@ -39,6 +41,7 @@ def main(argv=None):
   ap.add_argument("--image", type=str, default=None, help="optional image file (needs cv2); default: synthetic")
   ap.add_argument("--n", type=int, default=2000)
   ap.add_argument("--size", type=str, default="256,256")
+  ap.add_argument("--detail", type=float, default=1.0, help="spatial frequency of the synthetic target")
   ap.add_argument("--iters", type=int, default=200)
   ap.add_argument("--lr", type=float, default=0.02)
   ap.add_argument("--tile_size", type=int, default=16)
@@ -57,7 +60,7 @@ def main(argv=None):
     ref_image = (torch.from_numpy(img).to(torch.float32) / 255).to(device)
   else:
     w, h = map(int, args.size.split(","))
-    ref_image = synthetic_image(w, h, device)
+    ref_image = synthetic_image(w, h, device, args.detail)
   h, w = ref_image.shape[:2]
 
   g = random_2d_gaussians(args.n, (w, h), alpha_range=(0.5, 1.0), scale_factor=0.5, seed=0).to(device)

@@ -936,13 +936,17 @@ def test_benchmark_clis_run(ts, capsys):
 
 
 def test_fit_image_with_densification_beats_fixed_cloud(ts):
-  """N4: the image-fitting loop with heuristics-driven split / prune (600 -> 2400 points) ends above the same loop on
-  the fixed 600-point cloud, the cloud reaches its target size, and the optimiser's per-point state follows the rows."""
+  """N4: the image-fitting loop with heuristics-driven split / prune (150 -> 1500 points) ends well above the same loop
+  on the fixed 150-point cloud, the cloud reaches its target size, and the optimiser's per-point state follows the
+  rows.  The target is detailed enough that 150 points underfit it: measured margins +10.7 .. +11.1 dB over repeated
+  runs (profiles/r02/r02ae_densify_margin.txt; the float atomics of the raster backward make runs differ slightly --
+  on the smooth default target both loops saturate near 52 dB and the margin is only 2 .. 3 dB)."""
   from taichi_splatting_b200.examples import fit_image_gaussians as ex
   from taichi_splatting_b200.misc import densify
-  fixed = ex.main(["--n", "600", "--iters", "240", "--size", "192,160"])
-  grown = ex.main(["--n", "600", "--iters", "240", "--size", "192,160", "--target", "2400", "--epoch", "40"])
-  assert grown > fixed + 1.0, (fixed, grown)
+  common = ["--n", "150", "--iters", "300", "--size", "192,160", "--detail", "3"]
+  fixed = ex.main(common)
+  grown = ex.main(common + ["--target", "1500", "--epoch", "50"])
+  assert grown > fixed + 5.0, (fixed, grown)
   # masks: disjoint, sized to reach the target
   torch.manual_seed(0)
   cost, score = torch.rand(1000, device=DEV), torch.rand(1000, device=DEV)
