@@ -222,7 +222,9 @@ int gs_tile_emit_ordered(const float *gaussians, const int32_t *order, const int
  * as 4 x u16 + a 64-bit mask of the accepted tiles in enumeration order; spans over 64 tiles are marked and
  * re-queried), and the emit kernel walks the set bits instead of repeating the query.  hits: (v) x 16 bytes.
  * tile_lo / tile_hi: a tile-sharded multi-GPU rank keeps only the overlaps of its own contiguous tile-id range, so its
- * sort, pack and raster kernels see K / world overlaps. */
+ * sort, pack and raster kernels see K / world overlaps.  gs_tile_count_ordered_hits with order == NULL counts
+ * Gaussian r itself (counts / hits at the Gaussians' own indices); the whole-frame driver runs that form beside the
+ * depth sort and scans / emits through the order afterwards. */
 int gs_tile_count_ordered_hits(const float *gaussians, const int32_t *order, int64_t v, int32_t width_padded,
                                int32_t height_padded, int32_t tile_size, double alpha_threshold,
                                int32_t tile_lo, int32_t tile_hi /* keep tiles [lo, hi) only; (0, 0): all */,

@@ -7,6 +7,8 @@
 // obtained through fp64 -- the same recipe as oracle/gs_oracle.c.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "common.cuh"
 
@@ -166,7 +168,8 @@ tile_count_hits_kernel(const float *__restrict__ gaussians, const int32_t *__res
                        ulonglong2 *__restrict__ hits) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= v) return;
-  ObbQuery q = obb_grid_query(gaussians + 7 * (int64_t)order[r], w_pad, h_pad, ts, thr);
+  // order == NULL: Gaussian r itself (counts / hits then sit at the Gaussian's own index, not at its depth rank)
+  ObbQuery q = obb_grid_query(gaussians + 7 * (int64_t)(order != nullptr ? order[r] : (int32_t)r), w_pad, h_pad, ts, thr);
   int c = 0;
   unsigned long long mask = 0ull;
   const bool small = q.spanx * q.spany <= 64;
@@ -187,6 +190,7 @@ tile_count_hits_kernel(const float *__restrict__ gaussians, const int32_t *__res
   hits[r] = make_ulonglong2(box, mask);
 }
 
+template <bool HITS_BY_POINT>   // hit records indexed by Gaussian (count ran before / beside the depth sort) | by depth rank
 __global__ void __launch_bounds__(128)
 tile_emit_hits_kernel(const float *__restrict__ gaussians, const int32_t *__restrict__ order,
                       const int32_t *__restrict__ cum, const ulonglong2 *__restrict__ hits, int64_t v, int w_pad,
@@ -195,7 +199,7 @@ tile_emit_hits_kernel(const float *__restrict__ gaussians, const int32_t *__rest
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= v) return;
   const int32_t i = order[r];
-  const ulonglong2 h = hits[r];
+  const ulonglong2 h = hits[HITS_BY_POINT ? (int64_t)i : r];
   const int tiles_wide = w_pad / ts;
   int64_t k = cum[r];
   const int minx = (int)(h.x & 0xffff), miny = (int)((h.x >> 16) & 0xffff);
@@ -344,10 +348,18 @@ tile_bin_sort_kernel(const uint64_t *__restrict__ keys, const int32_t *__restric
   for (int i = tid; i < n; i += THREADS) overlap_to_point[start + i] = (int32_t)(uint32_t)sk[i];
 }
 
-__global__ void finish_scan_kernel(const int32_t *__restrict__ counts, int32_t *__restrict__ cum, int64_t v,
-                                   int32_t *__restrict__ total_dev, volatile int32_t *total_mapped) {
+// counts[order[i]]: the scan runs over the depth order while the counts sit at the Gaussians' own indices
+struct GatherCount {
+  const int32_t *counts, *order;
+  __host__ __device__ __forceinline__ int32_t operator()(int i) const { return counts[order[i]]; }
+};
+using GatherCountIt = cub::TransformInputIterator<int32_t, GatherCount, cub::CountingInputIterator<int>>;
+
+__global__ void finish_scan_kernel(const int32_t *__restrict__ counts, const int32_t *__restrict__ order,
+                                   int32_t *__restrict__ cum, int64_t v, int32_t *__restrict__ total_dev,
+                                   volatile int32_t *total_mapped) {
   // cum[0..v-1] holds the exclusive scan; complete entry v (cuda_lib/full_cumsum.cu:6-10)
-  int32_t t = cum[v - 1] + counts[v - 1];
+  int32_t t = cum[v - 1] + counts[order != nullptr ? order[v - 1] : v - 1];
   cum[v] = t;
   *total_dev = t;
   if (total_mapped != nullptr) {   // mapped pinned host word the host polls (common.cuh: kWordPending)
@@ -393,7 +405,7 @@ extern "C" int gs_tile_scan_workspace_bytes(int64_t v, size_t *bytes) {
 
 namespace gs {
 static int tile_scan_impl(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
-                          int32_t *total_host, cudaStream_t stream, bool mapped) {
+                          int32_t *total_host, cudaStream_t stream, bool mapped, const int32_t *order = nullptr) {
   GS_CHECK_ARG(total_host != nullptr, "tile_scan: total_host is NULL");
   GS_CHECK_ARG(v >= 0 && v < (int64_t(1) << 31), "tile_scan: v out of range");
   if (v == 0) {
@@ -410,16 +422,41 @@ static int tile_scan_impl(const int32_t *counts, int64_t v, int32_t *cum, void *
   int32_t *total_dev = (int32_t *)workspace;
   void *temp = (char *)workspace + 256;
   size_t temp_bytes = workspace_bytes - 256;
-  GS_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, cum, (int)v, stream));
-  gs::finish_scan_kernel<<<1, 1, 0, stream>>>(counts, cum, v, total_dev, mapped ? total_host : nullptr);
+  if (order != nullptr) {
+    GatherCountIt in(cub::CountingInputIterator<int>(0), GatherCount{counts, order});
+    size_t gather_need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, gather_need, in, cum, (int)v);
+    if (gather_need > temp_bytes) {
+      gs::set_error("tile_scan: workspace too small for the gathered scan (%zu < %zu)", temp_bytes, gather_need);
+      return GS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    GS_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, cum, (int)v, stream));
+  } else {
+    GS_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, cum, (int)v, stream));
+  }
+  gs::finish_scan_kernel<<<1, 1, 0, stream>>>(counts, order, cum, v, total_dev, mapped ? total_host : nullptr);
   GS_LAUNCH_CHECK();
   if (!mapped) GS_CUDA(cudaMemcpyAsync(total_host, total_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   return GS_OK;
 }
 
 int tile_scan_mapped(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
-                     int32_t *mapped_word, cudaStream_t stream) {
-  return tile_scan_impl(counts, v, cum, workspace, workspace_bytes, mapped_word, stream, true);
+                     int32_t *mapped_word, cudaStream_t stream, const int32_t *order) {
+  return tile_scan_impl(counts, v, cum, workspace, workspace_bytes, mapped_word, stream, true, order);
+}
+
+int tile_emit_hits_by_point(const float *gaussians, const int32_t *order, const int32_t *cum, const void *hits,
+                            int64_t v, int32_t w_pad, int32_t h_pad, int32_t ts, double alpha_threshold,
+                            int32_t tile_lo, int32_t tile_hi, uint32_t *tile_keys, int32_t *overlap_to_point,
+                            cudaStream_t stream) {
+  if (tile_lo == 0 && tile_hi == 0) tile_hi = 0x7fffffff;
+  GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_emit: image not padded to tile size");
+  if (v == 0) return GS_OK;
+  tile_emit_hits_kernel<true><<<(unsigned)ceil_div(v, 128), 128, 0, stream>>>(
+      gaussians, order, cum, reinterpret_cast<const ulonglong2 *>(hits), v, w_pad, h_pad, ts, (float)alpha_threshold,
+      tile_lo, tile_hi, tile_keys, overlap_to_point);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
 }
 }  // namespace gs
 
@@ -573,7 +610,7 @@ extern "C" int gs_tile_emit_hits(const float *gaussians, const int32_t *order, c
   if (tile_lo == 0 && tile_hi == 0) tile_hi = 0x7fffffff;
   GS_CHECK_ARG(ts > 0 && w_pad % ts == 0 && h_pad % ts == 0, "tile_emit: image not padded to tile size");
   if (v == 0) return GS_OK;
-  gs::tile_emit_hits_kernel<<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
+  gs::tile_emit_hits_kernel<false><<<(unsigned)gs::ceil_div(v, 128), 128, 0, (cudaStream_t)stream>>>(
       gaussians, order, cum, reinterpret_cast<const ulonglong2 *>(hits), v, w_pad, h_pad, ts, (float)alpha_threshold,
       tile_lo, tile_hi, tile_keys, overlap_to_point);
   GS_LAUNCH_CHECK();

@@ -19,6 +19,7 @@ namespace gs {
 struct DeviceAux {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t fence = nullptr, side_done = nullptr, raster_done = nullptr, fills_done = nullptr, bwd_join = nullptr;
+  cudaEvent_t count_done = nullptr;
   int32_t *host_words = nullptr;   // pinned: [0] V, [1] K, [2] largest tile population (binned ordering), [4] K (fallback)
   // The events, the side stream and the pinned words are shared by every frame on this device, so the whole-frame
   // drivers serialise on this lock: two host threads (or two streams) rendering on one device take turns instead of
@@ -54,6 +55,7 @@ static DeviceAux *device_aux(cudaStream_t stream) {
     cudaEventCreateWithFlags(&a.raster_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&a.fills_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&a.bwd_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&a.count_done, cudaEventDisableTiming);
     if (cudaHostAlloc((void **)&a.host_words, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
   }
   return &a;
@@ -154,9 +156,24 @@ static int wait_mapped_word(volatile int32_t *word, cudaStream_t stream, const c
   }
 }
 
+// GS_COUNT_BESIDE_SORT=0: tile count after the depth sort on the caller's stream (A/B switch)
+static bool count_beside_sort() {
+  static const bool on = [] { const char *e = getenv("GS_COUNT_BESIDE_SORT"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 static bool use_mapped_words() {
   static const bool on = [] { const char *e = getenv("GS_MAPPED_COUNTS"); return e == nullptr || e[0] != '0'; }();
   return on;
+}
+
+// The tile count does not need the depth order, only the scan of its results does: the two-level ordering runs it on
+// the auxiliary stream beside the four small radix passes of the depth sort (one wave of CTAs each, 2 us apart), with
+// counts and hit records at the Gaussians' own indices; scan and key emission then read them through the order.
+// A function of the arguments and the process-wide switches only, so stage A and stage B of a frame agree.
+static bool hits_by_point(const gs_render_args *a) {
+  return a->ordering != GS_ORDERING_BINNED && a->hits != nullptr && gs::use_side_stream() && count_beside_sort() &&
+         use_mapped_words();
 }
 
 static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_out, int64_t *max_per_tile_out,
@@ -187,9 +204,21 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
   }
   *v_out = v;
 
-  // ---- auxiliary stream: features, zero fills, raster digest (none of it feeds the mapper) ----
+  // ---- auxiliary stream: [tile count,] features, zero fills, raster digest ----
+  const int ts = c.tile_size;
+  const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
   GS_CUDA(cudaEventRecord(aux->fence, stream));
   GS_CUDA(cudaStreamWaitEvent(side, aux->fence, 0));
+  const bool by_point = hits_by_point(a);
+  if (by_point) {
+    GS_TRY(gs_tile_count_ordered_hits(a->points, nullptr, v, w_pad, h_pad, ts, c.alpha_threshold, a->tile_lo, a->tile_hi,
+                                      a->counts, a->hits, side));
+    GS_CUDA(cudaEventRecord(aux->count_done, side));
+  }
+  // the depth sort is enqueued before the bulk of the auxiliary work: its small kernels are then dispatched ahead of
+  // the machine-filling feature / digest kernels instead of queueing behind them
+  if (a->ordering != GS_ORDERING_BINNED)
+    GS_TRY(gs_depth_order(a->ndc, v, a->use_depth16, a->order, a->ws_order, a->ws_order_bytes, stream));
   if (a->use_sh) {
     GS_TRY(gs_sh_fwd_f32(a->feature, a->position, a->indexes, a->camera_pos, v, a->channels, a->sh_degree,
                          a->features, side));
@@ -205,8 +234,6 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
                               a->digest, side));
   GS_CUDA(cudaEventRecord(aux->side_done, side));
 
-  const int ts = c.tile_size;
-  const int w_pad = pad_to(a->width, ts), h_pad = pad_to(a->height, ts);
   if (a->ordering == GS_ORDERING_BINNED) {
     // ---- tile mapper, first half (binned ordering): per-tile counts -> tile ranges / slot cursors -> K ----
     const int64_t num_tiles = (int64_t)(w_pad / ts) * (h_pad / ts);
@@ -219,9 +246,10 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
     return GS_OK;
   }
   GS_CHECK_ARG((a->tile_lo == 0 && a->tile_hi == 0) || a->hits != nullptr, "render_stage_a: a tile range needs the hit-record buffer");
-  // ---- tile mapper, first half (two-level ordering): depth order -> counts -> scan -> K ----
-  GS_TRY(gs_depth_order(a->ndc, v, a->use_depth16, a->order, a->ws_order, a->ws_order_bytes, stream));
-  if (a->hits != nullptr)   // count and emit share one grid query through per-Gaussian hit records
+  // ---- tile mapper, first half (two-level ordering): depth order (enqueued above) -> counts -> scan -> K ----
+  if (by_point)
+    GS_CUDA(cudaStreamWaitEvent(stream, aux->count_done, 0));
+  else if (a->hits != nullptr)   // count and emit share one grid query through per-Gaussian hit records
     GS_TRY(gs_tile_count_ordered_hits(a->points, a->order, v, w_pad, h_pad, ts, c.alpha_threshold, a->tile_lo, a->tile_hi,
                                       a->counts, a->hits, stream));
   else
@@ -229,7 +257,8 @@ static int gs::stage_a_impl(const gs_render_args *a, int64_t *v_out, int64_t *k_
   if (mapped) {
     int64_t k = 0;
     aux->host_words[1] = kWordPending;
-    GS_TRY(tile_scan_mapped(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[1], stream));
+    GS_TRY(tile_scan_mapped(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[1], stream,
+                            by_point ? a->order : nullptr));
     GS_TRY(wait_mapped_word(&aux->host_words[1], stream, "render_stage_a (K)", &k));
     *k_out = v > 0 ? k : 0;
     return GS_OK;
@@ -285,7 +314,10 @@ static int gs::stage_b_impl(const gs_render_args *a, int64_t v, int64_t k, int64
       GS_TRY(gs_tile_scan(a->counts, v, a->cum, a->ws_scan, a->ws_scan_bytes, &aux->host_words[4], stream));
     }
     if (k > 0) {
-      if (a->hits != nullptr && !binned)
+      if (hits_by_point(a))
+        GS_TRY(tile_emit_hits_by_point(a->points, a->order, a->cum, a->hits, v, w_pad, h_pad, ts, c.alpha_threshold,
+                                       a->tile_lo, a->tile_hi, tiles, o2p, stream));
+      else if (a->hits != nullptr && !binned)
         GS_TRY(gs_tile_emit_hits(a->points, a->order, a->cum, a->hits, v, w_pad, h_pad, ts, c.alpha_threshold, a->tile_lo,
                                  a->tile_hi, tiles, o2p, stream));
       else
