@@ -183,9 +183,10 @@ OWN_KERNELS = {
     "gs_tile_bin_sort": 1, "gs_raster_fwd_f32": 3, "gs_raster_fwd_f64": 1, "gs_raster_fwd_median_f32": 3, "gs_raster_bwd_f32": 3,
     "gs_raster_bwd_f64": 1, "gs_raster_digest_f32": 1, "gs_raster_fwd_digest_f32": 2, "gs_raster_bwd_digest_f32": 2, "gs_raster_bwd_digest_strided_f32": 2,
     "gs_raster_pack_f32": 1, "gs_raster_pack_sorted_f32": 1, "gs_raster_fwd_packed_f32": 1, "gs_raster_bwd_packed_f32": 1,
-    # whole-frame drivers: project+compact (our projection functor inside cub::DeviceSelect), camera position, SH, digest,
-    # depth key, count, scan tail | emit, pack (+ ranges), raster forward | raster backward, projection backward, SH backward
-    "gs_render_stage_a_f32": 7, "gs_render_stage_b_f32": 3, "gs_render_backward_f32": 3, "gs_render_forward_f32": 7,
+    # whole-frame drivers: project+compact (our projection functor inside cub::DeviceSelect), V publish, camera position,
+    # SH, digest, depth key, count, scan tail (+ K publish) | emit, pack (+ ranges), raster forward | raster backward,
+    # projection backward, SH backward
+    "gs_render_stage_a_f32": 8, "gs_render_stage_b_f32": 3, "gs_render_backward_f32": 3, "gs_render_forward_f32": 8,
     "gs_optim_step_f32": 1, "gs_optim_update_visibility_f32": 1, "gs_morton_codes64": 1,
 }
 
