@@ -21,9 +21,11 @@ int project_compact_f32_mapped(const float *position, const float *log_scaling, 
                                int32_t height, double near_plane, double far_plane, double blur_cov, double clamp_margin,
                                double alpha_threshold, void *workspace, size_t workspace_bytes, float *points,
                                float *depth, int64_t *indexes, float *ndc, int32_t *mapped_word, cudaStream_t stream);
-// order != NULL: the counts sit at the Gaussians' own indices and are scanned in depth order (counts[order[i]])
-int tile_scan_mapped(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
-                     int32_t *mapped_word, cudaStream_t stream, const int32_t *order = nullptr);
+// gs_tile_scan for the drivers.  word_is_mapped: the total is stored into the mapped word by the device (else copied
+// into it, valid after a stream synchronisation).  order != NULL: the counts sit at the Gaussians' own indices and
+// are scanned in depth order (counts[order[i]]).
+int tile_scan_word(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
+                   int32_t *word, bool word_is_mapped, const int32_t *order, cudaStream_t stream);
 // gs_tile_emit_hits with the hit records indexed by Gaussian instead of by depth rank
 int tile_emit_hits_by_point(const float *gaussians, const int32_t *order, const int32_t *cum, const void *hits,
                             int64_t v, int32_t w_pad, int32_t h_pad, int32_t ts, double alpha_threshold,

@@ -440,9 +440,9 @@ static int tile_scan_impl(const int32_t *counts, int64_t v, int32_t *cum, void *
   return GS_OK;
 }
 
-int tile_scan_mapped(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
-                     int32_t *mapped_word, cudaStream_t stream, const int32_t *order) {
-  return tile_scan_impl(counts, v, cum, workspace, workspace_bytes, mapped_word, stream, true, order);
+int tile_scan_word(const int32_t *counts, int64_t v, int32_t *cum, void *workspace, size_t workspace_bytes,
+                   int32_t *word, bool word_is_mapped, const int32_t *order, cudaStream_t stream) {
+  return tile_scan_impl(counts, v, cum, workspace, workspace_bytes, word, stream, word_is_mapped, order);
 }
 
 int tile_emit_hits_by_point(const float *gaussians, const int32_t *order, const int32_t *cum, const void *hits,

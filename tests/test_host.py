@@ -133,7 +133,7 @@ def test_bench_line_contract():
   byte model reproduces SURVEY 8d's worked figure for the bench workload (2.22 GB per frame)."""
   import importlib.util
   import json
-  line = json.loads(open(os.path.join(ROOT, "profiles", "r02", "r02t_bench.json")).read().strip().splitlines()[-1])
+  line = json.loads(open(os.path.join(ROOT, "profiles", "r02", "r02al_bench.json")).read().strip().splitlines()[-1])
   for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
     assert key in line, key
