@@ -77,9 +77,13 @@ def _launch(group: Group, algorithm: int, vector: bool, weight, indexes, total_w
   ptr = _lib.ptr
   mask_lr = group.mask_lr.to(torch.float32).contiguous().view(-1) if group.mask_lr is not None else None
   point_lr = group.point_lr.to(torch.float32).contiguous().view(-1) if group.point_lr is not None else None
-  _lib.call("gs_optim_step_f32", algorithm, int(vector), int(group.bias_correction), ptr(indexes.contiguous()),
-            ptr(weight.contiguous()), ptr(grad_scale.contiguous()) if grad_scale is not None else None, float(grad_smooth),
-            indexes.shape[0], group.param.shape[1], ptr(first), ptr(second), ptr(total_weight), ptr(grad.contiguous()),
+  # contiguous copies (if any) stay referenced until the launch has been enqueued: a pointer taken from an unnamed
+  # temporary would outlive its tensor
+  indexes_c, weight_c, grad_c = indexes.contiguous(), weight.contiguous(), grad.contiguous()
+  grad_scale_c = grad_scale.contiguous() if grad_scale is not None else None
+  _lib.call("gs_optim_step_f32", algorithm, int(vector), int(group.bias_correction), ptr(indexes_c),
+            ptr(weight_c), ptr(grad_scale_c), float(grad_smooth),
+            indexes.shape[0], group.param.shape[1], ptr(first), ptr(second), ptr(total_weight), ptr(grad_c),
             float(group.lr), float(group.betas[0]), float(group.betas[1]), float(group.eps), ptr(lr_step),
             ptr(param) if param is not None else None, float(group.clip) if group.clip is not None else 0.0,
             ptr(mask_lr), ptr(point_lr), _lib.stream_ptr(group.param.device))

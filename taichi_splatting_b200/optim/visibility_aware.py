@@ -26,7 +26,8 @@ def update_visibility(running_vis: torch.Tensor, visibility: torch.Tensor, index
   _lib.require_cuda(running_vis=running_vis, visibility=visibility, indexes=indexes, total_weight=total_weight)
   vis = visibility.to(torch.float32).contiguous()
   weight = torch.empty_like(vis)
-  _lib.call("gs_optim_update_visibility_f32", _lib.ptr(running_vis), _lib.ptr(vis), _lib.ptr(indexes.contiguous()),
+  indexes_c = indexes.contiguous()   # named: the pointer must not outlive a temporary copy
+  _lib.call("gs_optim_update_visibility_f32", _lib.ptr(running_vis), _lib.ptr(vis), _lib.ptr(indexes_c),
             _lib.ptr(total_weight), float(beta), float(eps), indexes.shape[0], _lib.ptr(weight),
             _lib.stream_ptr(running_vis.device))
   return weight

@@ -144,19 +144,20 @@ class _RasterFunction(torch.autograd.Function):
     grad_g = torch.zeros_like(g) if need_g else None
     grad_f = torch.zeros_like(f) if need_f else None
     if need_g or need_f or config.compute_point_heuristic:
+      grad_image_c = grad_image.contiguous()   # named: the pointer must not outlive a temporary copy
       cfg = _lib.raster_config_c(config)
       heur_ptr = _lib.ptr(ctx.heuristic) if config.compute_point_heuristic else None
       if ctx.packed is not None:
         _lib.call("gs_raster_bwd_packed_f32", _lib.ptr(ctx.packed[0]), _lib.ptr(ctx.packed[1]), _lib.ptr(ranges),
-                  _lib.ptr(o2p), _lib.ptr(image), _lib.ptr(grad_image.contiguous()), None, g.shape[0], o2p.shape[0], w,
+                  _lib.ptr(o2p), _lib.ptr(image), _lib.ptr(grad_image_c), None, g.shape[0], o2p.shape[0], w,
                   h, f.shape[1], cfg, _lib.ptr(grad_g), _lib.ptr(grad_f), heur_ptr, _lib.stream_ptr(g.device))
       elif tuned_supported(config, f.shape[1], g.dtype):
         _lib.call("gs_raster_bwd_digest_f32", _lib.ptr(digest), _lib.ptr(ranges), _lib.ptr(o2p), _lib.ptr(image),
-                  _lib.ptr(grad_image.contiguous()), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
+                  _lib.ptr(grad_image_c), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
                   _lib.ptr(grad_g), _lib.ptr(grad_f), heur_ptr, _lib.stream_ptr(g.device))
       else:
         _lib.call(f"gs_raster_bwd_{sfx}", _lib.ptr(g), _lib.ptr(f), _lib.ptr(ranges), _lib.ptr(o2p), _lib.ptr(image),
-                  _lib.ptr(grad_image.contiguous()), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
+                  _lib.ptr(grad_image_c), g.shape[0], o2p.shape[0], w, h, f.shape[1], cfg,
                   _lib.ptr(grad_g), _lib.ptr(grad_f), heur_ptr, _lib.stream_ptr(g.device))
     return grad_g, grad_f, None, None, None, None, None
 

@@ -312,6 +312,7 @@ class _RenderFunction(torch.autograd.Function):
     # permuted CHW tensor, ...): no .contiguous() copy of a full image
     strided = d_image is not None and not d_image.is_contiguous()
     d_image_strides = (_lib.c_int64 * 3)(*(d_image.stride() if strided else (0, 0, 0)))
+    d_depths_c = d_depths.contiguous() if d_depths is not None else None   # named: outlives the launches below
     args = _lib.RenderBwdArgsC(
         ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(feature), ptr(T_camera_world), ptr(projection),
         n, v, k, w, h, blur, margin, int(use_sh), check_sh_degree(feature) if use_sh else 0, F, int(strided),
@@ -319,7 +320,7 @@ class _RenderFunction(torch.autograd.Function):
         ptr(indexes), ptr(features), ptr(image), ptr(cam_pos), ptr(digest), ptr(overlap_to_point), ptr(ranges),
         ptr(ctx.packed[0]), ptr(ctx.packed[1]),
         (d_image.data_ptr() if strided else ptr(d_image)) if d_image is not None else None,
-        ptr(d_depths.contiguous()) if d_depths is not None else None,
+        ptr(d_depths_c),
         ptr(grad_g), ptr(grad_f), int(d_g2d is not None), int(d_features is not None and grad_f is not None),
         ptr(heuristic) if config.compute_point_heuristic else None,
         *[ptr(g) for g in grads], ptr(d_feature),
@@ -365,6 +366,7 @@ class _RenderFunction(torch.autograd.Function):
     ev_bwd = _next_event_pair("bwd")
     strided = d_image is not None and not d_image.is_contiguous()
     d_image_strides = (_lib.c_int64 * 3)(*(d_image.stride() if strided else (0, 0, 0)))
+    d_depths_c = d_depths.contiguous() if d_depths is not None else None   # named: outlives the launches below
     args = _lib.RenderBwdArgsC(
         ptr(position), ptr(log_scaling), ptr(rotation), ptr(alpha_logit), ptr(feature), ptr(T_camera_world), ptr(projection),
         n, v, k, w, h, blur, margin, int(use_sh), check_sh_degree(feature), F, int(strided),
@@ -372,7 +374,7 @@ class _RenderFunction(torch.autograd.Function):
         ptr(indexes), ptr(features), ptr(image), ptr(cam_pos), ptr(digest), ptr(overlap_to_point), ptr(ranges),
         ptr(ctx.packed[0]), ptr(ctx.packed[1]),
         (d_image.data_ptr() if strided else ptr(d_image)) if d_image is not None else None,
-        ptr(d_depths.contiguous()) if d_depths is not None else None,
+        ptr(d_depths_c),
         ptr(grad_g), ptr(grad_f), int(d_g2d is not None), int(d_features is not None),
         ptr(heuristic) if config.compute_point_heuristic else None,
         *[ptr(g) for g in geom], ptr(d_T), ptr(d_proj), None,
@@ -439,19 +441,20 @@ class _RenderFunction(torch.autograd.Function):
     grad_g = d_g2d.clone() if d_g2d is not None else torch.zeros_like(g2d)
     grad_f = d_features.clone() if d_features is not None else torch.zeros_like(features)
     if d_image is not None and v > 0:
+      d_image_c = d_image.contiguous()   # named: the pointer must not outlive a temporary copy
       out_ptrs = (ptr(grad_g) if need_geom else None, ptr(grad_f) if need[4] else None,
                   ptr(heuristic) if config.compute_point_heuristic else None)
       if getattr(ctx, "packed", None) is not None:
         call("gs_raster_bwd_packed_f32", ptr(ctx.packed[0]), ptr(ctx.packed[1]), ptr(ranges), ptr(overlap_to_point),
-             ptr(image), ptr(d_image.contiguous()), None, v, overlap_to_point.shape[0], w, h, F,
+             ptr(image), ptr(d_image_c), None, v, overlap_to_point.shape[0], w, h, F,
              _lib.raster_config_c(config), *out_ptrs, stream)
       elif digest.shape[0] == v:
         call("gs_raster_bwd_digest_f32", ptr(digest), ptr(ranges), ptr(overlap_to_point), ptr(image),
-             ptr(d_image.contiguous()), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
+             ptr(d_image_c), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
              *out_ptrs, stream)
       else:
         call(f"gs_raster_bwd_{sfx}", ptr(g2d), ptr(features), ptr(ranges), ptr(overlap_to_point), ptr(image),
-             ptr(d_image.contiguous()), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
+             ptr(d_image_c), v, overlap_to_point.shape[0], w, h, F, _lib.raster_config_c(config),
              *out_ptrs, stream)
 
     # ---- features: SH backward; view-parallel runs launch the exchange of the SH-gradient factors instead, so that

@@ -45,8 +45,9 @@ class _ShFunction(torch.autograd.Function):
     d_points = torch.zeros_like(points) if need[1] else None
     d_cam = torch.zeros_like(camera_pos) if need[3] else None
     if (need[0] or need[1] or need[3]) and indexes.shape[0] > 0:
+      doutput_c = doutput.contiguous()   # named: the pointer must not outlive a temporary copy
       _lib.call(f"gs_sh_bwd_{sfx}", _lib.ptr(params), _lib.ptr(points), _lib.ptr(indexes), _lib.ptr(camera_pos),
-                _lib.ptr(doutput.contiguous()), _lib.ptr(out), indexes.shape[0], params.shape[1], ctx.degree, int(ctx.unique),
+                _lib.ptr(doutput_c), _lib.ptr(out), indexes.shape[0], params.shape[1], ctx.degree, int(ctx.unique),
                 _lib.ptr(d_params), _lib.ptr(d_points), _lib.ptr(d_cam), _lib.stream_ptr(params.device))
     return d_params, d_points, None, d_cam, None
 
