@@ -12,7 +12,13 @@
  *    frees caller-visible memory: outputs and workspaces are caller-owned (CUB-style size query);
  *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
  *    the device; the only host-visible results (V, K) are written asynchronously into pinned
- *    host words the caller reads after synchronising that stream;
+ *    host words the caller reads after synchronising that stream (the whole-frame drivers
+ *    gs_render_* return V and K themselves and wait for them internally);
+ *  - lifetime: every buffer passed to a call must stay allocated until the work enqueued by that
+ *    call has run -- the calls return before the device has touched anything.  A binding must not
+ *    take the address of a temporary (in Python: `ptr(x.contiguous())` frees the copy as soon as
+ *    `ptr` returns); buffers may be released in stream order (a stream-ordered allocator such as
+ *    torch's caching allocator on that stream is sufficient);
  *  - every function returns 0 on success or a negative GS_ERR_* code; gs_last_error_string()
  *    gives the thread-local message (reference convention: Python assert / RuntimeError,
  *    mapper/tile_mapper.py:177-178, cuda_lib/radix_sort_pairs.cu:66);

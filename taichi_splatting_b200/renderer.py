@@ -166,8 +166,9 @@ class _RenderFunction(torch.autograd.Function):
         dcfg = _lib.raster_config_c(replace(config, use_alpha_blending=False, saturate_threshold=config.median_threshold,
                                             compute_visibility=False, compute_point_heuristic=False))
         median3 = torch.empty((h, w, 1), dtype=dtype, device=device)
+        median_alpha = torch.empty((h, w), dtype=dtype, device=device)   # written, not used; named so it outlives the launch
         call(f"gs_raster_fwd_{sfx}", ptr(g2d), ptr(depths), ptr(ranges), ptr(overlap_to_point), v, k, w, h, 1, dcfg,
-             ptr(median3), ptr(torch.empty((h, w), dtype=dtype, device=device)), None, stream)
+             ptr(median3), ptr(median_alpha), None, stream)
         median = median3.squeeze(-1)
 
     ctx.save_for_backward(*tensors, feature_c, indexes, g2d, features, image, overlap_to_point, ranges,

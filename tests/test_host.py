@@ -153,3 +153,44 @@ def test_bench_line_contract():
   # the bench's image.sum() loss hands the backward an expanded scalar instead of a dense (H,W,3) gradient: 4PF fewer bytes
   _, total_sum = bench.algorithmic_bytes(1_000_000, 1_000_000, 3_838_201, 2048 * 2048, 16384, 3, 16)
   assert total - total_sum == 4 * 2048 * 2048 * 3
+
+
+def test_no_pointer_is_taken_from_a_temporary():
+  """`_lib.ptr(x.contiguous())` hands the library the address of an unnamed tensor that CPython frees as soon as `ptr`
+  returns -- before the launch (found by initcheck without the caching allocator, profiles/r02/r02an_initcheck.log).
+  Static check over the package: the argument of every `ptr(...)` / `.data_ptr()` is a name, an attribute or a
+  subscript of one, never the result of a call."""
+  import ast
+  import pathlib
+  pkg = pathlib.Path(ROOT) / "taichi_splatting_b200"
+
+  def is_stable(node):   # a name, attribute chain or subscript of one keeps its tensor alive; a call result does not
+    if isinstance(node, ast.Name):
+      return True
+    if isinstance(node, ast.Attribute):
+      return is_stable(node.value)
+    if isinstance(node, ast.Subscript):
+      return is_stable(node.value)
+    if isinstance(node, ast.Constant):
+      return True
+    return False
+
+  offenders = []
+  for path in sorted(pkg.rglob("*.py")):
+    tree = ast.parse(path.read_text())
+    for node in ast.walk(tree):
+      if not isinstance(node, ast.Call):
+        continue
+      f = node.func
+      name = f.id if isinstance(f, ast.Name) else f.attr if isinstance(f, ast.Attribute) else None
+      if name == "ptr" and node.args and not is_stable(node.args[0]):
+        if isinstance(node.args[0], ast.IfExp):   # `ptr(a if c else b)` of stable operands is fine
+          if all(is_stable(x) for x in (node.args[0].body, node.args[0].orelse)):
+            continue
+        offenders.append(f"{path.relative_to(ROOT)}:{node.lineno}")
+      if name == "data_ptr" and isinstance(f, ast.Attribute) and not is_stable(f.value):
+        v = f.value   # `x.untyped_storage().data_ptr()` only compares addresses (parallel.py: adjacency of gradients)
+        if isinstance(v, ast.Call) and isinstance(v.func, ast.Attribute) and v.func.attr == "untyped_storage" and is_stable(v.func.value):
+          continue
+        offenders.append(f"{path.relative_to(ROOT)}:{node.lineno}")
+  assert not offenders, offenders
